@@ -1,0 +1,173 @@
+/*
+ * include/audiosync_cuda.h -- C ABI of libaudiosync_cuda.so
+ *
+ * B200 (sm_100a) replacement for ONE translation unit of vidify/old-audiosync:
+ * src/cross_correlation.c.  Plain C types only; no torch / CUDA types in any
+ * signature (streams and device pointers travel as void*).
+ *
+ * Part 1 re-exports, unchanged, the two functions the reference declares in
+ * include/audiosync/cross_correlation.h:10-11 and :24-25, so the reference's
+ * src/audiosync.c (interval loop, :226-259) and src/bind.c link against this
+ * library instead of cross_correlation.c + -lfftw3 with no source change.
+ * Part 2 supplies the FFTW-named allocators src/audiosync.c:189,277 calls.
+ * Part 3 is new surface: a reusable context and a batched entry point that
+ * takes many (source, sample) pairs at once, on host or device memory, and
+ * shards them over the GPUs of one box.
+ *
+ * There is no CPU fallback: every entry point that computes fails (returns
+ * -1 / NaN and prints one "audiosync: ..." line on stderr) when no CUDA
+ * device or no sm_100 kernel image is available.
+ */
+#ifndef AUDIOSYNC_CUDA_H
+#define AUDIOSYNC_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------
+ * Part 1 -- drop-in for reference src/cross_correlation.c
+ * ------------------------------------------------------------------------ */
+
+/* Replaces reference src/cross_correlation.c:133-307
+ * (decl include/audiosync/cross_correlation.h:24-25).
+ *
+ * source[0 .. 2*sample_len), input_sample[0 .. sample_len): caller-owned host
+ * doubles, never modified; exactly those prefixes are snapshotted to the GPU
+ * at call time (the reference's reader threads keep appending behind them).
+ * Computes r = c2r(r2c(source) * conj(r2c(zero-padded sample))) (length
+ * 2*sample_len, unnormalised), idx = the reference's max_abs_index(r)
+ * (:52-67: signed r[0] seed, strict >, first index wins), folds idx into a
+ * signed lag (:256-271) and evaluates the Pearson coefficient of the aligned
+ * windows of the ORIGINAL double inputs (:74-116, :272-273).
+ *
+ * Returns 0 on success; -1 if the coefficient is NaN (outputs already
+ * written: *lag folded, *coefficient NaN -- :276) or on any CUDA/allocation
+ * failure (outputs untouched, one stderr line).  Prints the reference's
+ * "%ld frames of delay with a confidence of %f" line (:278) when the
+ * reference's global_debug (or audiosync_cuda_set_debug) is on.
+ * Thread-safe; concurrent callers are serialised on the default context. */
+int cross_correlation(double *source, double *input_sample,
+                      const size_t sample_len, long *lag, double *coefficient);
+
+/* Replaces reference src/cross_correlation.c:74-116
+ * (decl include/audiosync/cross_correlation.h:10-11).  Pointer ranges of equal
+ * length on the host; computed on the GPU in fp64.  Identical windows give
+ * exactly 1.0, a zero-variance window gives NaN, as the reference's
+ * tests/test_pearson_coefficient.c asserts.  NaN on CUDA failure. */
+double pearson_coefficient(double *source_start, const double *source_end,
+                           double *sample_start, const double *sample_end);
+
+/* ------------------------------------------------------------------------
+ * Part 2 -- allocators with FFTW's names (reference src/audiosync.c:189,277
+ * calls fftw_alloc_real / fftw_free for the 2,880,000-double source buffer).
+ * Memory is page-locked host memory when a CUDA device is present (so the
+ * per-interval upload is a straight DMA), otherwise 64-byte aligned malloc.
+ * ------------------------------------------------------------------------ */
+void   *fftw_malloc(size_t n_bytes);
+double *fftw_alloc_real(size_t n);
+void   *fftw_alloc_complex(size_t n);        /* n * 2 doubles */
+void    fftw_free(void *p);
+
+/* ------------------------------------------------------------------------
+ * Part 3 -- batched / multi-GPU surface (new; not in the reference)
+ * ------------------------------------------------------------------------ */
+
+typedef struct audiosync_cuda_ctx audiosync_cuda_ctx;
+
+enum { AUDIOSYNC_CUDA_F32 = 0, AUDIOSYNC_CUDA_F64 = 1 };
+enum { AUDIOSYNC_CUDA_HOST = 0, AUDIOSYNC_CUDA_DEVICE = 1 };
+
+/* Which transform path a given sample_len takes. */
+enum {
+    AUDIOSYNC_CUDA_PATH_AUTO   = 0,
+    AUDIOSYNC_CUDA_PATH_FFT    = 1,  /* 2/3/5-smooth even lengths: Stockham/four-step FFT  */
+    AUDIOSYNC_CUDA_PATH_DIRECT = 2   /* any length: O(L^2) time-domain correlation, fp64   */
+};
+
+/* One record per pair, 40 bytes, identical on host and device. */
+typedef struct audiosync_cuda_result {
+    int64_t lag;        /* folded lag in frames, [-L, L-1]  (cross_correlation.c:256-271)  */
+    double  coef;       /* Pearson coefficient or NaN                                      */
+    double  peak;       /* r[raw_index], unnormalised (x N) like FFTW's c2r                */
+    int32_t ret;        /* 0 / -1 exactly as cross_correlation() would return              */
+    int32_t success;    /* ret == 0 && coef >= 0.95   (src/audiosync.c:254)                */
+    int64_t raw_index;  /* argmax index before folding, [0, 2L)                            */
+} audiosync_cuda_result;
+
+/* devices == NULL or n_devices <= 0: use every visible device.
+ * Returns 0 and a context, or -1 (no device, no kernel image, out of memory). */
+int  audiosync_cuda_create(audiosync_cuda_ctx **ctx, const int *devices, int n_devices);
+void audiosync_cuda_destroy(audiosync_cuda_ctx *ctx);
+int  audiosync_cuda_device_count(const audiosync_cuda_ctx *ctx);
+
+/* Host-facing batch call.  sources: [n_pairs][2*sample_len], samples:
+ * [n_pairs][sample_len], both contiguous, of `dtype`, in `memspace`.
+ *   HOST   : pairs are split in contiguous blocks over the context's devices
+ *            (one host thread + one stream per device, chunked and double
+ *            buffered so uploads overlap the kernels); pinned buffers are
+ *            used in place, pageable ones are staged.
+ *   DEVICE : all pointers live on one device of the context; no copies.
+ * Outputs are host arrays of n_pairs entries; any of lags/coefs/rets/peaks may
+ * be NULL.  Returns 0 if every pair was evaluated (per-pair NaN outcomes are
+ * reported in rets[], not here), -1 on CUDA failure. */
+int audiosync_cuda_xcorr_batch(audiosync_cuda_ctx *ctx,
+                               const void *sources, const void *samples,
+                               size_t n_pairs, size_t sample_len,
+                               int dtype, int memspace,
+                               long *lags, double *coefs, int *rets, double *peaks);
+
+/* Stream-ordered device call: enqueues every kernel for n_pairs device-resident
+ * pairs on `stream` (a cudaStream_t passed as void*, NULL = the context's own
+ * stream for that device) and returns without synchronising.  d_results is a
+ * device array of n_pairs audiosync_cuda_result.  `device` is a CUDA ordinal
+ * that belongs to the context. */
+int audiosync_cuda_xcorr_batch_device(audiosync_cuda_ctx *ctx, int device,
+                                      const void *d_sources, const void *d_samples,
+                                      size_t n_pairs, size_t sample_len, int dtype,
+                                      audiosync_cuda_result *d_results, void *stream);
+
+/* Seeded all-integer synthetic pairs written straight into device memory
+ * (same generator as oracle/xcorr_oracle.c: bit-identical values).  Pair ids
+ * first_pair .. first_pair+n_pairs-1; stream-ordered like the call above. */
+int audiosync_cuda_synth_pairs(audiosync_cuda_ctx *ctx, int device, uint64_t seed,
+                               uint64_t first_pair, size_t n_pairs, size_t sample_len,
+                               int dtype, void *d_sources, void *d_samples, void *stream);
+
+/* Blocks until everything enqueued by this context on `device` is done. */
+int audiosync_cuda_synchronize(audiosync_cuda_ctx *ctx, int device);
+
+/* Tuning / test knobs (default behaviour matches the reference's). */
+int  audiosync_cuda_set_path(audiosync_cuda_ctx *ctx, int path);          /* AUTO / FFT / DIRECT */
+int  audiosync_cuda_set_wave_pairs(audiosync_cuda_ctx *ctx, int pairs);   /* pairs per kernel wave, 0 = auto */
+void audiosync_cuda_set_debug(int on);                                    /* same effect as global_debug */
+
+/* Describes the plan for a length, e.g.
+ * "fft L=1440000 M1=600 M2=2400 col=6x10x10 row=8x10x30 static". Returns the
+ * number of characters written (excluding the NUL), -1 if buf is too small. */
+int audiosync_cuda_describe_plan(audiosync_cuda_ctx *ctx, size_t sample_len,
+                                 char *buf, size_t buf_len);
+
+/* Launch accounting: number of kernels this context has launched so far. */
+uint64_t audiosync_cuda_launch_count(const audiosync_cuda_ctx *ctx);
+
+/* Per-kernel device timing.  When enabled every launch is bracketed by CUDA
+ * events on its own stream; audiosync_cuda_profile_read() synchronises and
+ * returns, for kernel class `i`, its name, launch count and total device
+ * milliseconds since the last reset.  Returns the number of classes. */
+int audiosync_cuda_profile_enable(audiosync_cuda_ctx *ctx, int on);
+int audiosync_cuda_profile_reset(audiosync_cuda_ctx *ctx);
+int audiosync_cuda_profile_read(audiosync_cuda_ctx *ctx, int i, char *name, size_t name_len,
+                                uint64_t *launches, double *total_ms);
+
+/* Last error message of the calling thread ("" if none). */
+const char *audiosync_cuda_last_error(void);
+const char *audiosync_cuda_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOSYNC_CUDA_H */

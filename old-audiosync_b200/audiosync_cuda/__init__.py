@@ -1,0 +1,328 @@
+"""Host-side binding of ``libaudiosync_cuda.so`` (ctypes over the C ABI).
+
+This is the Python mirror of the reference's interface for its one hot path:
+``cross_correlation`` / ``pearson_coefficient`` keep the names, argument
+meaning and error behaviour of reference ``include/audiosync/cross_correlation.h``
+(:10-11, :24-25); ``interval_loop`` restates the caller side,
+``src/audiosync.c:226-259``, on top of it; ``Context`` exposes the new batched /
+multi-GPU surface of ``include/audiosync_cuda.h``.
+
+There is no CPU fallback here or in the library: importing works anywhere,
+but every call that computes raises ``AudiosyncCudaError`` when the shared
+object or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+__all__ = [
+    "AudiosyncCudaError", "lib", "lib_path", "cross_correlation", "pearson_coefficient",
+    "interval_loop", "Context", "RESULT_DTYPE", "MIN_CONFIDENCE", "SAMPLE_RATE",
+    "INTERV_SAMPLE", "frames_to_ms", "F32", "F64", "HOST", "DEVICE",
+    "PATH_AUTO", "PATH_FFT", "PATH_DIRECT", "EXPORTED_SYMBOLS",
+]
+
+F32, F64 = 0, 1
+HOST, DEVICE = 0, 1
+PATH_AUTO, PATH_FFT, PATH_DIRECT = 0, 1, 2
+
+MIN_CONFIDENCE = 0.95                                             # audiosync.h:24
+SAMPLE_RATE = 48000                                               # audiosync.h:14
+INTERV_SAMPLE = [s * SAMPLE_RATE for s in (3, 6, 10, 15, 20, 30)]  # src/audiosync.c:50-57
+
+# mirrors struct audiosync_cuda_result (40 bytes)
+RESULT_DTYPE = np.dtype([("lag", "<i8"), ("coef", "<f8"), ("peak", "<f8"),
+                         ("ret", "<i4"), ("success", "<i4"), ("raw_index", "<i8")])
+assert RESULT_DTYPE.itemsize == 40
+
+# every symbol include/audiosync_cuda.h declares
+EXPORTED_SYMBOLS = [
+    "cross_correlation", "pearson_coefficient",
+    "fftw_malloc", "fftw_alloc_real", "fftw_alloc_complex", "fftw_free",
+    "audiosync_cuda_create", "audiosync_cuda_destroy", "audiosync_cuda_device_count",
+    "audiosync_cuda_xcorr_batch", "audiosync_cuda_xcorr_batch_device",
+    "audiosync_cuda_synth_pairs", "audiosync_cuda_synchronize",
+    "audiosync_cuda_set_path", "audiosync_cuda_set_wave_pairs", "audiosync_cuda_set_debug",
+    "audiosync_cuda_describe_plan", "audiosync_cuda_launch_count",
+    "audiosync_cuda_profile_enable", "audiosync_cuda_profile_reset",
+    "audiosync_cuda_profile_read", "audiosync_cuda_last_error", "audiosync_cuda_version",
+]
+
+
+class AudiosyncCudaError(RuntimeError):
+    pass
+
+
+_PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB: Optional[C.CDLL] = None
+
+
+def lib_path() -> str:
+    return os.environ.get("AUDIOSYNC_CUDA_LIB", os.path.join(_PKG_DIR, "libaudiosync_cuda.so"))
+
+
+def lib() -> C.CDLL:
+    """Loads the shared object; raises (never falls back) if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise AudiosyncCudaError(
+            f"{path} not built: run `make -C old-audiosync_b200` or __graft_entry__.build(); "
+            "there is no CPU fallback")
+    L = C.CDLL(path)
+    vp, sz, i32, u64, dbl = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_double
+    L.cross_correlation.restype = i32
+    L.cross_correlation.argtypes = [vp, vp, sz, C.POINTER(C.c_long), C.POINTER(dbl)]
+    L.pearson_coefficient.restype = dbl
+    L.pearson_coefficient.argtypes = [vp, vp, vp, vp]
+    L.fftw_malloc.restype = vp
+    L.fftw_malloc.argtypes = [sz]
+    L.fftw_alloc_real.restype = vp
+    L.fftw_alloc_real.argtypes = [sz]
+    L.fftw_alloc_complex.restype = vp
+    L.fftw_alloc_complex.argtypes = [sz]
+    L.fftw_free.restype = None
+    L.fftw_free.argtypes = [vp]
+    L.audiosync_cuda_create.restype = i32
+    L.audiosync_cuda_create.argtypes = [C.POINTER(vp), C.POINTER(i32), i32]
+    L.audiosync_cuda_destroy.restype = None
+    L.audiosync_cuda_destroy.argtypes = [vp]
+    L.audiosync_cuda_device_count.restype = i32
+    L.audiosync_cuda_device_count.argtypes = [vp]
+    L.audiosync_cuda_xcorr_batch.restype = i32
+    L.audiosync_cuda_xcorr_batch.argtypes = [vp, vp, vp, sz, sz, i32, i32, vp, vp, vp, vp]
+    L.audiosync_cuda_xcorr_batch_device.restype = i32
+    L.audiosync_cuda_xcorr_batch_device.argtypes = [vp, i32, vp, vp, sz, sz, i32, vp, vp]
+    L.audiosync_cuda_synth_pairs.restype = i32
+    L.audiosync_cuda_synth_pairs.argtypes = [vp, i32, u64, u64, sz, sz, i32, vp, vp, vp]
+    L.audiosync_cuda_synchronize.restype = i32
+    L.audiosync_cuda_synchronize.argtypes = [vp, i32]
+    L.audiosync_cuda_set_path.restype = i32
+    L.audiosync_cuda_set_path.argtypes = [vp, i32]
+    L.audiosync_cuda_set_wave_pairs.restype = i32
+    L.audiosync_cuda_set_wave_pairs.argtypes = [vp, i32]
+    L.audiosync_cuda_set_debug.restype = None
+    L.audiosync_cuda_set_debug.argtypes = [i32]
+    L.audiosync_cuda_describe_plan.restype = i32
+    L.audiosync_cuda_describe_plan.argtypes = [vp, sz, C.c_char_p, sz]
+    L.audiosync_cuda_launch_count.restype = u64
+    L.audiosync_cuda_launch_count.argtypes = [vp]
+    L.audiosync_cuda_profile_enable.restype = i32
+    L.audiosync_cuda_profile_enable.argtypes = [vp, i32]
+    L.audiosync_cuda_profile_reset.restype = i32
+    L.audiosync_cuda_profile_reset.argtypes = [vp]
+    L.audiosync_cuda_profile_read.restype = i32
+    L.audiosync_cuda_profile_read.argtypes = [vp, i32, C.c_char_p, sz, C.POINTER(u64), C.POINTER(dbl)]
+    L.audiosync_cuda_last_error.restype = C.c_char_p
+    L.audiosync_cuda_version.restype = C.c_char_p
+    _LIB = L
+    return L
+
+
+def last_error() -> str:
+    return lib().audiosync_cuda_last_error().decode(errors="replace")
+
+
+def frames_to_ms(lag_frames: int) -> int:
+    """round(lag * 1000 / 48000), src/audiosync.c:255 with audiosync.h:21."""
+    import math
+    x = lag_frames * (1000.0 / SAMPLE_RATE)
+    return int(math.copysign(math.floor(abs(x) + 0.5), x))   # C round(): half away from zero
+
+
+# ----------------------------------------------------------- drop-in functions
+
+def cross_correlation(source: np.ndarray, sample: np.ndarray):
+    """``int cross_correlation(double*, double*, size_t, long*, double*)``.
+
+    Returns ``(ret, lag, coefficient)``.  ``source`` must hold at least
+    ``2 * len(sample)`` doubles; only that prefix is read.  ret == -1 with a NaN
+    coefficient means the reference's NaN gate fired (outputs are still valid);
+    ret == -1 with ``lag is None`` means the GPU call itself failed.
+    """
+    source = np.ascontiguousarray(source, dtype=np.float64)
+    sample = np.ascontiguousarray(sample, dtype=np.float64)
+    n = sample.shape[0]
+    if source.shape[0] < 2 * n:
+        raise ValueError("source must be at least twice as long as sample")
+    lag = C.c_long(-(2 ** 62))
+    coef = C.c_double(12345.0)
+    ret = lib().cross_correlation(source.ctypes.data, sample.ctypes.data, n, C.byref(lag), C.byref(coef))
+    if ret != 0 and lag.value == -(2 ** 62):
+        raise AudiosyncCudaError("cross_correlation failed: " + last_error())
+    return ret, lag.value, coef.value
+
+
+def pearson_coefficient(x: np.ndarray, y: np.ndarray) -> float:
+    """``double pearson_coefficient(start, end, start, end)`` on two equal-length windows."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    if x.shape != y.shape or x.ndim != 1:
+        raise ValueError("windows must be 1-D and of equal length")
+    n = x.shape[0]
+    return float(lib().pearson_coefficient(x.ctypes.data, x.ctypes.data + 8 * n,
+                                           y.ctypes.data, y.ctypes.data + 8 * n))
+
+
+def interval_loop(source: np.ndarray, sample: np.ndarray):
+    """The caller loop of reference src/audiosync.c:226-259 on complete buffers.
+
+    Calls the drop-in ``cross_correlation`` on the six interval prefixes, skips
+    failed intervals (:247-249), stops at the first ``coef >= 0.95`` (:254-258)
+    and converts that lag to milliseconds (:255).  Returns a dict with the
+    per-interval tuples and ``final_ret`` / ``final_lag`` as ``audiosync_run``
+    would report them (on failure the last frame lag, unconverted).
+    """
+    rets, lags, coefs, succ = [], [], [], []
+    final_ret, lag = -1, 0
+    for L in INTERV_SAMPLE:
+        ret, lag_i, coef = cross_correlation(source[:2 * L], sample[:L])
+        lag = lag_i
+        ok = ret == 0 and coef >= MIN_CONFIDENCE
+        rets.append(ret); lags.append(lag_i); coefs.append(coef); succ.append(int(ok))
+        if ret < 0:
+            continue
+        if ok:
+            lag = frames_to_ms(lag_i)
+            final_ret = 0
+            break
+    return dict(n=len(rets), rets=rets, lags=lags, coefs=coefs, succ=succ,
+                final_ret=final_ret, final_lag=lag)
+
+
+# -------------------------------------------------------------- batched surface
+
+class Context:
+    """``audiosync_cuda_ctx``: devices, streams, plans and workspaces."""
+
+    def __init__(self, devices: Optional[Sequence[int]] = None):
+        L = lib()
+        self._h = C.c_void_p()
+        if devices is None:
+            rc = L.audiosync_cuda_create(C.byref(self._h), None, 0)
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = L.audiosync_cuda_create(C.byref(self._h), arr, len(devices))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise AudiosyncCudaError("audiosync_cuda_create failed: " + last_error())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().audiosync_cuda_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise AudiosyncCudaError(f"{what} failed: {last_error()}")
+
+    def device_count(self) -> int:
+        return lib().audiosync_cuda_device_count(self._h)
+
+    def set_path(self, path: int):
+        self._check(lib().audiosync_cuda_set_path(self._h, path), "set_path")
+
+    def set_wave_pairs(self, pairs: int):
+        self._check(lib().audiosync_cuda_set_wave_pairs(self._h, pairs), "set_wave_pairs")
+
+    def describe_plan(self, sample_len: int) -> str:
+        buf = C.create_string_buffer(512)
+        n = lib().audiosync_cuda_describe_plan(self._h, sample_len, buf, 512)
+        if n < 0:
+            raise AudiosyncCudaError("describe_plan failed: " + last_error())
+        return buf.value.decode()
+
+    def launch_count(self) -> int:
+        return int(lib().audiosync_cuda_launch_count(self._h))
+
+    def synchronize(self, device: int = 0):
+        self._check(lib().audiosync_cuda_synchronize(self._h, device), "synchronize")
+
+    # -- host-facing batch call ------------------------------------------------
+    def xcorr_batch(self, sources: np.ndarray, samples: np.ndarray):
+        """sources [n][2L], samples [n][L], float32 or float64 host arrays.
+
+        Returns a dict of numpy arrays: lags (int64), coefs, rets (int32), peaks.
+        """
+        if sources.dtype != samples.dtype or sources.dtype not in (np.float32, np.float64):
+            raise TypeError("sources/samples must both be float32 or float64")
+        sources = np.ascontiguousarray(sources)
+        samples = np.ascontiguousarray(samples)
+        if sources.ndim != 2 or samples.ndim != 2 or sources.shape[0] != samples.shape[0] \
+                or sources.shape[1] != 2 * samples.shape[1]:
+            raise ValueError("expected sources [n][2L] and samples [n][L]")
+        n, L = samples.shape
+        lags = np.zeros(n, np.int64); coefs = np.zeros(n, np.float64)
+        rets = np.zeros(n, np.int32); peaks = np.zeros(n, np.float64)
+        dt = F32 if sources.dtype == np.float32 else F64
+        rc = lib().audiosync_cuda_xcorr_batch(self._h, sources.ctypes.data, samples.ctypes.data, n, L,
+                                              dt, HOST, lags.ctypes.data, coefs.ctypes.data,
+                                              rets.ctypes.data, peaks.ctypes.data)
+        self._check(rc, "xcorr_batch")
+        return dict(lags=lags, coefs=coefs, rets=rets, peaks=peaks)
+
+    def xcorr_batch_ptr(self, sources_ptr: int, samples_ptr: int, n_pairs: int, sample_len: int,
+                        dtype: int, memspace: int):
+        """Same call on raw pointers (pinned host buffers or device memory)."""
+        lags = np.zeros(n_pairs, np.int64); coefs = np.zeros(n_pairs, np.float64)
+        rets = np.zeros(n_pairs, np.int32); peaks = np.zeros(n_pairs, np.float64)
+        rc = lib().audiosync_cuda_xcorr_batch(self._h, sources_ptr, samples_ptr, n_pairs, sample_len,
+                                              dtype, memspace, lags.ctypes.data, coefs.ctypes.data,
+                                              rets.ctypes.data, peaks.ctypes.data)
+        self._check(rc, "xcorr_batch")
+        return dict(lags=lags, coefs=coefs, rets=rets, peaks=peaks)
+
+    # -- stream-ordered device calls --------------------------------------------
+    def xcorr_batch_device(self, device: int, d_sources: int, d_samples: int, n_pairs: int,
+                           sample_len: int, dtype: int, d_results: int, stream: int = 0):
+        rc = lib().audiosync_cuda_xcorr_batch_device(self._h, device, d_sources, d_samples, n_pairs,
+                                                     sample_len, dtype, d_results, stream or None)
+        self._check(rc, "xcorr_batch_device")
+
+    def synth_pairs(self, device: int, seed: int, first_pair: int, n_pairs: int, sample_len: int,
+                    dtype: int, d_sources: int, d_samples: int, stream: int = 0):
+        rc = lib().audiosync_cuda_synth_pairs(self._h, device, seed, first_pair, n_pairs, sample_len,
+                                              dtype, d_sources, d_samples, stream or None)
+        self._check(rc, "synth_pairs")
+
+    # -- per-kernel device timing -----------------------------------------------
+    def profile_enable(self, on: bool = True):
+        self._check(lib().audiosync_cuda_profile_enable(self._h, int(on)), "profile_enable")
+
+    def profile_reset(self):
+        self._check(lib().audiosync_cuda_profile_reset(self._h), "profile_reset")
+
+    def profile_read(self):
+        """{kernel class name: (launches, total device ms)} since the last reset."""
+        out = {}
+        name = C.create_string_buffer(64)
+        n = C.c_uint64(); ms = C.c_double()
+        count = lib().audiosync_cuda_profile_read(self._h, 0, name, 64, C.byref(n), C.byref(ms))
+        if count < 0:
+            raise AudiosyncCudaError("profile_read failed: " + last_error())
+        for i in range(count):
+            lib().audiosync_cuda_profile_read(self._h, i, name, 64, C.byref(n), C.byref(ms))
+            out[name.value.decode()] = (int(n.value), float(ms.value))
+        return out

@@ -1,0 +1,835 @@
+// audiosync_cuda.cu -- libaudiosync_cuda.so: context, wave scheduler,
+// multi-GPU dispatcher and the C ABI of include/audiosync_cuda.h.
+//
+// Product path only: nothing here (or anywhere in this library) calls the CPU
+// oracle, cuFFT, or any host-side arithmetic fallback.  If CUDA is missing or
+// a launch fails the entry points fail loudly (-1 / NaN + one stderr line).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <thread>
+
+#include "context.h"
+#include "fft_kernels.cuh"
+#include "fft_plan.h"
+#include "fft_small.cuh"
+#include "reduce_kernels.cuh"
+
+// The reference defines `volatile int global_debug` in src/audiosync.c:37 and its
+// LOG() macro (include/audiosync/audiosync.h:88-94) reads it.  When this library
+// is linked into the reference build the symbol resolves to that definition;
+// stand-alone (ctypes, tests) it is absent, hence weak.
+extern "C" {
+extern volatile int global_debug __attribute__((weak));
+}
+
+namespace asc {
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_last_error[512] = "";
+static int g_debug_flag = 0;
+
+void set_last_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+    fprintf(stderr, "audiosync: %s\n", g_last_error);
+}
+
+static bool debug_on() { return g_debug_flag || (&global_debug != nullptr && global_debug); }
+
+const char* kernel_class_name(int k) {
+    static const char* names[KC_COUNT] = {
+        "synth", "direct_corr", "argmax_f64", "peaks_reset", "col_fwd", "row_fused",
+        "col_inv_argmax", "small_fft", "pearson_partial", "pearson_final"};
+    return (k >= 0 && k < KC_COUNT) ? names[k] : "?";
+}
+
+// ----------------------------------------------------------------- buffers
+int DevBuf::ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+    size_t want = need + need / 8;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        cudaGetLastError();
+        want = need;
+        ASC_CUDA_OK(cudaMalloc(&p, want));
+    }
+    bytes = want;
+    return 0;
+}
+void DevBuf::release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+
+int PinnedBuf::ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) { cudaFreeHost(p); p = nullptr; bytes = 0; }
+    ASC_CUDA_OK(cudaMallocHost(&p, need));
+    bytes = need;
+    return 0;
+}
+void PinnedBuf::release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+
+// -------------------------------------------------------------------- plan
+struct FftPlan {
+    PathKind kind = PATH_DIRECT;
+    long long L = 0;
+    int M1 = 0, M2 = 0;
+    std::string desc;
+    size_t ws_bytes_per_pair = 0;
+    DevBuf col_tw, row_tw, m_lo, m_hi, n_lo, n_hi;   // static four-step
+    DevBuf wm, wn;                                   // short-length kernel
+    SmallPlan small;
+    // enqueues the transform kernels for `pairs` pairs (planes/r in ws)
+    std::function<int(audiosync_cuda_ctx*, DeviceState&, const void*, const void*, int, void*,
+                      PairPeak*, int, cudaStream_t)> run_wave;
+    ~FftPlan() {
+        col_tw.release(); row_tw.release(); m_lo.release(); m_hi.release();
+        n_lo.release(); n_hi.release(); wm.release(); wn.release();
+    }
+};
+
+static int upload(DevBuf& b, const std::vector<cplx>& v) {
+    if (b.ensure(v.size() * sizeof(cplx)) != 0) return -1;
+    ASC_CUDA_OK(cudaMemcpy(b.p, v.data(), v.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// ------------------------------------------------------------------ launch
+template <class F>
+static int launch(audiosync_cuda_ctx* ctx, DeviceState& d, int cls, cudaStream_t st, F&& fn) {
+    ProfileRecord rec{cls, nullptr, nullptr};
+    if (ctx->profile) {
+        for (cudaEvent_t* e : {&rec.e0, &rec.e1}) {
+            if (!d.event_pool.empty()) { *e = d.event_pool.back(); d.event_pool.pop_back(); }
+            else ASC_CUDA_OK(cudaEventCreate(e));
+        }
+        ASC_CUDA_OK(cudaEventRecord(rec.e0, st));
+    }
+    fn();
+    ASC_CUDA_OK(cudaGetLastError());
+    if (ctx->profile) {
+        ASC_CUDA_OK(cudaEventRecord(rec.e1, st));
+        d.prof_pending.push_back(rec);
+    }
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+template <class K>
+static int prepare_kernel(size_t smem) {
+    if (smem > 48 * 1024)
+        ASC_CUDA_OK(cudaFuncSetAttribute(fft_kernel_entry<K>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
+}
+
+template <class P>
+static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d,
+                           const void* src, const void* smp, int dtype, void* ws,
+                           PairPeak* peaks, int pairs, cudaStream_t st) {
+    using Col = typename P::Col;
+    using Row = typename P::Row;
+    constexpr int M1 = Col::n, M2 = Row::n;
+    cplx* planes = static_cast<cplx*>(ws);
+    const cplx* col_tw = static_cast<const cplx*>(plan->col_tw.p);
+    const cplx* row_tw = static_cast<const cplx*>(plan->row_tw.p);
+    const cplx* m_lo = static_cast<const cplx*>(plan->m_lo.p);
+    const cplx* m_hi = static_cast<const cplx*>(plan->m_hi.p);
+    const cplx* n_lo = static_cast<const cplx*>(plan->n_lo.p);
+    const cplx* n_hi = static_cast<const cplx*>(plan->n_hi.p);
+    const dim3 grid_a(M2 / COL_T, 2, pairs);
+    if (dtype == AUDIOSYNC_CUDA_F32) {
+        using K = ColFwdKernel<Col, P::NT_COL, float>;
+        typename K::Params p{static_cast<const float*>(src), static_cast<const float*>(smp), planes,
+                             col_tw, m_lo, m_hi, P::L, M2};
+        if (launch(ctx, d, KC_COL_FWD, st, [&] {
+                fft_kernel_entry<K><<<grid_a, K::THREADS, K::SMEM, st>>>(p);
+            }) != 0) return -1;
+    } else {
+        using K = ColFwdKernel<Col, P::NT_COL, double>;
+        typename K::Params p{static_cast<const double*>(src), static_cast<const double*>(smp), planes,
+                             col_tw, m_lo, m_hi, P::L, M2};
+        if (launch(ctx, d, KC_COL_FWD, st, [&] {
+                fft_kernel_entry<K><<<grid_a, K::THREADS, K::SMEM, st>>>(p);
+            }) != 0) return -1;
+    }
+    {
+        using K = RowFusedKernel<Row, P::NT_ROW>;
+        typename K::Params p{planes, row_tw, m_lo, m_hi, n_lo, n_hi, P::L, M1};
+        const dim3 grid(M1 / 2 + 1, 1, pairs);
+        if (launch(ctx, d, KC_ROW_FUSED, st, [&] {
+                fft_kernel_entry<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
+            }) != 0) return -1;
+    }
+    {
+        using K = ColInvKernel<Col, P::NT_COL>;
+        typename K::Params p{planes, peaks, col_tw, P::L, M2};
+        const dim3 grid(M2 / COL_T, 1, pairs);
+        if (launch(ctx, d, KC_COL_INV, st, [&] {
+                fft_kernel_entry<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
+            }) != 0) return -1;
+    }
+    return 0;
+}
+
+template <class P>
+static int build_static_plan(FftPlan* plan) {
+    using Col = typename P::Col;
+    using Row = typename P::Row;
+    plan->kind = PATH_STATIC_FFT;
+    plan->L = P::L;
+    plan->M1 = Col::n;
+    plan->M2 = Row::n;
+    plan->ws_bytes_per_pair = (size_t)2 * P::L * sizeof(cplx);
+    std::string d = "fft L=" + std::to_string(P::L) + " M1=" + std::to_string(Col::n) +
+                    " M2=" + std::to_string(Row::n) + " col=";
+    for (int i = 0; i < Col::count; i++) d += (i ? "x" : "") + std::to_string(Col::r(i));
+    d += " row=";
+    for (int i = 0; i < Row::count; i++) d += (i ? "x" : "") + std::to_string(Row::r(i));
+    d += " static four-step fp32";
+    plan->desc = d;
+    std::vector<cplx> m_lo, m_hi, n_lo, n_hi;
+    build_two_level(P::L, P::L - 1, m_lo, m_hi);
+    build_two_level(2 * P::L, P::L, n_lo, n_hi);
+    if (upload(plan->col_tw, build_pass_tables(radix_vector<Col>())) != 0 ||
+        upload(plan->row_tw, build_pass_tables(radix_vector<Row>())) != 0 ||
+        upload(plan->m_lo, m_lo) != 0 || upload(plan->m_hi, m_hi) != 0 ||
+        upload(plan->n_lo, n_lo) != 0 || upload(plan->n_hi, n_hi) != 0)
+        return -1;
+    if (prepare_kernel<ColFwdKernel<Col, P::NT_COL, float>>(ColFwdKernel<Col, P::NT_COL, float>::SMEM) != 0 ||
+        prepare_kernel<ColFwdKernel<Col, P::NT_COL, double>>(ColFwdKernel<Col, P::NT_COL, double>::SMEM) != 0 ||
+        prepare_kernel<RowFusedKernel<Row, P::NT_ROW>>(RowFusedKernel<Row, P::NT_ROW>::SMEM) != 0 ||
+        prepare_kernel<ColInvKernel<Col, P::NT_COL>>(ColInvKernel<Col, P::NT_COL>::SMEM) != 0)
+        return -1;
+    plan->run_wave = [plan](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
+                            int dtype, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
+        return run_static_wave<P>(plan, ctx, d, src, smp, dtype, ws, peaks, pairs, st);
+    };
+    return 0;
+}
+
+template <typename InT>
+static int run_small_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d, const void* src,
+                          const void* smp, PairPeak* peaks, int pairs, cudaStream_t st) {
+    using K = SmallXcorrKernel<InT>;
+    typename K::Params p{static_cast<const InT*>(src), static_cast<const InT*>(smp), peaks,
+                         static_cast<const cplx*>(plan->wm.p), static_cast<const cplx*>(plan->wn.p),
+                         plan->small};
+    const size_t smem = K::smem_bytes(plan->small.M);
+    const dim3 grid(1, 1, pairs);
+    return launch(ctx, d, KC_SMALL_FFT, st, [&] {
+        fft_kernel_entry<K><<<grid, K::THREADS, smem, st>>>(p);
+    });
+}
+
+static int build_small_plan(FftPlan* plan, long long L) {
+    plan->kind = PATH_SMALL_FFT;
+    plan->L = L;
+    if (!make_small_plan(L, &plan->small)) return -1;
+    plan->ws_bytes_per_pair = 0;
+    std::string d = "fft L=" + std::to_string(L) + " single-CTA radices=";
+    for (int i = 0; i < plan->small.npass; i++) d += (i ? "x" : "") + std::to_string(plan->small.radix[i]);
+    d += " fp32";
+    plan->desc = d;
+    if (upload(plan->wm, build_full_table(L, L)) != 0 || upload(plan->wn, build_full_table(2 * L, L)) != 0)
+        return -1;
+    const size_t smem = SmallXcorrKernel<float>::smem_bytes((int)L);
+    if (smem > 48 * 1024) {
+        ASC_CUDA_OK(cudaFuncSetAttribute(fft_kernel_entry<SmallXcorrKernel<float>>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SMALL_MAX_M * sizeof(cplx))));
+        ASC_CUDA_OK(cudaFuncSetAttribute(fft_kernel_entry<SmallXcorrKernel<double>>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SMALL_MAX_M * sizeof(cplx))));
+    }
+    plan->run_wave = [plan](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
+                            int dtype, void*, PairPeak* peaks, int pairs, cudaStream_t st) {
+        return dtype == AUDIOSYNC_CUDA_F32 ? run_small_wave<float>(plan, ctx, d, src, smp, peaks, pairs, st)
+                                           : run_small_wave<double>(plan, ctx, d, src, smp, peaks, pairs, st);
+    };
+    return 0;
+}
+
+template <typename InT>
+static int run_direct_wave(long long L, audiosync_cuda_ctx* ctx, DeviceState& d, const void* src,
+                           const void* smp, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
+    const long long N = 2 * L;
+    double* r = static_cast<double*>(ws);
+    const dim3 grid((unsigned)((N + DIRECT_TILE - 1) / DIRECT_TILE), pairs);
+    if (launch(ctx, d, KC_DIRECT, st, [&] {
+            direct_corr_kernel<InT><<<grid, DIRECT_TILE, 0, st>>>(static_cast<const InT*>(src),
+                                                                  static_cast<const InT*>(smp), r, L);
+        }) != 0) return -1;
+    return launch(ctx, d, KC_ARGMAX_F64, st, [&] {
+        argmax_f64_kernel<<<pairs, 1024, 0, st>>>(r, N, peaks);
+    });
+}
+
+static int build_direct_plan(FftPlan* plan, long long L) {
+    plan->kind = PATH_DIRECT;
+    plan->L = L;
+    plan->ws_bytes_per_pair = (size_t)2 * L * sizeof(double);
+    plan->desc = "direct L=" + std::to_string(L) + " time-domain O(L^2) fp64";
+    plan->run_wave = [L](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
+                         int dtype, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
+        return dtype == AUDIOSYNC_CUDA_F32 ? run_direct_wave<float>(L, ctx, d, src, smp, ws, peaks, pairs, st)
+                                           : run_direct_wave<double>(L, ctx, d, src, smp, ws, peaks, pairs, st);
+    };
+    return 0;
+}
+
+// plans are cached per device and per (L, forced path)
+static FftPlan* get_plan(audiosync_cuda_ctx* ctx, DeviceState& d, long long L) {
+    const size_t key = (size_t)L * 4 + (size_t)ctx->path;
+    auto it = d.plans.find(key);
+    if (it != d.plans.end()) return it->second.get();
+    auto plan = std::make_shared<FftPlan>();
+    const PathKind kind = choose_path(L, ctx->path);
+    int rc = -1;
+    if (kind == PATH_STATIC_FFT) {
+        for_each_static_plan([&](auto P) {
+            using PT = decltype(P);
+            if (PT::L == L) rc = build_static_plan<PT>(plan.get());
+        });
+    } else if (kind == PATH_SMALL_FFT) {
+        rc = build_small_plan(plan.get(), L);
+    } else {
+        rc = build_direct_plan(plan.get(), L);
+    }
+    if (rc != 0) return nullptr;
+    d.plans[key] = plan;
+    return plan.get();
+}
+
+static int default_wave_pairs(const FftPlan* plan, size_t n_pairs) {
+    long long w;
+    if (plan->kind == PATH_STATIC_FFT) {
+        w = (8LL * 1440000) / plan->L;
+        w = std::max(8LL, std::min(256LL, w));
+    } else if (plan->kind == PATH_SMALL_FFT) {
+        w = 16384;
+    } else {
+        const long long per = (long long)plan->ws_bytes_per_pair;
+        w = std::max(1LL, std::min(1024LL, (256LL << 20) / std::max(1LL, per)));
+    }
+    return (int)std::min<long long>(w, (long long)std::max<size_t>(n_pairs, 1));
+}
+
+// Enqueue the whole path for device-resident pairs on `st` (no sync).
+static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
+                         size_t n_pairs, long long L, int dtype, audiosync_cuda_result* d_results,
+                         cudaStream_t st) {
+    if (n_pairs == 0) return 0;
+    if (L <= 0 || L > (1LL << 30)) { set_last_error("unsupported sample_len %lld", L); return -1; }
+    ASC_CUDA_OK(cudaSetDevice(d.device));
+    FftPlan* plan = get_plan(ctx, d, L);
+    if (!plan) return -1;
+    const size_t esz = dtype == AUDIOSYNC_CUDA_F32 ? 4 : 8;
+    int wave = ctx->wave_pairs > 0 ? ctx->wave_pairs : default_wave_pairs(plan, n_pairs);
+    wave = (int)std::min<size_t>((size_t)wave, n_pairs);
+    wave = std::min(wave, 65535);
+    const int n_chunks = (int)((L + PEARSON_CHUNK - 1) / PEARSON_CHUNK);
+    if (d.ws.ensure(plan->ws_bytes_per_pair * (size_t)wave + 256) != 0) return -1;
+    if (d.peaks.ensure(sizeof(PairPeak) * (size_t)wave) != 0) return -1;
+    if (d.partials.ensure(sizeof(PearsonPartial) * (size_t)wave * n_chunks) != 0) return -1;
+    PairPeak* peaks = static_cast<PairPeak*>(d.peaks.p);
+    PearsonPartial* partials = static_cast<PearsonPartial*>(d.partials.p);
+    for (size_t p0 = 0; p0 < n_pairs; p0 += (size_t)wave) {
+        const int pairs = (int)std::min<size_t>((size_t)wave, n_pairs - p0);
+        const char* s = static_cast<const char*>(src) + p0 * (size_t)(2 * L) * esz;
+        const char* m = static_cast<const char*>(smp) + p0 * (size_t)L * esz;
+        if (launch(ctx, d, KC_PEAKS_RESET, st, [&] {
+                peaks_reset_kernel<<<(pairs + 127) / 128, 128, 0, st>>>(peaks, pairs);
+            }) != 0) return -1;
+        if (plan->run_wave(ctx, d, s, m, dtype, d.ws.p, peaks, pairs, st) != 0) return -1;
+        const dim3 grid(n_chunks, pairs);
+        int rc;
+        if (dtype == AUDIOSYNC_CUDA_F32) {
+            rc = launch(ctx, d, KC_PEARSON_PARTIAL, st, [&] {
+                pearson_partial_kernel<float><<<grid, PEARSON_THREADS, 0, st>>>(
+                    reinterpret_cast<const float*>(s), reinterpret_cast<const float*>(m), 2 * L, L, L,
+                    peaks, 0, partials, n_chunks);
+            });
+        } else {
+            rc = launch(ctx, d, KC_PEARSON_PARTIAL, st, [&] {
+                pearson_partial_kernel<double><<<grid, PEARSON_THREADS, 0, st>>>(
+                    reinterpret_cast<const double*>(s), reinterpret_cast<const double*>(m), 2 * L, L, L,
+                    peaks, 0, partials, n_chunks);
+            });
+        }
+        if (rc != 0) return -1;
+        if (launch(ctx, d, KC_PEARSON_FINAL, st, [&] {
+                pearson_final_kernel<<<pairs, 32, 0, st>>>(partials, n_chunks, L, peaks, 0, d_results + p0);
+            }) != 0) return -1;
+    }
+    return 0;
+}
+
+static int drain_profile(DeviceState& d) {
+    ASC_CUDA_OK(cudaSetDevice(d.device));
+    ASC_CUDA_OK(cudaDeviceSynchronize());
+    for (auto& r : d.prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+            d.prof_ms[r.cls] += ms;
+            d.prof_launches[r.cls] += 1;
+        }
+        d.event_pool.push_back(r.e0);
+        d.event_pool.push_back(r.e1);
+    }
+    d.prof_pending.clear();
+    return 0;
+}
+
+static void destroy_device_state(DeviceState& d) {
+    if (d.device < 0) return;
+    cudaSetDevice(d.device);
+    cudaDeviceSynchronize();
+    d.plans.clear();
+    d.ws.release(); d.peaks.release(); d.partials.release(); d.results.release();
+    for (int i = 0; i < 2; i++) {
+        d.in_src[i].release(); d.in_smp[i].release(); d.h_stage[i].release();
+        if (d.ev_up[i]) cudaEventDestroy(d.ev_up[i]);
+        if (d.ev_done[i]) cudaEventDestroy(d.ev_done[i]);
+    }
+    d.h_results.release();
+    for (auto& r : d.prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    for (auto e : d.event_pool) cudaEventDestroy(e);
+    if (d.stream) cudaStreamDestroy(d.stream);
+    if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+    d.device = -1;
+}
+
+// Host-memory pairs [p0, p1) on one device: chunked, double buffered.
+static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* sources,
+                          const char* samples, size_t p0, size_t p1, long long L, int dtype,
+                          audiosync_cuda_result* out) {
+    if (p1 <= p0) return 0;
+    ASC_CUDA_OK(cudaSetDevice(d.device));
+    const size_t esz = dtype == AUDIOSYNC_CUDA_F32 ? 4 : 8;
+    const size_t src_bytes = (size_t)(2 * L) * esz, smp_bytes = (size_t)L * esz;
+    // chunk: about 192 MB of input per buffer, at least one pair
+    size_t chunk = std::max<size_t>(1, (192u << 20) / (src_bytes + smp_bytes));
+    chunk = std::min(chunk, p1 - p0);
+    for (int b = 0; b < 2; b++) {
+        if (d.in_src[b].ensure(src_bytes * chunk) != 0 || d.in_smp[b].ensure(smp_bytes * chunk) != 0) return -1;
+        if (!d.ev_up[b]) ASC_CUDA_OK(cudaEventCreateWithFlags(&d.ev_up[b], cudaEventDisableTiming));
+        if (!d.ev_done[b]) ASC_CUDA_OK(cudaEventCreateWithFlags(&d.ev_done[b], cudaEventDisableTiming));
+    }
+    const size_t total = p1 - p0;
+    if (d.results.ensure(sizeof(audiosync_cuda_result) * total) != 0) return -1;
+    if (d.h_results.ensure(sizeof(audiosync_cuda_result) * total) != 0) return -1;
+    audiosync_cuda_result* d_res = static_cast<audiosync_cuda_result*>(d.results.p);
+    int it = 0;
+    for (size_t c0 = 0; c0 < total; c0 += chunk, it++) {
+        const size_t n = std::min(chunk, total - c0);
+        const int b = it & 1;
+        if (it >= 2) ASC_CUDA_OK(cudaStreamWaitEvent(d.copy_stream, d.ev_done[b], 0));
+        ASC_CUDA_OK(cudaMemcpyAsync(d.in_src[b].p, sources + (p0 + c0) * src_bytes, src_bytes * n,
+                                    cudaMemcpyHostToDevice, d.copy_stream));
+        ASC_CUDA_OK(cudaMemcpyAsync(d.in_smp[b].p, samples + (p0 + c0) * smp_bytes, smp_bytes * n,
+                                    cudaMemcpyHostToDevice, d.copy_stream));
+        ASC_CUDA_OK(cudaEventRecord(d.ev_up[b], d.copy_stream));
+        ASC_CUDA_OK(cudaStreamWaitEvent(d.stream, d.ev_up[b], 0));
+        if (enqueue_batch(ctx, d, d.in_src[b].p, d.in_smp[b].p, n, L, dtype, d_res + c0, d.stream) != 0)
+            return -1;
+        ASC_CUDA_OK(cudaEventRecord(d.ev_done[b], d.stream));
+    }
+    ASC_CUDA_OK(cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result) * total,
+                                cudaMemcpyDeviceToHost, d.stream));
+    ASC_CUDA_OK(cudaStreamSynchronize(d.stream));
+    memcpy(out + p0, d.h_results.p, sizeof(audiosync_cuda_result) * total);
+    return 0;
+}
+
+}  // namespace asc
+
+using namespace asc;
+
+asc::DeviceState* audiosync_cuda_ctx::find(int device) {
+    for (auto& d : devs)
+        if (d.device == device) return &d;
+    return nullptr;
+}
+
+// ===========================================================================
+// C ABI (the only symbols with default visibility)
+// ===========================================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* audiosync_cuda_last_error(void) { return g_last_error; }
+const char* audiosync_cuda_version(void) { return "audiosync_cuda 0.1 (sm_100a)"; }
+void audiosync_cuda_set_debug(int on) { g_debug_flag = on; }
+
+int audiosync_cuda_create(audiosync_cuda_ctx** out, const int* devices, int n_devices) {
+    if (!out) return -1;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        set_last_error("no CUDA device available (this library has no CPU fallback)");
+        return -1;
+    }
+    std::vector<int> ids;
+    if (devices && n_devices > 0) ids.assign(devices, devices + n_devices);
+    else for (int i = 0; i < count; i++) ids.push_back(i);
+    auto* ctx = new audiosync_cuda_ctx();
+    ctx->devs.resize(ids.size());
+    for (size_t i = 0; i < ids.size(); i++) {
+        DeviceState& d = ctx->devs[i];
+        cudaDeviceProp prop;
+        if (ids[i] < 0 || ids[i] >= count || cudaSetDevice(ids[i]) != cudaSuccess ||
+            cudaGetDeviceProperties(&prop, ids[i]) != cudaSuccess) {
+            set_last_error("cannot use CUDA device %d", ids[i]);
+            audiosync_cuda_destroy(ctx);
+            return -1;
+        }
+        d.device = ids[i];
+        d.sm_count = prop.multiProcessorCount;
+        d.smem_optin = prop.sharedMemPerBlockOptin;
+        // the only kernel image in this library is sm_100a
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, peaks_reset_kernel) != cudaSuccess) {
+            cudaGetLastError();
+            set_last_error("device %d (%s, sm_%d%d) cannot run the sm_100a kernels of this library",
+                           ids[i], prop.name, prop.major, prop.minor);
+            audiosync_cuda_destroy(ctx);
+            return -1;
+        }
+        if (cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+            set_last_error("cudaStreamCreate failed on device %d", ids[i]);
+            audiosync_cuda_destroy(ctx);
+            return -1;
+        }
+    }
+    const char* w = getenv("AUDIOSYNC_CUDA_WAVE_PAIRS");
+    if (w) ctx->wave_pairs = atoi(w);
+    *out = ctx;
+    return 0;
+}
+
+void audiosync_cuda_destroy(audiosync_cuda_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->devs) destroy_device_state(d);
+    delete ctx;
+}
+
+int audiosync_cuda_device_count(const audiosync_cuda_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+int audiosync_cuda_set_path(audiosync_cuda_ctx* ctx, int path) {
+    if (!ctx || path < AUDIOSYNC_CUDA_PATH_AUTO || path > AUDIOSYNC_CUDA_PATH_DIRECT) return -1;
+    ctx->path = path;
+    return 0;
+}
+
+int audiosync_cuda_set_wave_pairs(audiosync_cuda_ctx* ctx, int pairs) {
+    if (!ctx || pairs < 0) return -1;
+    ctx->wave_pairs = pairs;
+    return 0;
+}
+
+uint64_t audiosync_cuda_launch_count(const audiosync_cuda_ctx* ctx) {
+    return ctx ? ctx->launches.load() : 0;
+}
+
+int audiosync_cuda_describe_plan(audiosync_cuda_ctx* ctx, size_t sample_len, char* buf, size_t buf_len) {
+    if (!ctx || !buf || ctx->devs.empty()) return -1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceState& d = ctx->devs[0];
+    if (cudaSetDevice(d.device) != cudaSuccess) return -1;
+    FftPlan* plan = get_plan(ctx, d, (long long)sample_len);
+    if (!plan || plan->desc.size() + 1 > buf_len) return -1;
+    memcpy(buf, plan->desc.c_str(), plan->desc.size() + 1);
+    return (int)plan->desc.size();
+}
+
+int audiosync_cuda_profile_enable(audiosync_cuda_ctx* ctx, int on) {
+    if (!ctx) return -1;
+    ctx->profile = on != 0;
+    return 0;
+}
+
+int audiosync_cuda_profile_reset(audiosync_cuda_ctx* ctx) {
+    if (!ctx) return -1;
+    for (auto& d : ctx->devs) {
+        if (drain_profile(d) != 0) return -1;
+        for (int k = 0; k < KC_COUNT; k++) { d.prof_ms[k] = 0; d.prof_launches[k] = 0; }
+    }
+    return 0;
+}
+
+int audiosync_cuda_profile_read(audiosync_cuda_ctx* ctx, int i, char* name, size_t name_len,
+                                uint64_t* launches, double* total_ms) {
+    if (!ctx) return -1;
+    if (i < 0 || i >= KC_COUNT) return KC_COUNT;
+    uint64_t n = 0;
+    double ms = 0;
+    for (auto& d : ctx->devs) {
+        if (drain_profile(d) != 0) return -1;
+        n += d.prof_launches[i];
+        ms += d.prof_ms[i];
+    }
+    if (name && name_len) snprintf(name, name_len, "%s", kernel_class_name(i));
+    if (launches) *launches = n;
+    if (total_ms) *total_ms = ms;
+    return KC_COUNT;
+}
+
+int audiosync_cuda_synchronize(audiosync_cuda_ctx* ctx, int device) {
+    if (!ctx) return -1;
+    DeviceState* d = ctx->find(device);
+    if (!d) { set_last_error("device %d is not part of this context", device); return -1; }
+    ASC_CUDA_OK(cudaSetDevice(d->device));
+    ASC_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int audiosync_cuda_synth_pairs(audiosync_cuda_ctx* ctx, int device, uint64_t seed, uint64_t first_pair,
+                               size_t n_pairs, size_t sample_len, int dtype, void* d_sources,
+                               void* d_samples, void* stream) {
+    if (!ctx || !d_sources || !d_samples) return -1;
+    DeviceState* d = ctx->find(device);
+    if (!d) { set_last_error("device %d is not part of this context", device); return -1; }
+    if (n_pairs == 0) return 0;
+    ASC_CUDA_OK(cudaSetDevice(d->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
+    const long long L = (long long)sample_len;
+    const size_t esz = dtype == AUDIOSYNC_CUDA_F32 ? 4 : 8;
+    const unsigned bx = (unsigned)std::min<long long>((3 * L + 255) / 256, 4096);
+    for (size_t p0 = 0; p0 < n_pairs; p0 += 32768) {
+        const unsigned np = (unsigned)std::min<size_t>(32768, n_pairs - p0);
+        const dim3 grid(bx, np);
+        char* s = static_cast<char*>(d_sources) + p0 * (size_t)(2 * L) * esz;
+        char* m = static_cast<char*>(d_samples) + p0 * (size_t)L * esz;
+        int rc;
+        if (dtype == AUDIOSYNC_CUDA_F32)
+            rc = launch(ctx, *d, KC_SYNTH, st, [&] {
+                synth_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<float*>(s),
+                                                          reinterpret_cast<float*>(m), seed, first_pair + p0, L);
+            });
+        else
+            rc = launch(ctx, *d, KC_SYNTH, st, [&] {
+                synth_kernel<double><<<grid, 256, 0, st>>>(reinterpret_cast<double*>(s),
+                                                           reinterpret_cast<double*>(m), seed, first_pair + p0, L);
+            });
+        if (rc != 0) return -1;
+    }
+    return 0;
+}
+
+int audiosync_cuda_xcorr_batch_device(audiosync_cuda_ctx* ctx, int device, const void* d_sources,
+                                      const void* d_samples, size_t n_pairs, size_t sample_len,
+                                      int dtype, audiosync_cuda_result* d_results, void* stream) {
+    if (!ctx || !d_sources || !d_samples || !d_results) { set_last_error("null argument"); return -1; }
+    if (dtype != AUDIOSYNC_CUDA_F32 && dtype != AUDIOSYNC_CUDA_F64) { set_last_error("bad dtype"); return -1; }
+    DeviceState* d = ctx->find(device);
+    if (!d) { set_last_error("device %d is not part of this context", device); return -1; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
+    return enqueue_batch(ctx, *d, d_sources, d_samples, n_pairs, (long long)sample_len, dtype, d_results, st);
+}
+
+int audiosync_cuda_xcorr_batch(audiosync_cuda_ctx* ctx, const void* sources, const void* samples,
+                               size_t n_pairs, size_t sample_len, int dtype, int memspace, long* lags,
+                               double* coefs, int* rets, double* peaks) {
+    if (!ctx || !sources || !samples) { set_last_error("null argument"); return -1; }
+    if (dtype != AUDIOSYNC_CUDA_F32 && dtype != AUDIOSYNC_CUDA_F64) { set_last_error("bad dtype"); return -1; }
+    if (n_pairs == 0) return 0;
+    if (sample_len == 0) { set_last_error("sample_len must be > 0"); return -1; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const long long L = (long long)sample_len;
+    std::vector<audiosync_cuda_result> res(n_pairs);
+    int rc = 0;
+    if (memspace == AUDIOSYNC_CUDA_DEVICE) {
+        cudaPointerAttributes at;
+        ASC_CUDA_OK(cudaPointerGetAttributes(&at, sources));
+        DeviceState* d = ctx->find(at.device);
+        if (at.type != cudaMemoryTypeDevice || !d) {
+            set_last_error("device-memspace pointers must live on a device of the context");
+            return -1;
+        }
+        ASC_CUDA_OK(cudaSetDevice(d->device));
+        if (d->results.ensure(sizeof(audiosync_cuda_result) * n_pairs) != 0) return -1;
+        auto* d_res = static_cast<audiosync_cuda_result*>(d->results.p);
+        if (enqueue_batch(ctx, *d, sources, samples, n_pairs, L, dtype, d_res, d->stream) != 0) return -1;
+        ASC_CUDA_OK(cudaMemcpyAsync(res.data(), d_res, sizeof(audiosync_cuda_result) * n_pairs,
+                                    cudaMemcpyDeviceToHost, d->stream));
+        ASC_CUDA_OK(cudaStreamSynchronize(d->stream));
+    } else {
+        // contiguous block split over the devices, one host thread per device
+        const size_t G = ctx->devs.size();
+        std::vector<int> rcs(G, 0);
+        std::vector<std::thread> th;
+        const size_t base = n_pairs / G, rem = n_pairs % G;
+        size_t p0 = 0;
+        for (size_t g = 0; g < G; g++) {
+            const size_t cnt = base + (g < rem ? 1 : 0);
+            const size_t a = p0, b = p0 + cnt;
+            p0 = b;
+            if (cnt == 0) continue;
+            auto work = [&, g, a, b] {
+                rcs[g] = run_host_range(ctx, ctx->devs[g], static_cast<const char*>(sources),
+                                        static_cast<const char*>(samples), a, b, L, dtype, res.data());
+            };
+            if (G == 1) work(); else th.emplace_back(work);
+        }
+        for (auto& t : th) t.join();
+        for (int r : rcs) rc |= r;
+        if (rc != 0) return -1;
+    }
+    for (size_t i = 0; i < n_pairs; i++) {
+        if (lags) lags[i] = (long)res[i].lag;
+        if (coefs) coefs[i] = res[i].coef;
+        if (rets) rets[i] = res[i].ret;
+        if (peaks) peaks[i] = res[i].peak;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------ default context
+static audiosync_cuda_ctx* g_default_ctx = nullptr;
+static std::mutex g_default_mu;
+
+static audiosync_cuda_ctx* default_ctx() {
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (!g_default_ctx) {
+        int dev = 0;
+        const char* e = getenv("AUDIOSYNC_CUDA_DEVICE");
+        if (e) dev = atoi(e);
+        audiosync_cuda_ctx* c = nullptr;
+        if (audiosync_cuda_create(&c, &dev, 1) != 0) return nullptr;
+        const char* p = getenv("AUDIOSYNC_CUDA_PATH");
+        if (p && !strcmp(p, "direct")) c->path = AUDIOSYNC_CUDA_PATH_DIRECT;
+        g_default_ctx = c;
+    }
+    return g_default_ctx;
+}
+
+// ---- Part 1: drop-in for reference src/cross_correlation.c -----------------
+int cross_correlation(double* source, double* input_sample, const size_t sample_len, long* lag,
+                      double* coefficient) {
+    if (!source || !input_sample || !lag || !coefficient || sample_len == 0) {
+        set_last_error("cross_correlation: invalid argument");
+        return -1;
+    }
+    audiosync_cuda_ctx* ctx = default_ctx();
+    if (!ctx) return -1;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceState& d = ctx->devs[0];
+    const long long L = (long long)sample_len;
+    ASC_CUDA_OK(cudaSetDevice(d.device));
+    if (d.in_src[0].ensure(sizeof(double) * 2 * L) != 0 || d.in_smp[0].ensure(sizeof(double) * L) != 0 ||
+        d.results.ensure(sizeof(audiosync_cuda_result)) != 0 ||
+        d.h_results.ensure(sizeof(audiosync_cuda_result)) != 0)
+        return -1;
+    // snapshot exactly the prefixes the reference reads (src/cross_correlation.c:164, :204-213)
+    ASC_CUDA_OK(cudaMemcpyAsync(d.in_src[0].p, source, sizeof(double) * 2 * L, cudaMemcpyHostToDevice, d.stream));
+    ASC_CUDA_OK(cudaMemcpyAsync(d.in_smp[0].p, input_sample, sizeof(double) * L, cudaMemcpyHostToDevice, d.stream));
+    auto* d_res = static_cast<audiosync_cuda_result*>(d.results.p);
+    if (enqueue_batch(ctx, d, d.in_src[0].p, d.in_smp[0].p, 1, L, AUDIOSYNC_CUDA_F64, d_res, d.stream) != 0)
+        return -1;
+    ASC_CUDA_OK(cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result), cudaMemcpyDeviceToHost, d.stream));
+    ASC_CUDA_OK(cudaStreamSynchronize(d.stream));
+    const audiosync_cuda_result r = *static_cast<audiosync_cuda_result*>(d.h_results.p);
+    *lag = (long)r.lag;                 // written before the NaN gate, like :259/:272
+    *coefficient = r.coef;
+    if (r.ret != 0) return -1;          // :276
+    if (debug_on())                     // :278, LOG() format of audiosync.h:88-94
+        fprintf(stderr, "\x1B[36maudiosync: \x1B[0m%ld frames of delay with a confidence of %f\n",
+                *lag, *coefficient);
+    return 0;
+}
+
+double pearson_coefficient(double* source_start, const double* source_end, double* sample_start,
+                           const double* sample_end) {
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    if (!source_start || !source_end || !sample_start || !sample_end) return nan;
+    const long long n = (long long)(source_end - source_start);
+    if (n < 0 || (long long)(sample_end - sample_start) != n) {
+        set_last_error("pearson_coefficient: ranges must have equal, non-negative length");
+        return nan;
+    }
+    if (n == 0) return nan;             // 0/0 in the reference
+    audiosync_cuda_ctx* ctx = default_ctx();
+    if (!ctx) return nan;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceState& d = ctx->devs[0];
+    auto fail = [&]() { return nan; };
+    if (cudaSetDevice(d.device) != cudaSuccess) return fail();
+    const int n_chunks = (int)((n + PEARSON_CHUNK - 1) / PEARSON_CHUNK);
+    if (d.in_src[0].ensure(sizeof(double) * n) != 0 || d.in_smp[0].ensure(sizeof(double) * n) != 0 ||
+        d.partials.ensure(sizeof(PearsonPartial) * n_chunks) != 0 ||
+        d.results.ensure(sizeof(audiosync_cuda_result)) != 0 ||
+        d.h_results.ensure(sizeof(audiosync_cuda_result)) != 0)
+        return fail();
+    cudaStream_t st = d.stream;
+    auto* d_res = static_cast<audiosync_cuda_result*>(d.results.p);
+    auto* partials = static_cast<PearsonPartial*>(d.partials.p);
+    if (cudaMemcpyAsync(d.in_src[0].p, source_start, sizeof(double) * n, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(d.in_smp[0].p, sample_start, sizeof(double) * n, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        set_last_error("pearson_coefficient: upload failed");
+        return fail();
+    }
+    if (launch(ctx, d, KC_PEARSON_PARTIAL, st, [&] {
+            pearson_partial_kernel<double><<<dim3(n_chunks, 1), PEARSON_THREADS, 0, st>>>(
+                static_cast<const double*>(d.in_src[0].p), static_cast<const double*>(d.in_smp[0].p), 0, 0,
+                n, nullptr, n, partials, n_chunks);
+        }) != 0) return fail();
+    if (launch(ctx, d, KC_PEARSON_FINAL, st, [&] {
+            pearson_final_kernel<<<1, 32, 0, st>>>(partials, n_chunks, n, nullptr, n, d_res);
+        }) != 0) return fail();
+    if (cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+        set_last_error("pearson_coefficient: %s", cudaGetErrorString(cudaGetLastError()));
+        return fail();
+    }
+    return static_cast<audiosync_cuda_result*>(d.h_results.p)->coef;
+}
+
+// ---- Part 2: FFTW-named allocators (reference src/audiosync.c:189,277) -------
+// A small header in front of every block remembers how it was obtained.
+struct AllocHeader { uint64_t magic; uint64_t pinned; void* base; uint64_t pad; };
+static const uint64_t ALLOC_MAGIC = 0xA5D10C0DAFF7E11AULL;
+
+void* fftw_malloc(size_t n_bytes) {
+    const size_t total = n_bytes + 64;
+    void* base = nullptr;
+    uint64_t pinned = 0;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) == cudaSuccess && count > 0 &&
+        cudaMallocHost(&base, total) == cudaSuccess) {
+        pinned = 1;
+    } else {
+        cudaGetLastError();
+        base = nullptr;
+        if (posix_memalign(&base, 64, total) != 0) return nullptr;
+    }
+    AllocHeader* h = reinterpret_cast<AllocHeader*>(static_cast<char*>(base) + 64 - sizeof(AllocHeader));
+    h->magic = ALLOC_MAGIC; h->pinned = pinned; h->base = base; h->pad = 0;
+    return static_cast<char*>(base) + 64;
+}
+
+double* fftw_alloc_real(size_t n) { return static_cast<double*>(fftw_malloc(n * sizeof(double))); }
+void* fftw_alloc_complex(size_t n) { return fftw_malloc(n * 2 * sizeof(double)); }
+
+void fftw_free(void* p) {
+    if (!p) return;
+    AllocHeader* h = reinterpret_cast<AllocHeader*>(static_cast<char*>(p) - sizeof(AllocHeader));
+    if (h->magic != ALLOC_MAGIC) {
+        fprintf(stderr, "audiosync: fftw_free of a pointer not obtained from this library\n");
+        return;
+    }
+    h->magic = 0;
+    if (h->pinned) cudaFreeHost(h->base); else free(h->base);
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,102 @@
+// context.h -- host-side state of libaudiosync_cuda: devices, streams,
+// growable device buffers, launch accounting and per-kernel event timing.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace asc {
+
+void set_last_error(const char* fmt, ...);
+
+#define ASC_CUDA_OK(expr)                                                              \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            asc::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                __FILE__, __LINE__);                                   \
+            return -1;                                                                 \
+        }                                                                              \
+    } while (0)
+
+// Kernel classes for launch accounting / timing.
+enum KernelClass {
+    KC_SYNTH = 0,
+    KC_DIRECT,
+    KC_ARGMAX_F64,
+    KC_PEAKS_RESET,
+    KC_COL_FWD,      // K_A  forward column pass (source and sample)
+    KC_ROW_FUSED,    // K_B  forward rows + split + conj-multiply + merge + inverse rows
+    KC_COL_INV,      // K_C  inverse column pass + |r| argmax epilogue
+    KC_SMALL_FFT,    // single-CTA transform for short lengths
+    KC_PEARSON_PARTIAL,
+    KC_PEARSON_FINAL,
+    KC_COUNT
+};
+
+const char* kernel_class_name(int k);
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need);      // grows (never shrinks); returns 0 / -1
+    void release();
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need);
+    void release();
+};
+
+struct ProfileRecord { int cls; cudaEvent_t e0, e1; };
+
+struct FftPlan;   // fft_plan.h
+
+struct DeviceState {
+    int device = -1;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;        // compute
+    cudaStream_t copy_stream = nullptr;   // uploads for the host-facing batch call
+    DevBuf ws;            // transform workspace (direct: r[]; fft: A/B planes)
+    DevBuf peaks;         // PairPeak per in-flight pair
+    DevBuf partials;      // PearsonPartial
+    DevBuf results;       // audiosync_cuda_result for host-facing calls
+    DevBuf in_src[2], in_smp[2];          // device copies of host inputs (double buffered)
+    PinnedBuf h_results;
+    PinnedBuf h_stage[2];                 // staging for pageable host inputs
+    cudaEvent_t ev_up[2] = {nullptr, nullptr};
+    cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    std::map<size_t, std::shared_ptr<FftPlan>> plans;   // by sample_len
+    // profiling
+    std::vector<ProfileRecord> prof_pending;
+    std::vector<cudaEvent_t> event_pool;
+    uint64_t prof_launches[KC_COUNT] = {0};
+    double prof_ms[KC_COUNT] = {0};
+};
+
+}  // namespace asc
+
+struct audiosync_cuda_ctx {
+    std::vector<asc::DeviceState> devs;
+    std::mutex mu;
+    int path = AUDIOSYNC_CUDA_PATH_AUTO;
+    int wave_pairs = 0;
+    bool profile = false;
+    std::atomic<uint64_t> launches{0};
+
+    asc::DeviceState* find(int device);
+};

@@ -1,0 +1,490 @@
+// fft_kernels.cuh -- the three transform kernels of the four-step plan.
+//
+// Complex length M = L (two reals packed per complex point), split M = M1 * M2,
+// point n = n1*M2 + n2, bin k = k1 + M1*k2.  Per pair, per wave:
+//
+//   K_A  ColFwdKernel   one CTA per (16-column tile, signal): M1-point forward
+//        FFT down the columns n2 of the packed input (read straight from the
+//        caller's real array; the zero half of the padded sample is never read),
+//        times W_M^(n2*k1), written as plane[k1][n2].
+//   K_B  RowFusedKernel one CTA per row pair (k1, M1-k1): M2-point forward FFT
+//        of those rows of both planes, the real-FFT split, the conj-multiply,
+//        the merge for the inverse real FFT, and the M2-point inverse FFT of
+//        the two product rows, times conj W_M^(n2*k1), written back in place.
+//        (reference src/cross_correlation.c:232-233 lives inside this kernel.)
+//   K_C  ColInvKernel   one CTA per 16-column tile: M1-point inverse FFT down
+//        the columns and the |r| argmax epilogue (reference :52-67, :242) --
+//        the correlation itself is never written to memory.
+//
+// All passes are in-place radix passes in shared memory (decimation in
+// frequency forward, decimation in time for the inverse rows), the first pass
+// fused with the global load and the last with the global store / epilogue.
+//
+// Kernel bodies are written against an executor (DeviceExec on the GPU,
+// tests/emu's HostExec on the CPU) that runs one "phase" for every thread and
+// then synchronises, so the same source is what the emulator checks.
+#pragma once
+
+#include "common.cuh"
+#include "fft_device.cuh"
+
+namespace asc {
+
+constexpr int COL_T = 16;          // columns per tile: 16 * 8 B = one 128-byte line
+constexpr unsigned TW2_BITS = 10;  // two-level twiddle tables: a = hi * 1024 + lo
+constexpr unsigned TW2_MASK = (1u << TW2_BITS) - 1u;
+
+// exp(-2*pi*i*a/base) from the two-level tables (both halves correctly rounded
+// from fp64 on the host; one fp32 complex product here).
+ASC_HD cplx tw2(const cplx* __restrict__ lo, const cplx* __restrict__ hi, unsigned a) {
+    return cmul(ldg(lo + (a & TW2_MASK)), ldg(hi + (a >> TW2_BITS)));
+}
+
+template <typename InT>
+ASC_HD cplx load_packed(const InT* __restrict__ x, long long n);
+
+template <>
+ASC_HD cplx load_packed<float>(const float* __restrict__ x, long long n) {
+    return ldg(reinterpret_cast<const float2*>(x) + n);
+}
+template <>
+ASC_HD cplx load_packed<double>(const double* __restrict__ x, long long n) {
+    double2 d = ldg(reinterpret_cast<const double2*>(x) + n);
+    return cmake((float)d.x, (float)d.y);
+}
+
+// --------------------------------------------------------------------- K_A
+template <class RL, int NT, typename InT>
+struct ColFwdKernel {
+    static constexpr int M1 = RL::n;
+    static constexpr int P = RL::count;
+    static constexpr int THREADS = NT;
+    static constexpr size_t SMEM = (size_t)M1 * COL_T * sizeof(cplx);
+
+    struct Params {
+        const InT* sources;      // [pair][2L] reals
+        const InT* samples;      // [pair][L] reals
+        cplx* planes;            // [pair][2][M1*M2]: plane 0 source, plane 1 sample
+        const cplx* tw;          // RL pass tables (forward sign)
+        const cplx* m_lo;        // W_M two-level tables
+        const cplx* m_hi;
+        long long L;             // sample_len == M
+        int M2;
+    };
+
+    // grid = (M2 / 16, 2, pairs)
+    template <class Ex>
+    static ASC_HD void run(Ex& ex, const Params& p, cplx* __restrict__ buf) {
+        const int c0 = ex.bx() * COL_T;
+        const int sig = ex.by();
+        const long long pair = ex.bz();
+        const long long M = p.L;
+        const int M2 = p.M2;
+        const InT* __restrict__ x = sig == 0 ? p.sources + pair * 2 * M : p.samples + pair * M;
+        // number of valid packed points: source M, sample M/2 (upper half is the zero pad)
+        const long long nvalid = sig == 0 ? M : M / 2;
+        cplx* __restrict__ out = p.planes + (pair * 2 + sig) * M;
+
+        static_for<0, P>([&](auto PP) {
+            constexpr int ps = decltype(PP)::value;
+            constexpr int R = RL::r(ps);
+            constexpr int S = RL::stride(ps);
+            constexpr bool first = ps == 0, last = ps == P - 1;
+            constexpr int items = (M1 / R) * COL_T;
+            ex.phase([&](int tid) {
+                for (int w = tid; w < items; w += NT) {
+                    const int c = w & (COL_T - 1);
+                    const int bf = w >> 4;
+                    const int blk = bf / S;
+                    const int j = bf - blk * S;
+                    const int i0 = blk * (S * R) + j;
+                    cplx v[R];
+                    if constexpr (first) {
+                        static_for<0, R>([&](auto Q) {
+                            constexpr int q = decltype(Q)::value;
+                            const long long n = (long long)(i0 + q * S) * M2 + c0 + c;
+                            v[q] = n < nvalid ? load_packed<InT>(x, n) : cmake(0.f, 0.f);
+                        });
+                    } else {
+                        static_for<0, R>([&](auto Q) {
+                            constexpr int q = decltype(Q)::value;
+                            v[q] = buf[(i0 + q * S) * COL_T + c];
+                        });
+                    }
+                    dft_reg<R, -1>(v);
+                    if constexpr (!last) {
+                        buf[i0 * COL_T + c] = v[0];
+                        static_for<1, R>([&](auto K) {
+                            constexpr int k = decltype(K)::value;
+                            cplx t = ldg(p.tw + RL::tw_offset(ps) + (k - 1) * S + j);
+                            buf[(i0 + k * S) * COL_T + c] = cmul(v[k], t);
+                        });
+                    } else {
+                        // S == 1: positions i0 .. i0+R-1 hold bins f0 + k * weight
+                        const int f0 = RL::freq_of_pos(i0);
+                        const unsigned n2 = (unsigned)(c0 + c);
+                        static_for<0, R>([&](auto K) {
+                            constexpr int k = decltype(K)::value;
+                            const unsigned k1 = (unsigned)(f0 + k * RL::weight(ps));
+                            cplx t = tw2(p.m_lo, p.m_hi, n2 * k1);
+                            out[(long long)k1 * M2 + n2] = cmul(v[k], t);
+                        });
+                    }
+                }
+            });
+        });
+    }
+};
+
+// --------------------------------------------------------------------- K_C
+template <class RL, int NT>
+struct ColInvKernel {
+    static constexpr int M1 = RL::n;
+    static constexpr int P = RL::count;
+    static constexpr int THREADS = NT;
+    static constexpr size_t SMEM = (size_t)M1 * COL_T * sizeof(cplx);
+
+    struct Params {
+        const cplx* planes;      // [pair][2][M1*M2]; plane 0 holds the K_B output
+        PairPeak* peaks;         // [pair]
+        const cplx* tw;          // RL pass tables (forward sign; conjugated here)
+        long long L;
+        int M2;
+    };
+
+    // grid = (M2 / 16, 1, pairs)
+    template <class Ex>
+    static ASC_HD void run(Ex& ex, const Params& p, cplx* __restrict__ buf) {
+        const int c0 = ex.bx() * COL_T;
+        const long long pair = ex.bz();
+        const long long M = p.L;
+        const int M2 = p.M2;
+        const cplx* __restrict__ in = p.planes + pair * 2 * M;
+
+        static_for<0, P - 1>([&](auto PP) {
+            constexpr int ps = decltype(PP)::value;
+            constexpr int R = RL::r(ps);
+            constexpr int S = RL::stride(ps);
+            constexpr bool first = ps == 0;
+            constexpr int items = (M1 / R) * COL_T;
+            ex.phase([&](int tid) {
+                for (int w = tid; w < items; w += NT) {
+                    const int c = w & (COL_T - 1);
+                    const int bf = w >> 4;
+                    const int blk = bf / S;
+                    const int j = bf - blk * S;
+                    const int i0 = blk * (S * R) + j;
+                    cplx v[R];
+                    static_for<0, R>([&](auto Q) {
+                        constexpr int q = decltype(Q)::value;
+                        if constexpr (first) v[q] = ldg(in + (long long)(i0 + q * S) * M2 + c0 + c);
+                        else v[q] = buf[(i0 + q * S) * COL_T + c];
+                    });
+                    dft_reg<R, +1>(v);
+                    buf[i0 * COL_T + c] = v[0];
+                    static_for<1, R>([&](auto K) {
+                        constexpr int k = decltype(K)::value;
+                        cplx t = ldg(p.tw + RL::tw_offset(ps) + (k - 1) * S + j);
+                        buf[(i0 + k * S) * COL_T + c] = cmulc(v[k], t);
+                    });
+                }
+            });
+        });
+
+        // last pass + argmax epilogue: packed point n = n1*M2 + n2 carries
+        // r[2n] (real part) and r[2n+1] (imaginary part).
+        {
+            constexpr int ps = P - 1;
+            constexpr int R = RL::r(ps);
+            constexpr bool first = ps == 0;
+            constexpr int items = (M1 / R) * COL_T;
+            ex.phase_argmax(
+                [&](int tid) -> unsigned long long {
+                    unsigned long long best = 0ull;
+                    for (int w = tid; w < items; w += NT) {
+                        const int c = w & (COL_T - 1);
+                        const int blk = w >> 4;
+                        const int i0 = blk * R;
+                        cplx v[R];
+                        static_for<0, R>([&](auto Q) {
+                            constexpr int q = decltype(Q)::value;
+                            if constexpr (first) v[q] = ldg(in + (long long)(i0 + q) * M2 + c0 + c);
+                            else v[q] = buf[(i0 + q) * COL_T + c];
+                        });
+                        dft_reg<R, +1>(v);
+                        const int f0 = RL::freq_of_pos(i0);
+                        static_for<0, R>([&](auto K) {
+                            constexpr int k = decltype(K)::value;
+                            const long long n = (long long)(f0 + k * RL::weight(ps)) * M2 + c0 + c;
+                            const uint32_t i_re = (uint32_t)(2 * n);
+                            unsigned long long k_re = i_re == 0 ? argmax_key_seed(v[k].x)
+                                                                : argmax_key_abs(v[k].x, i_re);
+                            unsigned long long k_im = argmax_key_abs(v[k].y, i_re + 1u);
+                            best = k_re > best ? k_re : best;
+                            best = k_im > best ? k_im : best;
+                        });
+                    }
+                    return best;
+                },
+                &p.peaks[pair].key);
+        }
+    }
+};
+
+// --------------------------------------------------------------------- K_B
+// The pair (k, M-k) computation shared by the fused row kernel and the
+// single-CTA short-length kernel.
+//   a = Zs[k], b = Zs[M-k], c = Zp[k], d = Zp[M-k], w = exp(-2*pi*i*k/N).
+//   2X[k] = s + u,  2X[M-k] = conj(s - u)  with s = a + conj b, u = w*(-i)(a - conj b)
+//   p1 = 4 P[k] = 2X[k] conj(2Y[k]);  p2 = conj(4 P[M-k]) = (s-u) conj(s'-u')
+//   Q[k] = ((p1+p2) + i conj(w)(p1-p2)) / 4;  Q[M-k] = conj((p1+p2) - i conj(w)(p1-p2)) / 4
+ASC_HD void split_mul_merge(cplx a, cplx b, cplx c, cplx d, cplx w, cplx& qk, cplx& qmk) {
+    const cplx s = cmake(a.x + b.x, a.y - b.y);
+    const cplx t = cmake(a.x - b.x, a.y + b.y);
+    const cplx u = cmul(w, cmake(t.y, -t.x));
+    const cplx s2 = cmake(c.x + d.x, c.y - d.y);
+    const cplx t2 = cmake(c.x - d.x, c.y + d.y);
+    const cplx u2 = cmul(w, cmake(t2.y, -t2.x));
+    const cplx p1 = cmulc(cadd(s, u), cadd(s2, u2));
+    const cplx p2 = cmulc(csub(s, u), csub(s2, u2));
+    const cplx g = cadd(p1, p2);
+    const cplx e = csub(p1, p2);
+    // h = i * conj(w) * e
+    const cplx ce = cmulc(e, w);
+    const cplx h = cmake(-ce.y, ce.x);
+    qk = cmake(0.25f * (g.x + h.x), 0.25f * (g.y + h.y));
+    qmk = cmake(0.25f * (g.x - h.x), -0.25f * (g.y - h.y));
+}
+
+template <class RL, int NT>
+struct RowFusedKernel {
+    static constexpr int M2 = RL::n;
+    static constexpr int P = RL::count;
+    static constexpr int THREADS = NT;
+    static constexpr int RP = M2;   // row pitch in shared memory
+    static constexpr size_t SMEM = (size_t)4 * RP * sizeof(cplx);
+    static_assert(M2 % 2 == 0, "row length must be even");
+
+    struct Params {
+        cplx* planes;            // [pair][2][M1*M2]
+        const cplx* tw;          // RL pass tables (forward sign)
+        const cplx* m_lo;        // W_M tables
+        const cplx* m_hi;
+        const cplx* n_lo;        // W_N = W_2M tables
+        const cplx* n_hi;
+        long long L;
+        int M1;
+    };
+
+    // grid = (M1/2 + 1, 1, pairs); CTA r owns rows r and M1 - r.
+    template <class Ex>
+    static ASC_HD void run(Ex& ex, const Params& p, cplx* __restrict__ buf) {
+        const int r = ex.bx();
+        const long long pair = ex.bz();
+        const long long M = p.L;
+        const int M1 = p.M1;
+        const bool two = (r != 0) && (2 * r != M1);
+        const int nrows = two ? 2 : 1;
+        const int k1a = r, k1b = M1 - r;   // k1b unused when !two
+        cplx* __restrict__ plane_s = p.planes + pair * 2 * M;
+        cplx* __restrict__ plane_p = plane_s + M;
+
+        // ---- forward DIF on 2*nrows rows.  smem slots: 0,1 source rows; 2,3 sample rows.
+        static_for<0, P>([&](auto PP) {
+            constexpr int ps = decltype(PP)::value;
+            constexpr int R = RL::r(ps);
+            constexpr int S = RL::stride(ps);
+            constexpr bool first = ps == 0;
+            constexpr int per_row = M2 / R;
+            const int items = per_row * 2 * nrows;
+            ex.phase([&](int tid) {
+                for (int w = tid; w < items; w += NT) {
+                    const int b = w / per_row;
+                    const int bf = w - b * per_row;
+                    const int is_smp = b >= nrows ? 1 : 0;
+                    const int rr = b - is_smp * nrows;          // 0 or 1: which row of the pair
+                    cplx* __restrict__ row = buf + (is_smp * 2 + rr) * RP;
+                    const int blk = bf / S;
+                    const int j = bf - blk * S;
+                    const int i0 = blk * (S * R) + j;
+                    cplx v[R];
+                    if constexpr (first) {
+                        const cplx* __restrict__ g =
+                            (is_smp ? plane_p : plane_s) + (long long)(rr ? k1b : k1a) * M2;
+                        static_for<0, R>([&](auto Q) {
+                            constexpr int q = decltype(Q)::value;
+                            v[q] = g[i0 + q * S];
+                        });
+                    } else {
+                        static_for<0, R>([&](auto Q) {
+                            constexpr int q = decltype(Q)::value;
+                            v[q] = row[i0 + q * S];
+                        });
+                    }
+                    dft_reg<R, -1>(v);
+                    row[i0] = v[0];
+                    static_for<1, R>([&](auto K) {
+                        constexpr int k = decltype(K)::value;
+                        if constexpr (S > 1) {
+                            cplx t = ldg(p.tw + RL::tw_offset(ps) + (k - 1) * S + j);
+                            row[i0 + k * S] = cmul(v[k], t);
+                        } else {
+                            row[i0 + k * S] = v[k];
+                        }
+                    });
+                }
+            });
+        });
+
+        // ---- split + conj-multiply + merge, in place into the source rows.
+        {
+            // items: two rows -> every position e of row a pairs with position
+            // M2-1-e of row b (bin M2-1-k2); row M1/2 alone -> same map inside
+            // one row, e < M2/2; row 0 alone -> bins (k2, M2-k2), e <= M2/2.
+            const int items = two ? M2 : (r == 0 ? M2 / 2 + 1 : M2 / 2);
+            cplx* __restrict__ zs_a = buf;
+            cplx* __restrict__ zs_b = buf + (two ? RP : 0);
+            cplx* __restrict__ zp_a = buf + 2 * RP;
+            cplx* __restrict__ zp_b = buf + (two ? 3 * RP : 2 * RP);
+            ex.phase([&](int tid) {
+                for (int e = tid; e < items; e += NT) {
+                    int pa, pb, k2;
+                    if (r == 0) {
+                        k2 = e;
+                        pa = RL::pos_of_freq(e);
+                        pb = RL::pos_of_freq(e == 0 ? 0 : M2 - e);
+                    } else {
+                        pa = e;
+                        pb = M2 - 1 - e;
+                        k2 = RL::freq_of_pos(e);
+                    }
+                    const unsigned k = (unsigned)k1a + (unsigned)M1 * (unsigned)k2;
+                    const cplx w = tw2(p.n_lo, p.n_hi, k);
+                    cplx qk, qmk;
+                    split_mul_merge(zs_a[pa], zs_b[pb], zp_a[pa], zp_b[pb], w, qk, qmk);
+                    zs_a[pa] = qk;
+                    if (pa != pb || two) zs_b[pb] = qmk;
+                }
+            });
+        }
+
+        // ---- inverse DIT on nrows rows (slots 0,1), passes P-1 .. 0.
+        static_for<0, P>([&](auto PP) {
+            constexpr int ps = P - 1 - decltype(PP)::value;
+            constexpr int R = RL::r(ps);
+            constexpr int S = RL::stride(ps);
+            constexpr bool last = ps == 0;
+            constexpr int per_row = M2 / R;
+            const int items = per_row * nrows;
+            ex.phase([&](int tid) {
+                for (int w = tid; w < items; w += NT) {
+                    const int rr = w / per_row;
+                    const int bf = w - rr * per_row;
+                    cplx* __restrict__ row = buf + rr * RP;
+                    const int blk = bf / S;
+                    const int j = bf - blk * S;
+                    const int i0 = blk * (S * R) + j;
+                    cplx v[R];
+                    v[0] = row[i0];
+                    static_for<1, R>([&](auto Q) {
+                        constexpr int q = decltype(Q)::value;
+                        if constexpr (S > 1) {
+                            cplx t = ldg(p.tw + RL::tw_offset(ps) + (q - 1) * S + j);
+                            v[q] = cmulc(row[i0 + q * S], t);
+                        } else {
+                            v[q] = row[i0 + q * S];
+                        }
+                    });
+                    dft_reg<R, +1>(v);
+                    if constexpr (!last) {
+                        static_for<0, R>([&](auto K) {
+                            constexpr int k = decltype(K)::value;
+                            row[i0 + k * S] = v[k];
+                        });
+                    } else {
+                        // natural order n2 = j + k*S; apply conj W_M^(n2*k1), store in place
+                        const unsigned k1 = (unsigned)(rr ? k1b : k1a);
+                        cplx* __restrict__ g = plane_s + (long long)k1 * M2;
+                        static_for<0, R>([&](auto K) {
+                            constexpr int k = decltype(K)::value;
+                            const unsigned n2 = (unsigned)(j + k * S);
+                            cplx t = tw2(p.m_lo, p.m_hi, n2 * k1);
+                            g[n2] = cmulc(v[k], t);
+                        });
+                    }
+                }
+            });
+        });
+    }
+};
+
+// ------------------------------------------------------------- device entry
+// Executor used on the GPU.  Methods are __host__ __device__ only so that the
+// kernel bodies (shared with the CPU emulator) instantiate cleanly; the host
+// side of them is never called.
+struct DeviceExec {
+    ASC_HD int bx() const {
+#if defined(__CUDA_ARCH__)
+        return blockIdx.x;
+#else
+        return 0;
+#endif
+    }
+    ASC_HD int by() const {
+#if defined(__CUDA_ARCH__)
+        return blockIdx.y;
+#else
+        return 0;
+#endif
+    }
+    ASC_HD int bz() const {
+#if defined(__CUDA_ARCH__)
+        return blockIdx.z;
+#else
+        return 0;
+#endif
+    }
+    template <class F>
+    ASC_HD void phase(F&& f) {
+#if defined(__CUDA_ARCH__)
+        f((int)threadIdx.x);
+        __syncthreads();
+#endif
+    }
+    // CTA-wide maximum of a per-thread key, then one atomicMax on *dst.
+    template <class F>
+    ASC_HD void phase_argmax(F&& f, unsigned long long* dst) {
+#if defined(__CUDA_ARCH__)
+        __shared__ unsigned long long s_best[32];
+        unsigned long long best = f((int)threadIdx.x);
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) s_best[wid] = best;
+        __syncthreads();
+        if (wid == 0) {
+            const int nw = (blockDim.x + 31) >> 5;
+            best = lane < nw ? s_best[lane] : 0ull;
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+                best = other > best ? other : best;
+            }
+            if (lane == 0) atomicMax(dst, best);
+        }
+        __syncthreads();
+#endif
+    }
+};
+
+#if defined(__CUDACC__)
+template <class K>
+__global__ void __launch_bounds__(K::THREADS) fft_kernel_entry(const typename K::Params p) {
+    extern __shared__ __align__(16) unsigned char asc_smem[];
+    DeviceExec ex;
+    K::run(ex, p, reinterpret_cast<cplx*>(asc_smem));
+}
+#endif
+
+}  // namespace asc

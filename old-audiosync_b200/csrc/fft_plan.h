@@ -1,0 +1,195 @@
+// fft_plan.h -- host-side planning shared by the product library and the CPU
+// emulator: which path a sample_len takes, the static four-step plans for the
+// reference's interval schedule, and the twiddle tables (computed in long
+// double on the host, rounded once to fp32 -- never sincosf on the device).
+#pragma once
+
+#include <cmath>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "fft_device.cuh"
+#include "fft_small.cuh"
+
+namespace asc {
+
+// ------------------------------------------------------------ static plans
+// One per entry of the reference's interval schedule (src/audiosync.c:50-57:
+// sample_len = {3, 6, 10, 15, 20, 30} s x 48 kHz).  M = L = M1 * M2 with M2 a
+// multiple of 16 (full 128-byte lines per tile row) and even.  Row radix lists
+// end in an odd radix so the stride-1 pass is free of bank conflicts.
+struct Plan144k {
+    static constexpr long long L = 144000;
+    using Col = RadixList<10, 6, 5>;     // M1 = 300
+    using Row = RadixList<16, 10, 3>;    // M2 = 480
+    static constexpr int NT_COL = 160, NT_ROW = 128;
+};
+struct Plan288k {
+    static constexpr long long L = 288000;
+    using Col = RadixList<10, 6, 6>;     // M1 = 360
+    using Row = RadixList<16, 10, 5>;    // M2 = 800
+    static constexpr int NT_COL = 192, NT_ROW = 160;
+};
+struct Plan480k {
+    static constexpr long long L = 480000;
+    using Col = RadixList<10, 10, 6>;    // M1 = 600
+    using Row = RadixList<16, 10, 5>;    // M2 = 800
+    static constexpr int NT_COL = 320, NT_ROW = 160;
+};
+struct Plan720k {
+    static constexpr long long L = 720000;
+    using Col = RadixList<10, 10, 6>;    // M1 = 600
+    using Row = RadixList<16, 5, 15>;    // M2 = 1200
+    static constexpr int NT_COL = 320, NT_ROW = 256;
+};
+struct Plan960k {
+    static constexpr long long L = 960000;
+    using Col = RadixList<10, 10, 6>;    // M1 = 600
+    using Row = RadixList<8, 8, 5, 5>;   // M2 = 1600
+    static constexpr int NT_COL = 320, NT_ROW = 320;
+};
+struct Plan1440k {
+    static constexpr long long L = 1440000;
+    using Col = RadixList<10, 10, 6>;    // M1 = 600
+    using Row = RadixList<16, 10, 15>;   // M2 = 2400
+    static constexpr int NT_COL = 320, NT_ROW = 320;
+};
+
+using StaticPlans = std::tuple<Plan144k, Plan288k, Plan480k, Plan720k, Plan960k, Plan1440k>;
+
+template <class P>
+constexpr bool plan_is_consistent() {
+    return (long long)P::Col::n * P::Row::n == P::L && P::Row::n % COL_T == 0 && P::Row::n % 2 == 0;
+}
+static_assert(plan_is_consistent<Plan144k>() && plan_is_consistent<Plan288k>() &&
+              plan_is_consistent<Plan480k>() && plan_is_consistent<Plan720k>() &&
+              plan_is_consistent<Plan960k>() && plan_is_consistent<Plan1440k>(),
+              "static plan: M1*M2 != L or M2 not a multiple of 16");
+
+template <class RL>
+inline std::vector<int> radix_vector() {
+    std::vector<int> v;
+    for (int i = 0; i < RL::count; i++) v.push_back(RL::r(i));
+    return v;
+}
+
+template <class F, size_t... I>
+inline void for_each_static_plan_impl(F&& f, std::index_sequence<I...>) {
+    (f(std::tuple_element_t<I, StaticPlans>{}), ...);
+}
+template <class F>
+inline void for_each_static_plan(F&& f) {
+    for_each_static_plan_impl(static_cast<F&&>(f),
+                              std::make_index_sequence<std::tuple_size<StaticPlans>::value>{});
+}
+
+inline bool has_static_plan(long long L) {
+    bool found = false;
+    for_each_static_plan([&](auto P) { if (decltype(P)::L == L) found = true; });
+    return found;
+}
+
+// --------------------------------------------------------------- twiddles
+inline cplx unit_root(long long a, long long base) {   // exp(-2*pi*i*a/base)
+    a %= base;
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    // reduce to the first octant so that sinl/cosl see a small argument
+    long long q8 = (8 * a) / base;                      // octant 0..7
+    long double c, s;
+    auto cs = [&](long double num) {                    // angle = 2*pi*num/base
+        long double th = two_pi * num / (long double)base;
+        c = cosl(th); s = sinl(th);
+    };
+    switch (q8) {
+        case 0: cs((long double)a); break;
+        case 1: { cs((long double)(base / 4.0L - a)); long double t = c; c = s; s = t; } break;
+        case 2: { cs((long double)(a - base / 4.0L)); long double t = c; c = -s; s = t; } break;
+        case 3: { cs((long double)(base / 2.0L - a)); c = -c; } break;
+        case 4: { cs((long double)(a - base / 2.0L)); c = -c; s = -s; } break;
+        case 5: { cs((long double)(3.0L * base / 4.0L - a)); long double t = c; c = -s; s = -t; } break;
+        case 6: { cs((long double)(a - 3.0L * base / 4.0L)); long double t = c; c = s; s = -t; } break;
+        default: { cs((long double)(base - a)); s = -s; } break;
+    }
+    return cmake((float)c, (float)(-s));
+}
+
+// Pass tables for an in-place DIF radix list (layout: RadixList::tw_offset).
+inline std::vector<cplx> build_pass_tables(const std::vector<int>& radices) {
+    long long n = 1;
+    for (int r : radices) n *= r;
+    std::vector<cplx> t;
+    long long prod = 1;
+    for (size_t p = 0; p < radices.size(); p++) {
+        prod *= radices[p];
+        const long long s = n / prod, m = s * radices[p];
+        for (int k = 1; k < radices[p]; k++)
+            for (long long j = 0; j < s; j++) t.push_back(unit_root(j * k, m));
+    }
+    return t;
+}
+
+// Two-level tables for exp(-2*pi*i*a/base), a in [0, max_index].
+inline void build_two_level(long long base, long long max_index, std::vector<cplx>& lo,
+                            std::vector<cplx>& hi) {
+    lo.resize(1u << TW2_BITS);
+    for (long long a = 0; a < (long long)lo.size(); a++) lo[a] = unit_root(a, base);
+    const long long nh = (max_index >> TW2_BITS) + 1;
+    hi.resize(nh);
+    for (long long b = 0; b < nh; b++) hi[b] = unit_root(b << TW2_BITS, base);
+}
+
+inline std::vector<cplx> build_full_table(long long base, long long count) {
+    std::vector<cplx> t(count);
+    for (long long a = 0; a < count; a++) t[a] = unit_root(a, base);
+    return t;
+}
+
+// ------------------------------------------------------------- path choice
+inline bool is_235_smooth(long long n) {
+    if (n <= 0) return false;
+    for (int p : {2, 3, 5}) while (n % p == 0) n /= p;
+    return n == 1;
+}
+
+// Short-length plan: even, 2/3/5-smooth, M <= SMALL_MAX_M, at least 2 points.
+inline bool make_small_plan(long long L, SmallPlan* out) {
+    if (L < 2 || L % 2 != 0 || L > SMALL_MAX_M || !is_235_smooth(L)) return false;
+    SmallPlan pl;
+    pl.M = (int)L;
+    pl.npass = 0;
+    long long r = L;
+    // radix order: 4s and 2 first, odd radices last (stride-1 pass conflict-free)
+    auto push = [&](int f) { pl.radix[pl.npass++] = f; r /= f; };
+    while (r % 4 == 0) push(4);
+    while (r % 2 == 0) push(2);
+    while (r % 3 == 0) push(3);
+    while (r % 5 == 0) push(5);
+    if (pl.npass > SMALL_MAX_PASSES) return false;
+    long long prod = 1;
+    for (int p = 0; p < pl.npass; p++) {
+        prod *= pl.radix[p];
+        pl.stride[p] = (int)(L / prod);
+    }
+    *out = pl;
+    return true;
+}
+
+enum PathKind { PATH_STATIC_FFT, PATH_SMALL_FFT, PATH_DIRECT };
+
+// Below this length AUTO prefers the fp64 time-domain kernel: it costs
+// microseconds and keeps fp64 accuracy where the reference's own tests live
+// (tests/test_cross_correlation.c T7: sin(i), L = 1000, has two peaks that
+// differ by 1.2e-9 relative -- unresolvable by an fp32 transform).
+constexpr long long DIRECT_AUTO_BELOW = 4096;
+
+inline PathKind choose_path(long long L, int forced) {
+    if (forced == AUDIOSYNC_CUDA_PATH_DIRECT) return PATH_DIRECT;
+    SmallPlan sp;
+    if (has_static_plan(L)) return PATH_STATIC_FFT;
+    if (forced != AUDIOSYNC_CUDA_PATH_FFT && L < DIRECT_AUTO_BELOW) return PATH_DIRECT;
+    if (make_small_plan(L, &sp)) return PATH_SMALL_FFT;
+    return PATH_DIRECT;   // also when FFT is forced but no plan exists
+}
+
+}  // namespace asc

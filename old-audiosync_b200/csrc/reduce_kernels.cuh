@@ -1,0 +1,281 @@
+// reduce_kernels.cuh -- non-FFT kernels of the path: seeded generator, the
+// universal time-domain (direct) correlation, argmax resolution, Pearson.
+#pragma once
+
+#include "common.cuh"
+
+namespace asc {
+
+// ---------------------------------------------------------------------------
+// Seeded synthetic pairs (same integers as oracle/xcorr_oracle.c
+// synth_pair_i32).  grid = (blocks, n_pairs); element e < 2L -> source[e],
+// else sample[e - 2L].
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+synth_kernel(T* __restrict__ sources, T* __restrict__ samples, uint64_t seed,
+             uint64_t first_pair, long long L)
+{
+    const uint64_t pair = first_pair + blockIdx.y;
+    const uint64_t k0 = seed ^ (pair * 0xD1342543DE82EF95ULL);
+    const uint64_t k1 = k0 ^ 0xA0761D6478BD642FULL;
+    const uint64_t k2 = k0 ^ (2ULL * 0xA0761D6478BD642FULL);
+    const long long tl = (long long)(splitmix64(k2) % (uint64_t)(L + 1)) - (L / 2);
+    const long long amp = (pair % 4 == 3) ? 768 : 102;
+    const long long half = L / 2;
+    T* src = sources + (size_t)blockIdx.y * (size_t)(2 * L);
+    T* smp = samples + (size_t)blockIdx.y * (size_t)L;
+    const T scale = (T)(1.0 / 8388608.0);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < 3 * L;
+         e += (long long)gridDim.x * blockDim.x) {
+        if (e < 2 * L) {
+            long long q = (long long)(splitmix64(k0 + (uint64_t)(half + e)) >> 40) - (1LL << 23);
+            src[e] = (T)q * scale;
+        } else {
+            long long j = e - 2 * L;
+            long long b = (long long)(splitmix64(k0 + (uint64_t)(half + tl + j)) >> 40) - (1LL << 23);
+            long long n = (long long)(splitmix64(k1 + (uint64_t)j) >> 40) - (1LL << 23);
+            smp[j] = (T)(b + ((n * amp) >> 10)) * scale;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Direct path: r[j] = N * sum_{n<L} source[(n + j) mod N] * sample[n], the
+// quantity c2r(r2c(source) * conj(r2c(pad(sample)))) equals (reference
+// src/cross_correlation.c:232-239, FFTW's unnormalised c2r).  fp64
+// accumulation, any L.  grid = (ceil(N / 256), n_pairs), block = 256.
+// ---------------------------------------------------------------------------
+constexpr int DIRECT_TILE = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(DIRECT_TILE)
+direct_corr_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
+                   double* __restrict__ r_out, long long L)
+{
+    __shared__ double s_smp[DIRECT_TILE];
+    __shared__ double s_src[2 * DIRECT_TILE];
+    const long long N = 2 * L;
+    const T* src = sources + (size_t)blockIdx.y * (size_t)N;
+    const T* smp = samples + (size_t)blockIdx.y * (size_t)L;
+    const long long j0 = (long long)blockIdx.x * DIRECT_TILE;
+    const int t = threadIdx.x;
+    double acc = 0.0;
+    for (long long n0 = 0; n0 < L; n0 += DIRECT_TILE) {
+        s_smp[t] = (n0 + t < L) ? (double)smp[n0 + t] : 0.0;
+        s_src[t] = (double)src[(j0 + n0 + t) % N];
+        s_src[t + DIRECT_TILE] = (double)src[(j0 + n0 + t + DIRECT_TILE) % N];
+        __syncthreads();
+#pragma unroll 8
+        for (int i = 0; i < DIRECT_TILE; i++) acc = fma(s_smp[i], s_src[t + i], acc);
+        __syncthreads();
+    }
+    if (j0 + t < N) r_out[(size_t)blockIdx.y * (size_t)N + j0 + t] = acc * (double)N;
+}
+
+// Argmax over a double array with the reference's semantics (one CTA / pair).
+struct KeyF64 { double v; long long i; };
+
+__device__ __forceinline__ KeyF64 key_better(KeyF64 a, KeyF64 b) {
+    // larger value wins; equal values -> smaller index wins
+    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+    return a;
+}
+
+__global__ void __launch_bounds__(1024)
+argmax_f64_kernel(const double* __restrict__ r, long long N, PairPeak* __restrict__ peaks)
+{
+    __shared__ double s_v[32];
+    __shared__ long long s_i[32];
+    const double* rp = r + (size_t)blockIdx.x * (size_t)N;
+    const double ninf = -INFINITY, pinf = INFINITY;
+    KeyF64 best; best.v = ninf; best.i = 0x7fffffffffffffffLL;
+    for (long long i = threadIdx.x; i < N; i += blockDim.x) {
+        double x = rp[i];
+        KeyF64 c;
+        c.i = i;
+        if (i == 0) c.v = (x != x) ? pinf : x;
+        else { double a = fabs(x); c.v = (a != a) ? ninf : a; }
+        // a NaN candidate (ninf) must still lose to a real -inf seed on index order only
+        best = key_better(best, c);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        KeyF64 c;
+        c.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+        c.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+        best = key_better(best, c);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { s_v[w] = best.v; s_i[w] = best.i; }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        best.v = (l < nw) ? s_v[l] : ninf;
+        best.i = (l < nw) ? s_i[l] : 0x7fffffffffffffffLL;
+        for (int o = 16; o > 0; o >>= 1) {
+            KeyF64 c;
+            c.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+            c.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+            best = key_better(best, c);
+        }
+        if (l == 0) {
+            PairPeak p;
+            p.key = 0ull;
+            p.raw_index = best.i;
+            p.peak = rp[best.i];
+            p.resolved = 1;
+            p.pad = 0;
+            peaks[blockIdx.x] = p;
+        }
+    }
+}
+
+// Resets the per-pair argmax slot before a transform-path wave.
+__global__ void peaks_reset_kernel(PairPeak* __restrict__ peaks, int n)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        PairPeak p; p.key = 0ull; p.raw_index = 0; p.peak = 0.0; p.resolved = 0; p.pad = 0;
+        peaks[i] = p;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Pearson coefficient of the aligned windows (reference
+// src/cross_correlation.c:74-116 on the windows of :256-271).
+//
+// One pass over the data with fp64 accumulators of the PIVOT-SHIFTED values
+// dx = x - px, dy = y - py, where the pivots are the mean of 32 evenly spaced
+// window samples (identical in every CTA of the pair): the shift removes the
+// cancellation of the textbook one-pass formula without a second read of the
+// window.  All five sums use one fixed reduction tree, so identical windows
+// give cov == varx == vary bit for bit and the quotient is exactly +-1.0, as
+// the reference's two-pass form does (tests/test_pearson_coefficient.c).
+//
+//   partial: grid = (n_chunks, n_pairs), block = 256; chunk c covers window
+//            elements [c * PEARSON_CHUNK, (c + 1) * PEARSON_CHUNK).
+//   final  : grid = n_pairs, block = 32; sums the chunk partials in index
+//            order and writes the audiosync_cuda_result record.
+// ---------------------------------------------------------------------------
+constexpr int PEARSON_CHUNK = 16384;
+constexpr int PEARSON_THREADS = 256;
+
+struct PearsonPartial { double sx, sy, sxx, syy, sxy; };
+
+template <typename T>
+__device__ __forceinline__ void pearson_window(const PairPeak* peaks, int pair, long long L,
+                                               long long explicit_n, Window& w)
+{
+    if (peaks == nullptr) {           // explicit window: whole arrays of length explicit_n
+        w.lag = 0; w.xoff = 0; w.yoff = 0; w.n = explicit_n;
+        return;
+    }
+    PairPeak p = peaks[pair];
+    long long idx = p.resolved ? p.raw_index : (long long)argmax_key_index(p.key);
+    w = fold_index(idx, L);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(PEARSON_THREADS)
+pearson_partial_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
+                       long long src_pitch, long long smp_pitch, long long L,
+                       const PairPeak* __restrict__ peaks, long long explicit_n,
+                       PearsonPartial* __restrict__ partials, int n_chunks)
+{
+    __shared__ double s_piv[2];
+    __shared__ double s_red[PEARSON_THREADS / 32][5];
+    const int pair = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
+    Window w;
+    pearson_window<T>(peaks, pair, L, explicit_n, w);
+    const T* x = sources + (size_t)pair * (size_t)src_pitch + w.xoff;
+    const T* y = samples + (size_t)pair * (size_t)smp_pitch + w.yoff;
+
+    PearsonPartial acc = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const long long lo = (long long)chunk * PEARSON_CHUNK;
+    if (lo < w.n) {
+        if (t < 32) {
+            long long k = ((long long)t * w.n) >> 5;
+            double px = (double)x[k], py = (double)y[k];
+            for (int o = 16; o > 0; o >>= 1) {
+                px += __shfl_xor_sync(0xffffffffu, px, o);
+                py += __shfl_xor_sync(0xffffffffu, py, o);
+            }
+            if (t == 0) { s_piv[0] = px * (1.0 / 32.0); s_piv[1] = py * (1.0 / 32.0); }
+        }
+        __syncthreads();
+        const double px = s_piv[0], py = s_piv[1];
+        long long hi = lo + PEARSON_CHUNK;
+        if (hi > w.n) hi = w.n;
+        for (long long i = lo + t; i < hi; i += PEARSON_THREADS) {
+            double dx = (double)x[i] - px;
+            double dy = (double)y[i] - py;
+            acc.sx += dx;
+            acc.sy += dy;
+            acc.sxx = fma(dx, dx, acc.sxx);
+            acc.syy = fma(dy, dy, acc.syy);
+            acc.sxy = fma(dx, dy, acc.sxy);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        acc.sx += __shfl_xor_sync(0xffffffffu, acc.sx, o);
+        acc.sy += __shfl_xor_sync(0xffffffffu, acc.sy, o);
+        acc.sxx += __shfl_xor_sync(0xffffffffu, acc.sxx, o);
+        acc.syy += __shfl_xor_sync(0xffffffffu, acc.syy, o);
+        acc.sxy += __shfl_xor_sync(0xffffffffu, acc.sxy, o);
+    }
+    const int wid = t >> 5, lane = t & 31;
+    if (lane == 0) {
+        s_red[wid][0] = acc.sx; s_red[wid][1] = acc.sy; s_red[wid][2] = acc.sxx;
+        s_red[wid][3] = acc.syy; s_red[wid][4] = acc.sxy;
+    }
+    __syncthreads();
+    if (t == 0) {
+        PearsonPartial o = {0.0, 0.0, 0.0, 0.0, 0.0};
+        for (int k = 0; k < PEARSON_THREADS / 32; k++) {
+            o.sx += s_red[k][0]; o.sy += s_red[k][1]; o.sxx += s_red[k][2];
+            o.syy += s_red[k][3]; o.sxy += s_red[k][4];
+        }
+        partials[(size_t)pair * n_chunks + chunk] = o;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+pearson_final_kernel(const PearsonPartial* __restrict__ partials, int n_chunks, long long L,
+                     const PairPeak* __restrict__ peaks, long long explicit_n,
+                     audiosync_cuda_result* __restrict__ results)
+{
+    const int pair = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    Window w;
+    long long raw = 0;
+    double peak = 0.0;
+    if (peaks == nullptr) {
+        w.lag = 0; w.xoff = 0; w.yoff = 0; w.n = explicit_n;
+    } else {
+        PairPeak p = peaks[pair];
+        raw = p.resolved ? p.raw_index : (long long)argmax_key_index(p.key);
+        peak = p.peak;
+        w = fold_index(raw, L);
+    }
+    PearsonPartial s = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int c = 0; c < n_chunks; c++) {
+        PearsonPartial q = partials[(size_t)pair * n_chunks + c];
+        s.sx += q.sx; s.sy += q.sy; s.sxx += q.sxx; s.syy += q.syy; s.sxy += q.sxy;
+    }
+    // n == 0 -> 0/0 = NaN, like the reference's empty pointer range.
+    const double n = (double)w.n;
+    const double cov = s.sxy - s.sx * s.sy / n;
+    const double vx = s.sxx - s.sx * s.sx / n;
+    const double vy = s.syy - s.sy * s.sy / n;
+    const double coef = cov / sqrt(vx * vy);
+    audiosync_cuda_result r;
+    r.lag = w.lag;
+    r.coef = coef;
+    r.peak = peak;
+    r.ret = (coef != coef) ? -1 : 0;                       // src/cross_correlation.c:276
+    r.success = (r.ret == 0 && coef >= 0.95) ? 1 : 0;       // src/audiosync.c:254
+    r.raw_index = raw;
+    results[pair] = r;
+}
+
+}  // namespace asc

@@ -1,0 +1,147 @@
+// tests/emu/emu.cu -- CPU emulator of the transform kernels (TEST ONLY).
+//
+// Compiles the *same* kernel bodies the GPU runs (fft_kernels.cuh /
+// fft_small.cuh are written against an executor) with a HostExec that runs
+// every phase for all thread ids in turn.  It lets the CPU suite check the
+// index maps, digit reversal, twiddle tables and the split/multiply/merge
+// against the oracle without a GPU.  It is never linked into the product.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "fft_plan.h"
+
+using namespace asc;
+
+struct HostExec {
+    int bx_, by_, bz_, nt;
+    int bx() const { return bx_; }
+    int by() const { return by_; }
+    int bz() const { return bz_; }
+    template <class F>
+    void phase(F&& f) {
+        for (int t = 0; t < nt; t++) f(t);
+    }
+    template <class F>
+    void phase_argmax(F&& f, unsigned long long* dst) {
+        unsigned long long best = 0;
+        for (int t = 0; t < nt; t++) {
+            unsigned long long k = f(t);
+            if (k > best) best = k;
+        }
+        if (best > *dst) *dst = best;
+    }
+};
+
+template <class P, typename InT>
+static int run_static(const InT* source, const InT* sample, PairPeak* peak, cplx* planes_out) {
+    using Col = typename P::Col;
+    using Row = typename P::Row;
+    constexpr int M1 = Col::n, M2 = Row::n;
+    const long long M = P::L;
+    std::vector<cplx> planes(2 * M);
+    std::vector<cplx> col_tw = build_pass_tables(radix_vector<Col>());
+    std::vector<cplx> row_tw = build_pass_tables(radix_vector<Row>());
+    std::vector<cplx> m_lo, m_hi, n_lo, n_hi;
+    build_two_level(M, M - 1, m_lo, m_hi);
+    build_two_level(2 * M, M, n_lo, n_hi);
+    peak->key = 0; peak->resolved = 0; peak->raw_index = 0; peak->peak = 0;
+
+    {
+        using K = ColFwdKernel<Col, P::NT_COL, InT>;
+        typename K::Params p{source, sample, planes.data(), col_tw.data(), m_lo.data(), m_hi.data(), M, M2};
+        std::vector<cplx> smem(K::SMEM / sizeof(cplx));
+        for (int sig = 0; sig < 2; sig++)
+            for (int tile = 0; tile < M2 / COL_T; tile++) {
+                HostExec ex{tile, sig, 0, K::THREADS};
+                K::run(ex, p, smem.data());
+            }
+    }
+    {
+        using K = RowFusedKernel<Row, P::NT_ROW>;
+        typename K::Params p{planes.data(), row_tw.data(), m_lo.data(), m_hi.data(), n_lo.data(), n_hi.data(), M, M1};
+        std::vector<cplx> smem(K::SMEM / sizeof(cplx));
+        for (int r = 0; r <= M1 / 2; r++) {
+            HostExec ex{r, 0, 0, K::THREADS};
+            K::run(ex, p, smem.data());
+        }
+    }
+    if (planes_out) memcpy(planes_out, planes.data(), sizeof(cplx) * M);
+    {
+        using K = ColInvKernel<Col, P::NT_COL>;
+        typename K::Params p{planes.data(), peak, col_tw.data(), M, M2};
+        std::vector<cplx> smem(K::SMEM / sizeof(cplx));
+        for (int tile = 0; tile < M2 / COL_T; tile++) {
+            HostExec ex{tile, 0, 0, K::THREADS};
+            K::run(ex, p, smem.data());
+        }
+    }
+    return 0;
+}
+
+template <typename InT>
+static int run_small(const InT* source, const InT* sample, long long L, PairPeak* peak) {
+    SmallPlan pl;
+    if (!make_small_plan(L, &pl)) return -1;
+    std::vector<cplx> wm = build_full_table(L, L), wn = build_full_table(2 * L, L);
+    using K = SmallXcorrKernel<InT>;
+    typename K::Params p{source, sample, peak, wm.data(), wn.data(), pl};
+    std::vector<cplx> smem(K::smem_bytes((int)L) / sizeof(cplx));
+    peak->key = 0; peak->resolved = 0;
+    HostExec ex{0, 0, 0, K::THREADS};
+    K::run(ex, p, smem.data());
+    return 0;
+}
+
+template <typename InT>
+static int emu_any(const InT* source, const InT* sample, long long L, int forced,
+                   long long* raw_index, double* peak_value, int* path) {
+    PairPeak pk;
+    memset(&pk, 0, sizeof(pk));
+    PathKind kind = choose_path(L, forced);
+    *path = (int)kind;
+    int rc = -1;
+    if (kind == PATH_STATIC_FFT) {
+        for_each_static_plan([&](auto P) {
+            using PT = decltype(P);
+            if (PT::L == L) rc = run_static<PT, InT>(source, sample, &pk, nullptr);
+        });
+    } else if (kind == PATH_SMALL_FFT) {
+        rc = run_small<InT>(source, sample, L, &pk);
+    } else {
+        return -2;   // direct path has no transform to emulate
+    }
+    if (rc != 0) return rc;
+    *raw_index = (long long)argmax_key_index(pk.key);
+    *peak_value = (double)argmax_key_value(pk.key);
+    return 0;
+}
+
+extern "C" {
+
+int emu_xcorr_f32(const float* source, const float* sample, long long L, int forced,
+                  long long* raw_index, double* peak_value, int* path) {
+    return emu_any<float>(source, sample, L, forced, raw_index, peak_value, path);
+}
+
+int emu_xcorr_f64(const double* source, const double* sample, long long L, int forced,
+                  long long* raw_index, double* peak_value, int* path) {
+    return emu_any<double>(source, sample, L, forced, raw_index, peak_value, path);
+}
+
+// fold of reference src/cross_correlation.c:256-271 as compiled into the product
+void emu_fold(long long idx, long long L, long long* lag, long long* xoff, long long* yoff,
+              long long* n) {
+    Window w = fold_index(idx, L);
+    *lag = w.lag; *xoff = w.xoff; *yoff = w.yoff; *n = w.n;
+}
+
+// argmax key helpers, for semantics tests
+unsigned long long emu_key_abs(float v, unsigned idx) { return argmax_key_abs(v, idx); }
+unsigned long long emu_key_seed(float v) { return argmax_key_seed(v); }
+unsigned emu_key_index(unsigned long long k) { return argmax_key_index(k); }
+float emu_key_value(unsigned long long k) { return argmax_key_value(k); }
+
+int emu_path_for(long long L, int forced) { return (int)choose_path(L, forced); }
+}

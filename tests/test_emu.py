@@ -1,0 +1,139 @@
+"""CPU emulation of the CUDA kernel bodies vs the oracle -- runs without a GPU.
+
+tests/emu compiles the same kernel source the GPU runs (ColFwd / RowFused /
+ColInv / SmallXcorr in old-audiosync_b200/csrc) against a host executor.  This
+checks the product's index maps, digit reversal, twiddle tables, real-FFT
+split/merge and argmax keys for every static plan (all six lengths of the
+reference's interval schedule, src/audiosync.c:50-57) and for short lengths.
+"""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import capi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SYNTH = json.load(open(os.path.join(HERE, "golden", "synth.json")))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    path = os.path.join(HERE, "emu", "libasc_emu.so")
+    subprocess.run(["make", "-C", os.path.join(HERE, "emu")], check=True, stdout=subprocess.DEVNULL)
+    E = C.CDLL(path)
+    sig = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.POINTER(C.c_longlong),
+           C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    E.emu_xcorr_f32.argtypes = sig
+    E.emu_xcorr_f64.argtypes = sig
+    E.emu_fold.argtypes = [C.c_longlong, C.c_longlong] + [C.POINTER(C.c_longlong)] * 4
+    E.emu_key_abs.restype = C.c_ulonglong
+    E.emu_key_abs.argtypes = [C.c_float, C.c_uint]
+    E.emu_key_seed.restype = C.c_ulonglong
+    E.emu_key_seed.argtypes = [C.c_float]
+    E.emu_key_index.restype = C.c_uint
+    E.emu_key_index.argtypes = [C.c_ulonglong]
+    E.emu_key_value.restype = C.c_float
+    E.emu_key_value.argtypes = [C.c_ulonglong]
+    E.emu_path_for.argtypes = [C.c_longlong, C.c_int]
+    return E
+
+
+PATH_AUTO, PATH_FFT = 0, 1
+
+
+def run_emu(E, src, smp, f64=False, forced=PATH_FFT):
+    L = len(smp)
+    idx, pk, path = C.c_longlong(), C.c_double(), C.c_int()
+    dt = np.float64 if f64 else np.float32
+    s = np.ascontiguousarray(src, dt); p = np.ascontiguousarray(smp, dt)
+    fn = E.emu_xcorr_f64 if f64 else E.emu_xcorr_f32
+    rc = fn(s.ctypes.data, p.ctypes.data, L, forced, C.byref(idx), C.byref(pk), C.byref(path))
+    assert rc == 0
+    return idx.value, pk.value, path.value
+
+
+def _fft_cases():
+    out = []
+    for c in SYNTH["cases"]:
+        if c["L"] % 2 == 0 and c["tag"] == "pair" and c["pair_id"] in (0, 3):
+            out.append(c)
+    return out
+
+
+@pytest.mark.parametrize("case", _fft_cases(), ids=lambda c: "L%d-p%d" % (c["L"], c["pair_id"]))
+def test_emulated_kernels_match_golden(emu, case):
+    L = case["L"]
+    path = emu.emu_path_for(L, PATH_FFT)
+    if path == 2:
+        pytest.skip("length has no FFT plan (direct path: nothing to emulate)")
+    src, smp = capi.synth_pair(case["seed"], case["pair_id"], L)
+    idx, peak, used = run_emu(emu, src, smp, f64=(case["pair_id"] == 3))
+    assert used == path
+    assert case["margin"] > 1e-4                     # unique peak => index must be exact
+    assert idx == case["raw_index"]
+    assert abs(peak - case["peak"]) <= 1e-4 * abs(case["peak"])
+    # the fold compiled into the product gives the reference's lag
+    lag, xo, yo, n = (C.c_longlong() for _ in range(4))
+    emu.emu_fold(idx, L, C.byref(lag), C.byref(xo), C.byref(yo), C.byref(n))
+    assert lag.value == case["lag"]
+
+
+def test_static_plans_cover_interval_schedule(emu):
+    for L in (144000, 288000, 480000, 720000, 960000, 1440000):
+        assert emu.emu_path_for(L, PATH_AUTO) == 0          # PATH_STATIC_FFT
+    for L in (4096, 4320, 5000, 6250, 8192):
+        assert emu.emu_path_for(L, PATH_AUTO) == 1          # PATH_SMALL_FFT
+    for L in (2, 6, 10, 12, 1000, 2000):
+        assert emu.emu_path_for(L, PATH_AUTO) == 2          # short: fp64 direct by default
+        assert emu.emu_path_for(L, PATH_FFT) == 1           # ... FFT when asked for
+    for L in (1, 5, 7, 14, 4374 * 2 + 1, 24000, 10 ** 6):
+        assert emu.emu_path_for(L, PATH_AUTO) == 2          # PATH_DIRECT
+        assert emu.emu_path_for(L, PATH_FFT) == 2
+
+
+@pytest.mark.parametrize("L", [2, 4, 6, 8, 10, 12, 16, 18, 20, 30, 36, 48, 50, 100, 250, 486, 1000,
+                               1024, 2000, 3600, 4096, 6250, 8192])
+def test_small_path_against_oracle(emu, L):
+    for pid in (0, 1, 2):
+        src, smp = capi.synth_pair(0xABCD, pid, L)
+        o = capi.cross_correlation(src, smp)
+        idx, peak, used = run_emu(emu, src, smp)
+        assert used == 1
+        margin = (abs(o["peak"]) - o["second"]) / abs(o["peak"])
+        if margin > 1e-4:
+            assert idx == o["raw_index"]
+            assert abs(peak - o["peak"]) <= 1e-4 * abs(o["peak"])
+
+
+def test_kat_sine_cases_through_emulator(emu):
+    # reference tests/test_cross_correlation.c T7, T8 (L = 1000)
+    # T7 (sin(i) vs sin(i)) has peaks at 0 and 710 (= 113 * 2pi + 6e-5) that differ by
+    # 1.2e-9 relative: only the fp64 direct path, AUTO's choice at L = 1000, can
+    # separate them.  The fp32 transform must still land on one of the two.
+    p7 = np.sin(np.arange(1000.0))
+    idx, _, _ = run_emu(emu, np.sin(np.arange(2000.0)), p7, f64=True)
+    assert idx in (0, 710)
+    s8 = np.concatenate([np.sin(np.arange(1000.0) + 180), np.zeros(1000)])
+    idx, peak, _ = run_emu(emu, s8, p7, f64=True)
+    assert idx == 1999 and peak < 0               # lag -1, negative correlation
+
+
+def test_argmax_key_semantics(emu):
+    # reference src/cross_correlation.c:52-67 as a max-reduction over packed keys
+    ka, ks, ki, kv = emu.emu_key_abs, emu.emu_key_seed, emu.emu_key_index, emu.emu_key_value
+    nan = float("nan")
+    assert ks(5.0) > ka(-5.0, 1) and ks(5.0) > ka(5.0, 7)         # ties keep index 0
+    assert ka(1.0, 3) > ka(-1.0, 4) and ka(-1.0, 3) > ka(1.0, 4)   # ties keep the earlier index
+    assert ka(0.0, 1) > ks(-5.0) and ka(0.0, 1) > ks(-0.5)         # negative seed loses to |0|
+    assert ks(0.0) > ka(0.0, 1) and ks(-0.0) > ka(-0.0, 1)         # all-zero -> index 0
+    assert ka(nan, 1) < ks(-1e30) and ka(nan, 1) < ka(0.0, 2)      # NaN never wins
+    assert ks(nan) > ka(float("inf"), 1)                           # NaN seed is never beaten
+    assert ka(2.0, 9) > ka(1.5, 1)
+    for v, i in ((3.5, 1), (-2.25, 12345), (1e-30, 2 ** 22), (-7.0, 2879999)):
+        k = ka(v, i)
+        assert ki(k) == i and kv(k) == np.float32(v)
+    assert ki(ks(-4.0)) == 0 and kv(ks(-4.0)) == -4.0

@@ -1,0 +1,363 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle, the committed
+golden vectors of the compiled reference, and size-independent properties.
+
+Tolerances (BASELINE.json north_star): lag index bit-exact and ret / success
+identical wherever the oracle's peak is unique (margin > 1e-4 of the peak);
+peak correlation value and Pearson coefficient within 1e-4 relative.
+"""
+import json
+import math
+import os
+import threading
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KAT = json.load(open(os.path.join(HERE, "golden", "kat.json")))
+SYNTH = json.load(open(os.path.join(HERE, "golden", "synth.json")))
+RTOL = 1e-4
+SEED = 0x5EED
+
+
+@pytest.fixture(scope="module")
+def ac():
+    import audiosync_cuda
+    audiosync_cuda.lib()
+    return audiosync_cuda
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from oracle import capi
+    return capi
+
+
+@pytest.fixture(scope="module")
+def ctx(ac):
+    c = ac.Context([0])
+    yield c
+    c.close()
+
+
+def close(a, b, rtol=RTOL):
+    if a != a or b != b:
+        return a != a and b != b
+    return abs(a - b) <= rtol * max(abs(a), abs(b), 1e-300)
+
+
+def kat_inputs(rec):
+    if rec["name"] == "T7":
+        return np.sin(np.arange(2000.0)), np.sin(np.arange(1000.0))
+    if rec["name"] == "T8":
+        src = np.concatenate([np.array([math.sin(i + 180) for i in range(1000)]), np.zeros(1000)])
+        return src, np.array([math.sin(i) for i in range(1000)])
+    return np.array(rec["source"], float), np.array(rec["sample"], float)
+
+
+# ------------------------------------------------------------------ reference KATs
+
+@pytest.mark.parametrize("rec", KAT["cross_correlation"], ids=lambda r: r["name"])
+def test_kat_cross_correlation_dropin(ac, rec):
+    """reference tests/test_cross_correlation.c:13-116 through the unchanged C signature."""
+    src, smp = kat_inputs(rec)
+    ret, lag, coef = ac.cross_correlation(src, smp)
+    exp = rec["expect"]
+    assert ret == exp["ret"]
+    if "lag" in exp:
+        assert lag == exp["lag"]
+    if "coef_eq" in exp:
+        assert coef == exp["coef_eq"]            # exact 1.0, as the reference asserts
+    if "coef_gt" in exp:
+        assert coef > exp["coef_gt"]
+    if "coef_lt" in exp:
+        assert coef < exp["coef_lt"]
+    if rec["ref"]["coef"] is None:
+        assert coef != coef
+    else:
+        assert close(coef, rec["ref"]["coef"])
+
+
+@pytest.mark.parametrize("rec", KAT["pearson"], ids=lambda r: r["name"])
+def test_kat_pearson_dropin(ac, rec):
+    """reference tests/test_pearson_coefficient.c:13-61 (exact equality)."""
+    v = ac.pearson_coefficient(np.array(rec["x"]), np.array(rec["y"]))
+    if rec["expect"].get("nan"):
+        assert v != v
+    else:
+        assert v == rec["expect"]["eq"]
+
+
+# ------------------------------------------------------------------ golden vectors
+
+def _pairs():
+    return [c for c in SYNTH["cases"] if c["tag"] == "pair"]
+
+
+@pytest.mark.parametrize("case", _pairs(), ids=lambda c: "L%d-p%d" % (c["L"], c["pair_id"]))
+def test_golden_dropin_f64(ac, capi, case):
+    """cross_correlation(double*, ...) vs the compiled reference's recorded outputs."""
+    src, smp = capi.synth_pair(case["seed"], case["pair_id"], case["L"])
+    ret, lag, coef = ac.cross_correlation(src, smp)
+    assert case["margin"] > 1e-4
+    assert ret == case["ret"] and lag == case["lag"]
+    assert close(coef, case["coef"])
+    assert (ret == 0 and coef >= ac.MIN_CONFIDENCE) == case["success"]
+
+
+def _batch_on_device(ac, ctx, seed, first, n, L, dtype=None):
+    import torch
+    dtype = ac.F32 if dtype is None else dtype
+    tdt = torch.float32 if dtype == ac.F32 else torch.float64
+    d_src = torch.empty(n * 2 * L, dtype=tdt, device="cuda:0")
+    d_smp = torch.empty(n * L, dtype=tdt, device="cuda:0")
+    d_res = torch.zeros(n * ac.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda:0")
+    ctx.synth_pairs(0, seed, first, n, L, dtype, d_src.data_ptr(), d_smp.data_ptr())
+    ctx.xcorr_batch_device(0, d_src.data_ptr(), d_smp.data_ptr(), n, L, dtype, d_res.data_ptr())
+    ctx.synchronize(0)
+    return d_res.cpu().numpy().view(ac.RESULT_DTYPE), d_src, d_smp
+
+
+@pytest.mark.parametrize("L", [144000, 288000, 480000, 720000, 960000, 1440000])
+def test_golden_batch_device_f32(ac, ctx, L):
+    """Device-resident fp32 batch (the headline configuration) vs golden, all six interval sizes."""
+    cases = {c["pair_id"]: c for c in _pairs() if c["L"] == L}
+    n = max(cases) + 1
+    res, _, _ = _batch_on_device(ac, ctx, SEED, 0, n, L)
+    for pid, c in cases.items():
+        r = res[pid]
+        assert int(r["raw_index"]) == c["raw_index"] and int(r["lag"]) == c["lag"]
+        assert int(r["ret"]) == c["ret"] and bool(r["success"]) == c["success"]
+        assert close(float(r["coef"]), c["coef"]) and close(float(r["peak"]), c["peak"])
+
+
+def test_device_generator_is_bit_identical(ac, ctx, capi):
+    import torch
+    L, n = 6000, 5
+    for dtype, npdt in ((ac.F32, np.float32), (ac.F64, np.float64)):
+        _, d_src, d_smp = _batch_on_device(ac, ctx, SEED + 7, 3, n, L, dtype)
+        hs = d_src.cpu().numpy().reshape(n, 2 * L); hp = d_smp.cpu().numpy().reshape(n, L)
+        for i in range(n):
+            s, p = capi.synth_pair(SEED + 7, 3 + i, L, npdt)
+            assert np.array_equal(hs[i], s) and np.array_equal(hp[i], p)
+
+
+# ------------------------------------------------------------------ oracle, many shapes
+
+@pytest.mark.parametrize("L", [1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12, 50, 63, 64, 250, 255, 256, 257, 1000, 1001, 2187])
+def test_short_and_odd_lengths_vs_oracle(ac, capi, L):
+    """Arbitrary sample_len > 0 (primes, odd, tiny) -- the universal direct path."""
+    for pid in range(4):
+        src, smp = capi.synth_pair(SEED + 1, pid, L)
+        o = capi.cross_correlation(src, smp)
+        ret, lag, coef = ac.cross_correlation(src, smp)
+        margin = (abs(o["peak"]) - o["second"]) / abs(o["peak"]) if o["peak"] != 0 else 0.0
+        assert ret == o["ret"]
+        if margin > 1e-4:
+            assert lag == o["lag"]
+            assert close(coef, o["coef"])
+
+
+@pytest.mark.parametrize("L", [64, 250, 1000, 1024, 3600, 4096, 6000, 8192])
+def test_small_fft_path_vs_direct_and_oracle(ac, capi, L):
+    """Single-CTA FFT kernel (forced) and the direct kernel agree with the oracle."""
+    n = 6
+    srcs = np.empty((n, 2 * L), np.float32); smps = np.empty((n, L), np.float32)
+    for i in range(n):
+        srcs[i], smps[i] = capi.synth_pair(SEED + 2, i, L, np.float32)
+    outs = {}
+    for path in (ac.PATH_FFT, ac.PATH_DIRECT):
+        with ac.Context([0]) as c:
+            c.set_path(path)
+            desc = c.describe_plan(L)
+            assert desc.startswith("fft" if path == ac.PATH_FFT else "direct"), desc
+            outs[path] = c.xcorr_batch(srcs, smps)
+    for i in range(n):
+        o = capi.cross_correlation(srcs[i].astype(np.float64), smps[i].astype(np.float64))
+        for path in outs:
+            r = outs[path]
+            assert r["lags"][i] == o["lag"] and r["rets"][i] == o["ret"]
+            assert close(r["coefs"][i], o["coef"]) and close(r["peaks"][i], o["peak"])
+
+
+def test_all_zero_sample_and_constant_inputs(ac):
+    L = 1000
+    src = np.arange(2 * L, dtype=np.float64)
+    ret, lag, coef = ac.cross_correlation(src, np.zeros(L))
+    assert ret == -1 and lag == 0 and coef != coef         # T2 at a larger size
+    ret, lag, coef = ac.cross_correlation(np.ones(2 * L), np.ones(L))
+    assert ret == -1 and coef != coef                      # zero variance -> NaN gate
+
+
+def test_fold_boundary_idx_equals_L(ac, capi):
+    """idx == L => empty Pearson window => NaN => -1 with lag = -L written (cross_correlation.c:256-276)."""
+    for L in (8, 1000, 4096):
+        src = np.zeros(2 * L); smp = np.zeros(L)
+        smp[0] = 1.0; src[L] = 1.0
+        o = capi.cross_correlation(src, smp)
+        ret, lag, coef = ac.cross_correlation(src, smp)
+        assert (ret, lag) == (o["ret"], o["lag"]) == (-1, -L) and coef != coef
+
+
+def test_argmax_ties_and_sign_semantics(ac, capi):
+    """max_abs_index (cross_correlation.c:52-67): first index wins ties; r[0] enters signed."""
+    L = 9   # odd -> direct fp64 path, exact arithmetic on these integers
+    smp = np.zeros(L); smp[0] = 1.0
+    src = np.zeros(2 * L); src[3] = 2.0; src[11] = -2.0            # |r[3]| == |r[11]|
+    o = capi.cross_correlation(src, smp)
+    ret, lag, coef = ac.cross_correlation(src, smp)
+    assert o["raw_index"] == 3 and (ret, lag) == (o["ret"], o["lag"])
+    src = np.zeros(2 * L); src[0] = -5.0; src[4] = 1.0              # r[0] < 0 never wins
+    o = capi.cross_correlation(src, smp)
+    ret, lag, coef = ac.cross_correlation(src, smp)
+    assert o["raw_index"] == 4 and (ret, lag) == (o["ret"], o["lag"])
+    src = np.zeros(2 * L); src[0] = 5.0; src[4] = -5.0              # r[0] >= |r[i]| keeps index 0
+    o = capi.cross_correlation(src, smp)
+    ret, lag, coef = ac.cross_correlation(src, smp)
+    assert o["raw_index"] == 0 and (ret, lag) == (o["ret"], o["lag"])
+
+
+# ------------------------------------------------------------------ interval schedule (config 2)
+
+@pytest.mark.parametrize("pid", [0, 6])
+def test_interval_schedule_vs_golden(ac, capi, pid):
+    """src/audiosync.c:226-259 on one full-length pair: per-interval (ret, lag, coef, success)."""
+    cases = [c for c in SYNTH["cases"] if c["tag"] == "interval-prefix" and c["pair_id"] == pid]
+    src, smp = capi.synth_pair(cases[0]["seed"], pid, 1440000)
+    out = ac.interval_loop(src, smp)
+    first_ok = next(i for i, c in enumerate(cases) if c["success"])
+    assert out["n"] == first_ok + 1 and out["final_ret"] == 0
+    for i in range(out["n"]):
+        c = cases[i]
+        assert out["rets"][i] == c["ret"] and bool(out["succ"][i]) == c["success"]
+        if c["margin"] > 1e-4:
+            assert out["lags"][i] == c["lag"]
+            assert abs(out["coefs"][i] - c["coef"]) <= max(RTOL * abs(c["coef"]), 1e-6)
+    assert out["final_lag"] == ac.frames_to_ms(cases[first_ok]["lag"])
+    # every interval individually, also past the first success
+    for c in cases:
+        ret, lag, coef = ac.cross_correlation(src[:2 * c["L"]], smp[:c["L"]])
+        assert ret == c["ret"] and (ret == 0 and coef >= 0.95) == c["success"]
+        if c["margin"] > 1e-4:
+            assert lag == c["lag"]
+
+
+# ------------------------------------------------------------------ host batch API
+
+@pytest.mark.parametrize("npdt", [np.float32, np.float64])
+def test_host_batch_api(ac, ctx, capi, npdt):
+    L, n = 144000, 7
+    srcs = np.empty((n, 2 * L), npdt); smps = np.empty((n, L), npdt)
+    for i in range(n):
+        srcs[i], smps[i] = capi.synth_pair(SEED, i, L, npdt)
+    r = ctx.xcorr_batch(srcs, smps)
+    gold = {c["pair_id"]: c for c in _pairs() if c["L"] == L}
+    for i in range(n):
+        assert r["lags"][i] == capi.synth_true_lag(SEED, i, L)
+        if i in gold:
+            assert r["rets"][i] == gold[i]["ret"] and close(r["coefs"][i], gold[i]["coef"])
+            assert close(r["peaks"][i], gold[i]["peak"])
+
+
+def test_host_batch_multi_chunk_and_wave_sizes(ac, capi):
+    """More pairs than one upload chunk / one kernel wave; every wave size gives the same answer."""
+    L, n = 6000, 300
+    srcs = np.empty((n, 2 * L), np.float32); smps = np.empty((n, L), np.float32)
+    for i in range(n):
+        srcs[i], smps[i] = capi.synth_pair(SEED + 3, i, L, np.float32)
+    base = None
+    for wave in (0, 1, 7, 64):
+        with ac.Context([0]) as c:
+            c.set_wave_pairs(wave)
+            r = c.xcorr_batch(srcs, smps)
+        for i in range(n):
+            assert r["lags"][i] == capi.synth_true_lag(SEED + 3, i, L)
+        if base is None:
+            base = r
+        else:
+            for k in base:
+                assert np.array_equal(base[k], r[k], equal_nan=True)   # deterministic
+
+
+# ------------------------------------------------------------------ full-size properties
+
+def test_full_size_batch_recovers_injected_lags(ac, ctx, capi):
+    """L = 1,440,000 (BASELINE configs 3-5): a batch generated on the device; the recovered
+    lag must equal the injected one and success must follow the generator's noise level."""
+    L, n, first = 1440000, 48, 100
+    res, _, _ = _batch_on_device(ac, ctx, SEED, first, n, L)
+    for i in range(n):
+        pid = first + i
+        assert int(res["lag"][i]) == capi.synth_true_lag(SEED, pid, L)
+        assert int(res["ret"][i]) == 0
+        assert bool(res["success"][i]) == (pid % 4 != 3)
+        c = float(res["coef"][i])
+        assert (0.994 < c < 0.996) if pid % 4 != 3 else (0.79 < c < 0.81)
+
+
+def test_scaling_and_negation_properties(ac, ctx, capi):
+    """r is bilinear: scaling the sample by a power of two scales the peak exactly and leaves
+    lag and coefficient unchanged; negating it flips the peak sign and the coefficient."""
+    L = 480000
+    src, smp = capi.synth_pair(SEED, 5, L, np.float32)
+    srcs = np.stack([src, src, src]); smps = np.stack([smp, smp * np.float32(4.0), -smp])
+    r = ctx.xcorr_batch(srcs, smps)
+    assert r["lags"][0] == r["lags"][1] == r["lags"][2]
+    assert r["peaks"][1] == 4.0 * r["peaks"][0] and r["peaks"][2] == -r["peaks"][0]
+    assert close(r["coefs"][1], r["coefs"][0], 1e-12) and close(r["coefs"][2], -r["coefs"][0], 1e-12)
+
+
+def test_identical_windows_give_exactly_one(ac, capi):
+    """coef == 1.0 exactly when the windows are identical (reference T1 at real sizes)."""
+    for L in (1000, 144000):
+        src, _ = capi.synth_pair(SEED, 2, L)
+        for lag in (0, 17):
+            smp = src[lag:lag + L].copy()
+            ret, got, coef = ac.cross_correlation(src, smp)
+            assert ret == 0 and got == lag and coef == 1.0
+
+
+# ------------------------------------------------------------------ allocator + threads
+
+def test_pinned_allocator_roundtrip(ac, capi):
+    import ctypes
+    L = 144000
+    lib = ac.lib()
+    p = lib.fftw_alloc_real(2 * L)
+    assert p
+    buf = np.ctypeslib.as_array((ctypes.c_double * (2 * L)).from_address(p))
+    src, smp = capi.synth_pair(SEED, 0, L)
+    buf[:] = src
+    ret, lag, coef = ac.cross_correlation(buf, smp)
+    assert ret == 0 and lag == capi.synth_true_lag(SEED, 0, L)
+    del buf
+    lib.fftw_free(p)
+
+
+def test_concurrent_callers(ac, capi):
+    L = 144000
+    pairs = [capi.synth_pair(SEED, i, L) for i in range(4)]
+    out = [None] * 4
+
+    def work(i):
+        out[i] = ac.cross_correlation(*pairs[i])
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(4):
+        assert out[i][0] == 0 and out[i][1] == capi.synth_true_lag(SEED, i, L)
+
+
+def test_profile_and_launch_accounting(ac, capi):
+    L, n = 144000, 16
+    with ac.Context([0]) as c:
+        c.profile_enable(True)
+        before = c.launch_count()
+        res, _, _ = _batch_on_device(ac, c, SEED, 0, n, L)
+        prof = c.profile_read()
+        assert c.launch_count() > before
+    for k in ("col_fwd", "row_fused", "col_inv_argmax", "pearson_partial", "pearson_final"):
+        assert prof[k][0] >= 1 and prof[k][1] > 0.0, (k, prof)
