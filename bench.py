@@ -1,0 +1,372 @@
+#!/usr/bin/env python3
+"""Benchmark of the FFT cross-correlation hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Metric (BASELINE.json): xcorr pairs/sec at L = 1,440,000 (N = 2,880,000), batched.
+A step is one pass of the whole path (forward FFTs, conj-multiply, inverse FFT,
+|r| argmax, fold, Pearson) over one batch of device-resident fp32 pairs --
+config[3]: 4,096 pairs per GPU.  With N GPUs every rank owns its own 4,096
+pairs (pairs are independent: no collective on the data path), so the N = 8 run
+is config[4] (32,768 pairs) and scaling is weak.  torch / torch.distributed are
+used for device buffers, the barrier and the max-over-ranks only.
+
+The printed JSON line carries, besides the base contract:
+  roofline      -- dominant kernel: algorithmic bytes per launch / its average
+                   launch duration (CUDA events around every launch, on its own
+                   stream, inside the timed region) vs MEASURED_PEAKS.json;
+  path_roofline -- the whole path: SURVEY 8(d)'s 21*L*4 bytes/pair * pairs/s;
+  e2e           -- the same metric through the host-facing C-ABI batch call with
+                   pinned HOST buffers (uploads and result download timed);
+  cpu_baseline  -- the reference's CPU path (oracle/_ref, FFT shim) on this box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "old-audiosync_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+L_HEADLINE = 1440000
+PAIRS_PER_GPU = 4096
+SEED = 0x5EED + 4          # seed + config number
+METRIC = "xcorr_pairs_per_sec_L1440000"
+UNIT = "pairs/s"
+
+# Algorithmic bytes per pair, in units of U = L * 4 bytes (fp32 device-resident).
+# SURVEY 8(d) schedule: 21 U for the whole path.  Per kernel of THIS design:
+#   col_fwd   reads 2U (source) + 1U (sample, zero half never read), writes 4U      = 7 U
+#   row_fused reads 4U (both planes), writes 2U (product rows, in place)           = 6 U
+#   col_inv   reads 2U                                                             = 2 U
+#   pearson   reads 2U (the two windows)                                           = 2 U
+KERNEL_U = {"col_fwd": 7, "row_fused": 6, "col_inv_argmax": 2, "pearson_partial": 2}
+PATH_U = 21
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU per step")
+    ap.add_argument("--sample-len", type=int, default=L_HEADLINE)
+    ap.add_argument("--e2e-pairs", type=int, default=192)
+    ap.add_argument("--wave", type=int, default=0, help="pairs per kernel wave (0 = library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # samples under load = upper half of the observed clocks
+        sm_load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(sm_load) if sm_load else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference arm / CPU baseline
+
+def cpu_reference_run(sample_len: int, n_pairs: int, threads: int, seed: int):
+    """Times the reference's CPU path on n_pairs seeded pairs with `threads` concurrent callers.
+
+    Uses oracle/_ref (the reference's own src/cross_correlation.c compiled against the
+    FFT shim; kind "reference") when that build is present, else the restatement
+    (kind "port").  Returns (seconds, kind, backend, lags).
+    """
+    import numpy as np
+    from oracle import capi
+    ref = capi.ref_lib()
+    kind = "reference" if ref is not None else "port"
+    lags = [None] * n_pairs
+    inputs = [capi.synth_pair(seed, i, sample_len) for i in range(n_pairs)]   # outside the timing
+
+    def work(tid):
+        for i in range(tid, n_pairs, threads):
+            s, p = inputs[i]
+            if ref is not None:
+                lags[i] = capi.ref_cross_correlation(s, p)[1]
+            else:
+                lags[i] = capi.cross_correlation(s, p)["lag"]
+
+    if n_pairs:                       # warm the shim's twiddle cache like a long-lived process
+        s, p = inputs[0]
+        (capi.ref_cross_correlation if ref is not None else capi.cross_correlation)(s, p)
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    dt = time.perf_counter() - t0
+    for i in range(n_pairs):
+        assert lags[i] == capi.synth_true_lag(seed, i, sample_len), "CPU reference lost a lag"
+    return dt, kind, capi.backend(), lags
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    L = args.sample_len
+    cores = os.cpu_count() or 1
+    # the reference runs two FFT threads per call: nproc/2 concurrent callers use every core
+    callers = max(1, cores // 2)
+    per_step = max(2 * callers, 8)
+    for _ in range(args.warmup):
+        cpu_reference_run(L, callers, callers, SEED)
+    times = []
+    kind = backend = None
+    for _ in range(args.steps):
+        dt, kind, backend, _ = cpu_reference_run(L, per_step, callers, SEED)
+        times.append(dt)
+    total = sum(times)
+    value = per_step * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (seeded integer generator, SURVEY 8d)",
+        "config": {"workload": "reference CPU path (src/cross_correlation.c) on %d-pair samples of "
+                               "config[3]: L=%d, N=%d" % (per_step, L, 2 * L),
+                   "sample_len": L, "pairs_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "%d pairs/step x %d steps, %d concurrent callers x 2 FFT threads, "
+                                   "FFT backend %s (stand-in for FFTW3, which is not installed)"
+                                   % (per_step, args.steps, callers, backend)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ our arm
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import audiosync_cuda as ac
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    L, n = args.sample_len, args.pairs
+    U = L * 4
+    first_pair = rank * n                      # contiguous block split of the pair ids
+    ctx = ac.Context([local])
+    if args.wave:
+        ctx.set_wave_pairs(args.wave)
+    plan = ctx.describe_plan(L)
+
+    d_src = torch.empty(n * 2 * L, dtype=torch.float32, device=dev)
+    d_smp = torch.empty(n * L, dtype=torch.float32, device=dev)
+    d_res = torch.zeros(n * ac.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    ctx.synth_pairs(local, SEED, first_pair, n, L, ac.F32, d_src.data_ptr(), d_smp.data_ptr(),
+                    stream.cuda_stream)
+    torch.cuda.synchronize(dev)
+
+    def step():
+        ctx.xcorr_batch_device(local, d_src.data_ptr(), d_smp.data_ptr(), n, L, ac.F32,
+                               d_res.data_ptr(), stream.cuda_stream)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count() - launches0
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+
+    # correctness of what was timed: every pair recovers its injected lag
+    res = d_res.cpu().numpy().view(ac.RESULT_DTYPE)
+    from oracle import capi   # checker only (synth_true_lag), never the thing measured
+    bad = sum(1 for i in range(0, n, max(1, n // 256))
+              if int(res["lag"][i]) != capi.synth_true_lag(SEED, first_pair + i, L))
+    ok_flags = int(res["success"].sum())
+
+    t = torch.tensor([ms, float(launches), float(bad)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, launches, bad = float(tmax[0]), int(tsum[1]), int(tsum[2])
+    value = world * n * args.steps / (ms * 1e-3)
+
+    # ---- end to end: host-facing C-ABI batch call, pinned host buffers -----------------------
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_pairs, n)
+        h_src = torch.empty(ne * 2 * L, dtype=torch.float32, pin_memory=True)
+        h_smp = torch.empty(ne * L, dtype=torch.float32, pin_memory=True)
+        h_src.copy_(d_src[: ne * 2 * L]); h_smp.copy_(d_smp[: ne * L])
+        torch.cuda.synchronize(dev)
+        out = None
+        for _ in range(2):
+            out = ctx.xcorr_batch_ptr(h_src.data_ptr(), h_smp.data_ptr(), ne, L, ac.F32, ac.HOST)
+        barrier()
+        t0 = time.perf_counter()
+        reps = max(2, args.steps)
+        for _ in range(reps):
+            out = ctx.xcorr_batch_ptr(h_src.data_ptr(), h_smp.data_ptr(), ne, L, ac.F32, ac.HOST)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        assert all(int(out["lags"][i]) == int(res["lag"][i]) for i in range(ne))
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * ne * reps / float(tt[0]), "unit": UNIT,
+               "h2d_bytes_per_step": ne * 3 * L * 4, "d2h_bytes_per_step": ne * ac.RESULT_DTYPE.itemsize,
+               "pairs_per_step": ne, "host_dtype": "f32", "host_memory": "pinned",
+               "api": "audiosync_cuda_xcorr_batch(memspace=HOST)"}
+        del h_src, h_smp
+
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        # dominant kernel by device time inside the timed region
+        dom = max(KERNEL_U, key=lambda k: prof.get(k, (0, 0.0))[1])
+        n_launch, tot_ms = prof[dom]
+        pairs_per_launch = n * args.steps / max(1, n_launch)
+        alg_bytes = KERNEL_U[dom] * U * pairs_per_launch
+        avg_ms = tot_ms / max(1, n_launch)
+        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                if dom in tj and tj[dom].get("bytes_per_pair"):
+                    traffic = tj[dom]["bytes_per_pair"] * pairs_per_launch
+            except Exception:
+                traffic = None
+        total_kernel_ms = sum(v[1] for v in prof.values())
+        shares = {k: round(v[1] / total_kernel_ms, 4) for k, v in prof.items() if v[1] > 0}
+        path_achieved = PATH_U * U * value / world / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded integer "
+            "generator, SURVEY 8d; generated on device)",
+            "config": {"workload": "config[3]: %d pairs/GPU of L=%d frames (N=%d real points), "
+                                   "device-resident fp32, whole path incl. argmax + Pearson" % (n, L, 2 * L),
+                       "sample_len": L, "pairs_per_gpu": n, "total_pairs": world * n, "plan": plan,
+                       "inputs_larger_than_l2": bool(n * 3 * L * 4 > 126e6),
+                       "input_bytes_per_gpu": n * 3 * L * 4, "sharding": "contiguous pair blocks, no collective"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
+                         "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
+                         "launches": n_launch, "bytes_per_pair": KERNEL_U[dom] * U,
+                         "kernel_time_shares": shares},
+            "path_roofline": {"bytes_per_pair": PATH_U * U, "achieved": path_achieved, "peak": peak,
+                              "unit": "GB/s", "frac": path_achieved / peak, "per_gpu": True},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "check": {"lag_mismatches": bad, "success_flags": ok_flags, "pairs_checked_per_rank": min(n, 256)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            callers = max(1, cores // 2)
+            npairs = max(2 * callers, 8)
+            dt, kind, backend, _ = cpu_reference_run(L, npairs, callers, SEED)
+            line["cpu_baseline"] = {
+                "value": npairs / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                "sample": "%d pairs of the same workload, %d concurrent callers x 2 FFT threads, %.1f s wall, "
+                          "FFT backend %s (stand-in for FFTW3, not installed)" % (npairs, callers, dt, backend)}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

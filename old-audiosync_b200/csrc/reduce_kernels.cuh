@@ -254,7 +254,7 @@ pearson_final_kernel(const PearsonPartial* __restrict__ partials, int n_chunks, 
     } else {
         PairPeak p = peaks[pair];
         raw = p.resolved ? p.raw_index : (long long)argmax_key_index(p.key);
-        peak = p.peak;
+        peak = p.resolved ? p.peak : (double)argmax_key_value(p.key);
         w = fold_index(raw, L);
     }
     PearsonPartial s = {0.0, 0.0, 0.0, 0.0, 0.0};
