@@ -48,7 +48,7 @@ UNIT = "pairs/s"
 #   row_fused reads 4U (both planes), writes 2U (product rows, in place)           = 6 U
 #   col_inv   reads 2U                                                             = 2 U
 #   pearson   reads 2U (the two windows)                                           = 2 U
-KERNEL_U = {"col_fwd": 7, "row_fused": 6, "col_inv_argmax": 2, "pearson_partial": 2}
+KERNEL_U = {"col_fwd": 7, "row_fused": 6, "col_inv_argmax": 2, "pearson": 2}
 PATH_U = 21
 
 

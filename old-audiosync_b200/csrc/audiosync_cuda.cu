@@ -48,8 +48,8 @@ static bool debug_on() { return g_debug_flag || (&global_debug != nullptr && glo
 
 const char* kernel_class_name(int k) {
     static const char* names[KC_COUNT] = {
-        "synth", "direct_corr", "argmax_f64", "peaks_reset", "col_fwd", "row_fused",
-        "col_inv_argmax", "small_fft", "pearson_partial", "pearson_final"};
+        "synth", "direct_corr", "argmax_f64", "col_fwd", "row_fused",
+        "col_inv_argmax", "small_fft", "pearson"};
     return (k >= 0 && k < KC_COUNT) ? names[k] : "?";
 }
 
@@ -84,14 +84,14 @@ struct FftPlan {
     int M1 = 0, M2 = 0;
     std::string desc;
     size_t ws_bytes_per_pair = 0;
-    DevBuf col_tw, row_tw, m_lo, m_hi, n_lo, n_hi;   // static four-step
+    DevBuf col_tw, col_tc, row_tw, row_rev, m_lo, m_hi, n_lo, n_hi;   // static four-step
     DevBuf wm, wn;                                   // short-length kernel
     SmallPlan small;
     // enqueues the transform kernels for `pairs` pairs (planes/r in ws)
     std::function<int(audiosync_cuda_ctx*, DeviceState&, const void*, const void*, int, void*,
                       PairPeak*, int, cudaStream_t)> run_wave;
     ~FftPlan() {
-        col_tw.release(); row_tw.release(); m_lo.release(); m_hi.release();
+        col_tw.release(); col_tc.release(); row_tw.release(); row_rev.release(); m_lo.release(); m_hi.release();
         n_lo.release(); n_hi.release(); wm.release(); wn.release();
     }
 };
@@ -141,6 +141,8 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
     cplx* planes = static_cast<cplx*>(ws);
     const cplx* col_tw = static_cast<const cplx*>(plan->col_tw.p);
     const cplx* row_tw = static_cast<const cplx*>(plan->row_tw.p);
+    const cplx* col_tc = static_cast<const cplx*>(plan->col_tc.p);
+    const cplx* row_rev = static_cast<const cplx*>(plan->row_rev.p);
     const cplx* m_lo = static_cast<const cplx*>(plan->m_lo.p);
     const cplx* m_hi = static_cast<const cplx*>(plan->m_hi.p);
     const cplx* n_lo = static_cast<const cplx*>(plan->n_lo.p);
@@ -149,21 +151,21 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
     if (dtype == AUDIOSYNC_CUDA_F32) {
         using K = ColFwdKernel<Col, P::NT_COL, float>;
         typename K::Params p{static_cast<const float*>(src), static_cast<const float*>(smp), planes,
-                             col_tw, m_lo, m_hi, P::L, M2};
+                             peaks, col_tw, col_tc, m_lo, m_hi, P::L, M2};
         if (launch(ctx, d, KC_COL_FWD, st, [&] {
                 fft_kernel_entry<K><<<grid_a, K::THREADS, K::SMEM, st>>>(p);
             }) != 0) return -1;
     } else {
         using K = ColFwdKernel<Col, P::NT_COL, double>;
         typename K::Params p{static_cast<const double*>(src), static_cast<const double*>(smp), planes,
-                             col_tw, m_lo, m_hi, P::L, M2};
+                             peaks, col_tw, col_tc, m_lo, m_hi, P::L, M2};
         if (launch(ctx, d, KC_COL_FWD, st, [&] {
                 fft_kernel_entry<K><<<grid_a, K::THREADS, K::SMEM, st>>>(p);
             }) != 0) return -1;
     }
     {
         using K = RowFusedKernel<Row, P::NT_ROW>;
-        typename K::Params p{planes, row_tw, m_lo, m_hi, n_lo, n_hi, P::L, M1};
+        typename K::Params p{planes, row_tw, row_rev, m_lo, m_hi, n_lo, n_hi, P::L, M1};
         const dim3 grid(M1 / 2 + 1, 1, pairs);
         if (launch(ctx, d, KC_ROW_FUSED, st, [&] {
                 fft_kernel_entry<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
@@ -201,6 +203,8 @@ static int build_static_plan(FftPlan* plan) {
     build_two_level(2 * P::L, P::L, n_lo, n_hi);
     if (upload(plan->col_tw, build_pass_tables(radix_vector<Col>())) != 0 ||
         upload(plan->row_tw, build_pass_tables(radix_vector<Row>())) != 0 ||
+        upload(plan->col_tc, build_col_tc(P::L, Col::weight(Col::count - 1))) != 0 ||
+        upload(plan->row_rev, build_row_rev<Row>()) != 0 ||
         upload(plan->m_lo, m_lo) != 0 || upload(plan->m_hi, m_hi) != 0 ||
         upload(plan->n_lo, n_lo) != 0 || upload(plan->n_hi, n_hi) != 0)
         return -1;
@@ -243,10 +247,11 @@ static int build_small_plan(FftPlan* plan, long long L) {
         return -1;
     const size_t smem = SmallXcorrKernel<float>::smem_bytes((int)L);
     if (smem > 48 * 1024) {
+        const int cap = (int)SmallXcorrKernel<float>::smem_bytes(SMALL_MAX_M);
         ASC_CUDA_OK(cudaFuncSetAttribute(fft_kernel_entry<SmallXcorrKernel<float>>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SMALL_MAX_M * sizeof(cplx))));
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         ASC_CUDA_OK(cudaFuncSetAttribute(fft_kernel_entry<SmallXcorrKernel<double>>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SMALL_MAX_M * sizeof(cplx))));
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     }
     plan->run_wave = [plan](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
                             int dtype, void*, PairPeak* peaks, int pairs, cudaStream_t st) {
@@ -321,6 +326,16 @@ static int default_wave_pairs(const FftPlan* plan, size_t n_pairs) {
     return (int)std::min<long long>(w, (long long)std::max<size_t>(n_pairs, 1));
 }
 
+// Ticket counters of the Pearson kernel: zeroed once, self-resetting afterwards.
+static int ensure_tickets(DeviceState& d, size_t n) {
+    const size_t need = sizeof(unsigned int) * n;
+    if (need <= d.tickets.bytes) return 0;
+    ASC_CUDA_OK(cudaDeviceSynchronize());
+    if (d.tickets.ensure(need) != 0) return -1;
+    ASC_CUDA_OK(cudaMemset(d.tickets.p, 0, d.tickets.bytes));
+    return 0;
+}
+
 // Enqueue the whole path for device-resident pairs on `st` (no sync).
 static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
                          size_t n_pairs, long long L, int dtype, audiosync_cuda_result* d_results,
@@ -340,33 +355,29 @@ static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, const void* sr
     if (d.partials.ensure(sizeof(PearsonPartial) * (size_t)wave * n_chunks) != 0) return -1;
     PairPeak* peaks = static_cast<PairPeak*>(d.peaks.p);
     PearsonPartial* partials = static_cast<PearsonPartial*>(d.partials.p);
+    if (ensure_tickets(d, (size_t)wave) != 0) return -1;
+    unsigned int* tickets = static_cast<unsigned int*>(d.tickets.p);
     for (size_t p0 = 0; p0 < n_pairs; p0 += (size_t)wave) {
         const int pairs = (int)std::min<size_t>((size_t)wave, n_pairs - p0);
         const char* s = static_cast<const char*>(src) + p0 * (size_t)(2 * L) * esz;
         const char* m = static_cast<const char*>(smp) + p0 * (size_t)L * esz;
-        if (launch(ctx, d, KC_PEAKS_RESET, st, [&] {
-                peaks_reset_kernel<<<(pairs + 127) / 128, 128, 0, st>>>(peaks, pairs);
-            }) != 0) return -1;
         if (plan->run_wave(ctx, d, s, m, dtype, d.ws.p, peaks, pairs, st) != 0) return -1;
         const dim3 grid(n_chunks, pairs);
         int rc;
         if (dtype == AUDIOSYNC_CUDA_F32) {
-            rc = launch(ctx, d, KC_PEARSON_PARTIAL, st, [&] {
-                pearson_partial_kernel<float><<<grid, PEARSON_THREADS, 0, st>>>(
+            rc = launch(ctx, d, KC_PEARSON, st, [&] {
+                pearson_kernel<float><<<grid, PEARSON_THREADS, 0, st>>>(
                     reinterpret_cast<const float*>(s), reinterpret_cast<const float*>(m), 2 * L, L, L,
-                    peaks, 0, partials, n_chunks);
+                    peaks, 0, partials, tickets, n_chunks, d_results + p0);
             });
         } else {
-            rc = launch(ctx, d, KC_PEARSON_PARTIAL, st, [&] {
-                pearson_partial_kernel<double><<<grid, PEARSON_THREADS, 0, st>>>(
+            rc = launch(ctx, d, KC_PEARSON, st, [&] {
+                pearson_kernel<double><<<grid, PEARSON_THREADS, 0, st>>>(
                     reinterpret_cast<const double*>(s), reinterpret_cast<const double*>(m), 2 * L, L, L,
-                    peaks, 0, partials, n_chunks);
+                    peaks, 0, partials, tickets, n_chunks, d_results + p0);
             });
         }
         if (rc != 0) return -1;
-        if (launch(ctx, d, KC_PEARSON_FINAL, st, [&] {
-                pearson_final_kernel<<<pairs, 32, 0, st>>>(partials, n_chunks, L, peaks, 0, d_results + p0);
-            }) != 0) return -1;
     }
     return 0;
 }
@@ -392,7 +403,7 @@ static void destroy_device_state(DeviceState& d) {
     cudaSetDevice(d.device);
     cudaDeviceSynchronize();
     d.plans.clear();
-    d.ws.release(); d.peaks.release(); d.partials.release(); d.results.release();
+    d.ws.release(); d.peaks.release(); d.partials.release(); d.results.release(); d.tickets.release();
     for (int i = 0; i < 2; i++) {
         d.in_src[i].release(); d.in_smp[i].release(); d.h_stage[i].release();
         if (d.ev_up[i]) cudaEventDestroy(d.ev_up[i]);
@@ -496,7 +507,7 @@ int audiosync_cuda_create(audiosync_cuda_ctx** out, const int* devices, int n_de
         d.smem_optin = prop.sharedMemPerBlockOptin;
         // the only kernel image in this library is sm_100a
         cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, peaks_reset_kernel) != cudaSuccess) {
+        if (cudaFuncGetAttributes(&fa, argmax_f64_kernel) != cudaSuccess) {
             cudaGetLastError();
             set_last_error("device %d (%s, sm_%d%d) cannot run the sm_100a kernels of this library",
                            ids[i], prop.name, prop.major, prop.minor);
@@ -778,13 +789,11 @@ double pearson_coefficient(double* source_start, const double* source_end, doubl
         set_last_error("pearson_coefficient: upload failed");
         return fail();
     }
-    if (launch(ctx, d, KC_PEARSON_PARTIAL, st, [&] {
-            pearson_partial_kernel<double><<<dim3(n_chunks, 1), PEARSON_THREADS, 0, st>>>(
+    if (ensure_tickets(d, 1) != 0) return fail();
+    if (launch(ctx, d, KC_PEARSON, st, [&] {
+            pearson_kernel<double><<<dim3(n_chunks, 1), PEARSON_THREADS, 0, st>>>(
                 static_cast<const double*>(d.in_src[0].p), static_cast<const double*>(d.in_smp[0].p), 0, 0,
-                n, nullptr, n, partials, n_chunks);
-        }) != 0) return fail();
-    if (launch(ctx, d, KC_PEARSON_FINAL, st, [&] {
-            pearson_final_kernel<<<1, 32, 0, st>>>(partials, n_chunks, n, nullptr, n, d_res);
+                n, nullptr, n, partials, static_cast<unsigned int*>(d.tickets.p), n_chunks, d_res);
         }) != 0) return fail();
     if (cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) {

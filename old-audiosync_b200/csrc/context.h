@@ -35,13 +35,11 @@ enum KernelClass {
     KC_SYNTH = 0,
     KC_DIRECT,
     KC_ARGMAX_F64,
-    KC_PEAKS_RESET,
     KC_COL_FWD,      // K_A  forward column pass (source and sample)
     KC_ROW_FUSED,    // K_B  forward rows + split + conj-multiply + merge + inverse rows
     KC_COL_INV,      // K_C  inverse column pass + |r| argmax epilogue
     KC_SMALL_FFT,    // single-CTA transform for short lengths
-    KC_PEARSON_PARTIAL,
-    KC_PEARSON_FINAL,
+    KC_PEARSON,      // window statistics + coefficient + result record
     KC_COUNT
 };
 
@@ -74,6 +72,7 @@ struct DeviceState {
     DevBuf ws;            // transform workspace (direct: r[]; fft: A/B planes)
     DevBuf peaks;         // PairPeak per in-flight pair
     DevBuf partials;      // PearsonPartial
+    DevBuf tickets;       // per-pair completion counters of the Pearson kernel
     DevBuf results;       // audiosync_cuda_result for host-facing calls
     DevBuf in_src[2], in_smp[2];          // device copies of host inputs (double buffered)
     PinnedBuf h_results;

@@ -270,6 +270,24 @@ struct DftReg {
 template <int R, int DIR>
 ASC_HD void dft_reg(cplx (&v)[R]) { DftReg<R, DIR>::run(v); }
 
+// w[k] = exp(-2*pi*i*j*k/(S*R)) for k = 1..R-1 from the power-of-two table
+// entries of one pass (tw points at the pass's table): k = 2^i is a load,
+// any other k is the product w[hb(k)] * w[k - hb(k)] (at most 3 products deep
+// for R <= 16, i.e. a few ulp).  Trades LSU wavefronts for FMA-pipe work.
+template <int R>
+ASC_HD void pass_twiddles(const cplx* __restrict__ tw, int S, int j, cplx (&w)[R]) {
+    static_for<1, R>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        if constexpr ((k & (k - 1)) == 0) {
+            constexpr int i = (k == 1) ? 0 : (k == 2) ? 1 : (k == 4) ? 2 : (k == 8) ? 3 : (k == 16) ? 4 : 5;
+            w[k] = ldg(tw + i * S + j);
+        } else {
+            constexpr int hb = (k >= 16) ? 16 : (k >= 8) ? 8 : (k >= 4) ? 4 : 2;
+            w[k] = cmul(w[hb], w[k - hb]);
+        }
+    });
+}
+
 // ---------------------------------------------------------------- radix list
 // In-place decimation-in-frequency order: pass p has radix r(p) and
 // sub-stride s(p) = n / (r(0) * ... * r(p)); after all passes position
@@ -292,12 +310,17 @@ struct RadixList {
         for (int i = 0; i < p; i++) prod *= r(i);
         return prod;
     }
-    // offset (in cplx) of pass p's twiddle table inside the concatenated
-    // per-plan array; pass p holds (r(p)-1) * s(p) entries:
-    // tw[(k-1)*s + j] = exp(-2*pi*i*j*k / (s*r)),  k in [1,r), j in [0,s)
+    // Pass p's twiddle table holds only the power-of-two multiples
+    //   tw[i*s + j] = exp(-2*pi*i * j * 2^i / (s*r)),  2^i < r,  j in [0,s);
+    // the other multiples are products of two table values (pass_twiddles).
+    static constexpr int npow(int radix) {
+        int n = 0;
+        for (int k = 1; k < radix; k *= 2) n++;
+        return n;
+    }
     static constexpr int tw_offset(int p) {
         int off = 0;
-        for (int i = 0; i < p; i++) off += (r(i) - 1) * stride(i);
+        for (int i = 0; i < p; i++) off += npow(r(i)) * stride(i);
         return off;
     }
     static constexpr int tw_total() { return tw_offset(count); }

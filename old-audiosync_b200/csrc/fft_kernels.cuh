@@ -53,6 +53,24 @@ ASC_HD cplx load_packed<double>(const double* __restrict__ x, long long n) {
     return cmake((float)d.x, (float)d.y);
 }
 
+// Running |r| argmax of one thread (reference src/cross_correlation.c:52-67 as
+// a max over packed keys, see common.cuh).  The packed key is only built for
+// the rare candidates that can still win; a NaN never passes `a >= mag`.
+struct ArgmaxAcc {
+    unsigned long long best = 0ull;
+    float mag = -1.0f;               // magnitude a candidate must reach to matter
+    ASC_HD void update(unsigned long long key) {
+        if (key > best) {
+            best = key;
+            mag = float_from_order_bits((uint32_t)(key >> 32));   // NaN seed -> NaN: nothing passes
+        }
+    }
+    ASC_HD void consider(float v, uint32_t index) {   // index >= 1
+        if (fabsf(v) >= mag) update(argmax_key_abs(v, index));
+    }
+    ASC_HD void consider_seed(float v) { update(argmax_key_seed(v)); }   // index 0, signed
+};
+
 // --------------------------------------------------------------------- K_A
 template <class RL, int NT, typename InT>
 struct ColFwdKernel {
@@ -60,12 +78,16 @@ struct ColFwdKernel {
     static constexpr int P = RL::count;
     static constexpr int THREADS = NT;
     static constexpr size_t SMEM = (size_t)M1 * COL_T * sizeof(cplx);
+    static_assert(NT % COL_T == 0, "a thread must keep its column across items");
+    static_assert(P >= 2, "column plans need at least two passes");
 
     struct Params {
         const InT* sources;      // [pair][2L] reals
         const InT* samples;      // [pair][L] reals
         cplx* planes;            // [pair][2][M1*M2]: plane 0 source, plane 1 sample
-        const cplx* tw;          // RL pass tables (forward sign)
+        PairPeak* peaks;         // [pair]: argmax slot, cleared here for K_C
+        const cplx* tw;          // RL pass tables (forward sign, power-of-two multiples)
+        const cplx* tc;          // [M1/R_last][16]: W_M^(c*f0)
         const cplx* m_lo;        // W_M two-level tables
         const cplx* m_hi;
         long long L;             // sample_len == M
@@ -84,6 +106,7 @@ struct ColFwdKernel {
         // number of valid packed points: source M, sample M/2 (upper half is the zero pad)
         const long long nvalid = sig == 0 ? M : M / 2;
         cplx* __restrict__ out = p.planes + (pair * 2 + sig) * M;
+        const bool clears_peak = ex.bx() == 0 && sig == 0;
 
         static_for<0, P>([&](auto PP) {
             constexpr int ps = decltype(PP)::value;
@@ -92,42 +115,66 @@ struct ColFwdKernel {
             constexpr bool first = ps == 0, last = ps == P - 1;
             constexpr int items = (M1 / R) * COL_T;
             ex.phase([&](int tid) {
-                for (int w = tid; w < items; w += NT) {
-                    const int c = w & (COL_T - 1);
-                    const int bf = w >> 4;
-                    const int blk = bf / S;
-                    const int j = bf - blk * S;
-                    const int i0 = blk * (S * R) + j;
-                    cplx v[R];
-                    if constexpr (first) {
-                        static_for<0, R>([&](auto Q) {
-                            constexpr int q = decltype(Q)::value;
-                            const long long n = (long long)(i0 + q * S) * M2 + c0 + c;
-                            v[q] = n < nvalid ? load_packed<InT>(x, n) : cmake(0.f, 0.f);
-                        });
-                    } else {
-                        static_for<0, R>([&](auto Q) {
-                            constexpr int q = decltype(Q)::value;
-                            v[q] = buf[(i0 + q * S) * COL_T + c];
-                        });
-                    }
-                    dft_reg<R, -1>(v);
-                    if constexpr (!last) {
+                if (first && clears_peak && tid == 0) {
+                    PairPeak z; z.key = 0ull; z.raw_index = 0; z.peak = 0.0; z.resolved = 0; z.pad = 0;
+                    p.peaks[pair] = z;
+                }
+                const int c = tid & (COL_T - 1);          // fixed column of this thread
+                if constexpr (!last) {
+                    for (int w = tid; w < items; w += NT) {
+                        const int bf = w >> 4;
+                        const int blk = bf / S;
+                        const int j = bf - blk * S;
+                        const int i0 = blk * (S * R) + j;
+                        cplx v[R];
+                        if constexpr (first) {
+                            static_for<0, R>([&](auto Q) {
+                                constexpr int q = decltype(Q)::value;
+                                const long long n = (long long)(i0 + q * S) * M2 + c0 + c;
+                                v[q] = n < nvalid ? load_packed<InT>(x, n) : cmake(0.f, 0.f);
+                            });
+                        } else {
+                            static_for<0, R>([&](auto Q) {
+                                constexpr int q = decltype(Q)::value;
+                                v[q] = buf[(i0 + q * S) * COL_T + c];
+                            });
+                        }
+                        dft_reg<R, -1>(v);
+                        cplx t[R];
+                        pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
                         buf[i0 * COL_T + c] = v[0];
                         static_for<1, R>([&](auto K) {
                             constexpr int k = decltype(K)::value;
-                            cplx t = ldg(p.tw + RL::tw_offset(ps) + (k - 1) * S + j);
-                            buf[(i0 + k * S) * COL_T + c] = cmul(v[k], t);
+                            buf[(i0 + k * S) * COL_T + c] = cmul(v[k], t[k]);
                         });
-                    } else {
-                        // S == 1: positions i0 .. i0+R-1 hold bins f0 + k * weight
+                    }
+                } else {
+                    // S == 1: positions i0 .. i0+R-1 hold bins k1 = f0 + k*Wt, f0 < Wt.
+                    // W_M^(n2*k1) = W_M^(n2*f0) * (W_M^(n2*Wt))^k; the second factor is a
+                    // per-thread constant, the first is tc[f0][c] * W_M^(c0*f0).
+                    constexpr int Wt = RL::weight(ps);
+                    const unsigned n2 = (unsigned)(c0 + c);
+                    cplx g[R];
+                    static_for<1, R>([&](auto K) {
+                        constexpr int k = decltype(K)::value;
+                        g[k] = tw2(p.m_lo, p.m_hi, n2 * (unsigned)(Wt * k));
+                    });
+                    for (int w = tid; w < items; w += NT) {
+                        const int blk = w >> 4;
+                        const int i0 = blk * R;
+                        cplx v[R];
+                        static_for<0, R>([&](auto Q) {
+                            constexpr int q = decltype(Q)::value;
+                            v[q] = buf[(i0 + q) * COL_T + c];
+                        });
+                        dft_reg<R, -1>(v);
                         const int f0 = RL::freq_of_pos(i0);
-                        const unsigned n2 = (unsigned)(c0 + c);
-                        static_for<0, R>([&](auto K) {
+                        const cplx t0 = cmul(ldg(p.tc + f0 * COL_T + c),
+                                             tw2(p.m_lo, p.m_hi, (unsigned)c0 * (unsigned)f0));
+                        out[(long long)f0 * M2 + n2] = cmul(v[0], t0);
+                        static_for<1, R>([&](auto K) {
                             constexpr int k = decltype(K)::value;
-                            const unsigned k1 = (unsigned)(f0 + k * RL::weight(ps));
-                            cplx t = tw2(p.m_lo, p.m_hi, n2 * k1);
-                            out[(long long)k1 * M2 + n2] = cmul(v[k], t);
+                            out[(long long)(f0 + k * Wt) * M2 + n2] = cmul(v[k], cmul(t0, g[k]));
                         });
                     }
                 }
@@ -143,6 +190,8 @@ struct ColInvKernel {
     static constexpr int P = RL::count;
     static constexpr int THREADS = NT;
     static constexpr size_t SMEM = (size_t)M1 * COL_T * sizeof(cplx);
+    static_assert(NT % COL_T == 0, "a thread must keep its column across items");
+    static_assert(P >= 2, "column plans need at least two passes");
 
     struct Params {
         const cplx* planes;      // [pair][2][M1*M2]; plane 0 holds the K_B output
@@ -168,8 +217,8 @@ struct ColInvKernel {
             constexpr bool first = ps == 0;
             constexpr int items = (M1 / R) * COL_T;
             ex.phase([&](int tid) {
+                const int c = tid & (COL_T - 1);
                 for (int w = tid; w < items; w += NT) {
-                    const int c = w & (COL_T - 1);
                     const int bf = w >> 4;
                     const int blk = bf / S;
                     const int j = bf - blk * S;
@@ -181,11 +230,12 @@ struct ColInvKernel {
                         else v[q] = buf[(i0 + q * S) * COL_T + c];
                     });
                     dft_reg<R, +1>(v);
+                    cplx t[R];
+                    pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
                     buf[i0 * COL_T + c] = v[0];
                     static_for<1, R>([&](auto K) {
                         constexpr int k = decltype(K)::value;
-                        cplx t = ldg(p.tw + RL::tw_offset(ps) + (k - 1) * S + j);
-                        buf[(i0 + k * S) * COL_T + c] = cmulc(v[k], t);
+                        buf[(i0 + k * S) * COL_T + c] = cmulc(v[k], t[k]);
                     });
                 }
             });
@@ -196,37 +246,35 @@ struct ColInvKernel {
         {
             constexpr int ps = P - 1;
             constexpr int R = RL::r(ps);
-            constexpr bool first = ps == 0;
+            constexpr int Wt = RL::weight(ps);
             constexpr int items = (M1 / R) * COL_T;
             ex.phase_argmax(
                 [&](int tid) -> unsigned long long {
-                    unsigned long long best = 0ull;
+                    ArgmaxAcc acc;
+                    const int c = tid & (COL_T - 1);
+                    const bool col0 = (c0 + c) == 0;
                     for (int w = tid; w < items; w += NT) {
-                        const int c = w & (COL_T - 1);
                         const int blk = w >> 4;
                         const int i0 = blk * R;
                         cplx v[R];
                         static_for<0, R>([&](auto Q) {
                             constexpr int q = decltype(Q)::value;
-                            if constexpr (first) v[q] = ldg(in + (long long)(i0 + q) * M2 + c0 + c);
-                            else v[q] = buf[(i0 + q) * COL_T + c];
+                            v[q] = buf[(i0 + q) * COL_T + c];
                         });
                         dft_reg<R, +1>(v);
                         const int f0 = RL::freq_of_pos(i0);
                         static_for<0, R>([&](auto K) {
                             constexpr int k = decltype(K)::value;
-                            const long long n = (long long)(f0 + k * RL::weight(ps)) * M2 + c0 + c;
-                            const uint32_t i_re = (uint32_t)(2 * n);
-                            unsigned long long k_re = i_re == 0 ? argmax_key_seed(v[k].x)
-                                                                : argmax_key_abs(v[k].x, i_re);
-                            unsigned long long k_im = argmax_key_abs(v[k].y, i_re + 1u);
-                            best = k_re > best ? k_re : best;
-                            best = k_im > best ? k_im : best;
+                            const int n1 = f0 + k * Wt;
+                            const uint32_t i_re = 2u * (uint32_t)((long long)n1 * M2 + c0 + c);
+                            if (col0 && n1 == 0) acc.consider_seed(v[k].x);
+                            else acc.consider(v[k].x, i_re);
+                            acc.consider(v[k].y, i_re + 1u);
                         });
                     }
-                    return best;
+                    return acc.best;
                 },
-                &p.peaks[pair].key);
+                &p.peaks[pair].key, buf);
         }
     }
 };
@@ -263,11 +311,21 @@ struct RowFusedKernel {
     static constexpr int THREADS = NT;
     static constexpr int RP = M2;   // row pitch in shared memory
     static constexpr size_t SMEM = (size_t)4 * RP * sizeof(cplx);
+    static constexpr int R0 = RL::r(0);
+    static constexpr int S0 = RL::stride(0);
     static_assert(M2 % 2 == 0, "row length must be even");
+    static_assert(P >= 2, "row plans need at least two passes");
+    static_assert(2 * (S0 + R0) <= 2 * RP, "final-pass twiddle tables must fit the dead sample rows");
+
+    // A pass whose sub-stride S is below 16 (but not 1) would have half-warps
+    // straddle blocks and collide in the banks; give each block 16 thread slots
+    // (S active) instead.  S == 1 passes must use an odd radix (conflict-free).
+    static constexpr int slots(int S) { return (S > 1 && S < 16) ? 16 : S; }
 
     struct Params {
         cplx* planes;            // [pair][2][M1*M2]
-        const cplx* tw;          // RL pass tables (forward sign)
+        const cplx* tw;          // RL pass tables (forward sign, power-of-two multiples)
+        const cplx* rev;         // [M2]: exp(-2*pi*i*freq_of_pos(e)/(2*M2)), position order
         const cplx* m_lo;        // W_M tables
         const cplx* m_hi;
         const cplx* n_lo;        // W_N = W_2M tables
@@ -288,24 +346,29 @@ struct RowFusedKernel {
         const int k1a = r, k1b = M1 - r;   // k1b unused when !two
         cplx* __restrict__ plane_s = p.planes + pair * 2 * M;
         cplx* __restrict__ plane_p = plane_s + M;
+        // final-pass twiddle tables, built in the (then dead) sample rows
+        cplx* __restrict__ tab_ab = buf + 2 * RP;             // [2][S0]: W_M^(j*k1)
+        cplx* __restrict__ tab_g = buf + 2 * RP + 2 * S0;     // [2][R0]: W_M^(k*S0*k1)
 
         // ---- forward DIF on 2*nrows rows.  smem slots: 0,1 source rows; 2,3 sample rows.
         static_for<0, P>([&](auto PP) {
             constexpr int ps = decltype(PP)::value;
             constexpr int R = RL::r(ps);
             constexpr int S = RL::stride(ps);
+            constexpr int SL = slots(S);
             constexpr bool first = ps == 0;
-            constexpr int per_row = M2 / R;
+            constexpr int per_row = (M2 / (S * R)) * SL;
             const int items = per_row * 2 * nrows;
             ex.phase([&](int tid) {
                 for (int w = tid; w < items; w += NT) {
                     const int b = w / per_row;
                     const int bf = w - b * per_row;
+                    const int blk = bf / SL;
+                    const int j = bf - blk * SL;
+                    if (SL != S && j >= S) continue;
                     const int is_smp = b >= nrows ? 1 : 0;
                     const int rr = b - is_smp * nrows;          // 0 or 1: which row of the pair
                     cplx* __restrict__ row = buf + (is_smp * 2 + rr) * RP;
-                    const int blk = bf / S;
-                    const int j = bf - blk * S;
                     const int i0 = blk * (S * R) + j;
                     cplx v[R];
                     if constexpr (first) {
@@ -323,15 +386,19 @@ struct RowFusedKernel {
                     }
                     dft_reg<R, -1>(v);
                     row[i0] = v[0];
-                    static_for<1, R>([&](auto K) {
-                        constexpr int k = decltype(K)::value;
-                        if constexpr (S > 1) {
-                            cplx t = ldg(p.tw + RL::tw_offset(ps) + (k - 1) * S + j);
-                            row[i0 + k * S] = cmul(v[k], t);
-                        } else {
-                            row[i0 + k * S] = v[k];
-                        }
-                    });
+                    if constexpr (S > 1) {
+                        cplx t[R];
+                        pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
+                        static_for<1, R>([&](auto K) {
+                            constexpr int k = decltype(K)::value;
+                            row[i0 + k * S] = cmul(v[k], t[k]);
+                        });
+                    } else {
+                        static_for<1, R>([&](auto K) {
+                            constexpr int k = decltype(K)::value;
+                            row[i0 + k] = v[k];
+                        });
+                    }
                 }
             });
         });
@@ -341,25 +408,24 @@ struct RowFusedKernel {
             // items: two rows -> every position e of row a pairs with position
             // M2-1-e of row b (bin M2-1-k2); row M1/2 alone -> same map inside
             // one row, e < M2/2; row 0 alone -> bins (k2, M2-k2), e <= M2/2.
+            // exp(-2*pi*i*(k1a + M1*k2)/N) = W_N^k1a * rev[position of k2].
             const int items = two ? M2 : (r == 0 ? M2 / 2 + 1 : M2 / 2);
             cplx* __restrict__ zs_a = buf;
             cplx* __restrict__ zs_b = buf + (two ? RP : 0);
             cplx* __restrict__ zp_a = buf + 2 * RP;
             cplx* __restrict__ zp_b = buf + (two ? 3 * RP : 2 * RP);
             ex.phase([&](int tid) {
+                const cplx wk1 = tw2(p.n_lo, p.n_hi, (unsigned)k1a);
                 for (int e = tid; e < items; e += NT) {
-                    int pa, pb, k2;
+                    int pa, pb;
                     if (r == 0) {
-                        k2 = e;
                         pa = RL::pos_of_freq(e);
                         pb = RL::pos_of_freq(e == 0 ? 0 : M2 - e);
                     } else {
                         pa = e;
                         pb = M2 - 1 - e;
-                        k2 = RL::freq_of_pos(e);
                     }
-                    const unsigned k = (unsigned)k1a + (unsigned)M1 * (unsigned)k2;
-                    const cplx w = tw2(p.n_lo, p.n_hi, k);
+                    const cplx w = cmul(ldg(p.rev + pa), wk1);
                     cplx qk, qmk;
                     split_mul_merge(zs_a[pa], zs_b[pb], zp_a[pa], zp_b[pb], w, qk, qmk);
                     zs_a[pa] = qk;
@@ -373,28 +439,45 @@ struct RowFusedKernel {
             constexpr int ps = P - 1 - decltype(PP)::value;
             constexpr int R = RL::r(ps);
             constexpr int S = RL::stride(ps);
+            constexpr int SL = slots(S);
             constexpr bool last = ps == 0;
-            constexpr int per_row = M2 / R;
+            constexpr bool setup = ps == P - 1;
+            constexpr int per_row = (M2 / (S * R)) * SL;
             const int items = per_row * nrows;
             ex.phase([&](int tid) {
+                if constexpr (setup) {
+                    // the sample rows are dead now: build the final-pass twiddle tables there
+                    for (int e = tid; e < nrows * (S0 + R0); e += NT) {
+                        const int rr = e / (S0 + R0);
+                        const int i = e - rr * (S0 + R0);
+                        const unsigned k1 = (unsigned)(rr ? k1b : k1a);
+                        if (i < S0) tab_ab[rr * S0 + i] = tw2(p.m_lo, p.m_hi, (unsigned)i * k1);
+                        else tab_g[rr * R0 + (i - S0)] = tw2(p.m_lo, p.m_hi, (unsigned)((i - S0) * S0) * k1);
+                    }
+                }
                 for (int w = tid; w < items; w += NT) {
                     const int rr = w / per_row;
                     const int bf = w - rr * per_row;
+                    const int blk = bf / SL;
+                    const int j = bf - blk * SL;
+                    if (SL != S && j >= S) continue;
                     cplx* __restrict__ row = buf + rr * RP;
-                    const int blk = bf / S;
-                    const int j = bf - blk * S;
                     const int i0 = blk * (S * R) + j;
                     cplx v[R];
                     v[0] = row[i0];
-                    static_for<1, R>([&](auto Q) {
-                        constexpr int q = decltype(Q)::value;
-                        if constexpr (S > 1) {
-                            cplx t = ldg(p.tw + RL::tw_offset(ps) + (q - 1) * S + j);
-                            v[q] = cmulc(row[i0 + q * S], t);
-                        } else {
-                            v[q] = row[i0 + q * S];
-                        }
-                    });
+                    if constexpr (S > 1) {
+                        cplx t[R];
+                        pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
+                        static_for<1, R>([&](auto Q) {
+                            constexpr int q = decltype(Q)::value;
+                            v[q] = cmulc(row[i0 + q * S], t[q]);
+                        });
+                    } else {
+                        static_for<1, R>([&](auto Q) {
+                            constexpr int q = decltype(Q)::value;
+                            v[q] = row[i0 + q];
+                        });
+                    }
                     dft_reg<R, +1>(v);
                     if constexpr (!last) {
                         static_for<0, R>([&](auto K) {
@@ -402,14 +485,14 @@ struct RowFusedKernel {
                             row[i0 + k * S] = v[k];
                         });
                     } else {
-                        // natural order n2 = j + k*S; apply conj W_M^(n2*k1), store in place
+                        // natural order n2 = j + k*S0; conj W_M^(n2*k1) = conj(ab[j] * g[k]); in place
                         const unsigned k1 = (unsigned)(rr ? k1b : k1a);
                         cplx* __restrict__ g = plane_s + (long long)k1 * M2;
-                        static_for<0, R>([&](auto K) {
+                        const cplx t0 = tab_ab[rr * S0 + j];
+                        g[j] = cmulc(v[0], t0);
+                        static_for<1, R>([&](auto K) {
                             constexpr int k = decltype(K)::value;
-                            const unsigned n2 = (unsigned)(j + k * S);
-                            cplx t = tw2(p.m_lo, p.m_hi, n2 * k1);
-                            g[n2] = cmulc(v[k], t);
+                            g[j + k * S] = cmulc(v[k], cmul(t0, tab_g[rr * R0 + k]));
                         });
                     }
                 }
@@ -452,11 +535,15 @@ struct DeviceExec {
 #endif
     }
     // CTA-wide maximum of a per-thread key, then one atomicMax on *dst.
+    // `scratch`: at least 32 * 8 bytes of the CTA's dynamic shared memory; it may
+    // alias data f() reads (a barrier separates the two uses).  No static
+    // shared memory, so the column kernels keep 3 CTAs per SM.
     template <class F>
-    ASC_HD void phase_argmax(F&& f, unsigned long long* dst) {
+    ASC_HD void phase_argmax(F&& f, unsigned long long* dst, void* scratch) {
 #if defined(__CUDA_ARCH__)
-        __shared__ unsigned long long s_best[32];
+        unsigned long long* s_best = reinterpret_cast<unsigned long long*>(scratch);
         unsigned long long best = f((int)threadIdx.x);
+        __syncthreads();
         for (int o = 16; o > 0; o >>= 1) {
             unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
             best = other > best ? other : best;

@@ -18,41 +18,43 @@ namespace asc {
 // One per entry of the reference's interval schedule (src/audiosync.c:50-57:
 // sample_len = {3, 6, 10, 15, 20, 30} s x 48 kHz).  M = L = M1 * M2 with M2 a
 // multiple of 16 (full 128-byte lines per tile row) and even.  Row radix lists
-// end in an odd radix so the stride-1 pass is free of bank conflicts.
+// are (a, b, 15): the stride-1 pass has an odd radix (free of bank conflicts)
+// and the stride-15 pass runs with 16 thread slots per block (see
+// RowFusedKernel::slots).
 struct Plan144k {
     static constexpr long long L = 144000;
     using Col = RadixList<10, 6, 5>;     // M1 = 300
-    using Row = RadixList<16, 10, 3>;    // M2 = 480
+    using Row = RadixList<4, 8, 15>;     // M2 = 480
     static constexpr int NT_COL = 160, NT_ROW = 128;
 };
 struct Plan288k {
     static constexpr long long L = 288000;
-    using Col = RadixList<10, 6, 6>;     // M1 = 360
-    using Row = RadixList<16, 10, 5>;    // M2 = 800
-    static constexpr int NT_COL = 192, NT_ROW = 160;
+    using Col = RadixList<10, 6, 5>;     // M1 = 300
+    using Row = RadixList<4, 16, 15>;    // M2 = 960
+    static constexpr int NT_COL = 160, NT_ROW = 256;
 };
 struct Plan480k {
     static constexpr long long L = 480000;
-    using Col = RadixList<10, 10, 6>;    // M1 = 600
-    using Row = RadixList<16, 10, 5>;    // M2 = 800
-    static constexpr int NT_COL = 320, NT_ROW = 160;
+    using Col = RadixList<10, 10, 4>;    // M1 = 400
+    using Row = RadixList<5, 16, 15>;    // M2 = 1200
+    static constexpr int NT_COL = 320, NT_ROW = 320;
 };
 struct Plan720k {
     static constexpr long long L = 720000;
     using Col = RadixList<10, 10, 6>;    // M1 = 600
-    using Row = RadixList<16, 5, 15>;    // M2 = 1200
-    static constexpr int NT_COL = 320, NT_ROW = 256;
+    using Row = RadixList<5, 16, 15>;    // M2 = 1200
+    static constexpr int NT_COL = 320, NT_ROW = 320;
 };
 struct Plan960k {
     static constexpr long long L = 960000;
-    using Col = RadixList<10, 10, 6>;    // M1 = 600
-    using Row = RadixList<8, 8, 5, 5>;   // M2 = 1600
+    using Col = RadixList<10, 10, 4>;    // M1 = 400
+    using Row = RadixList<10, 16, 15>;   // M2 = 2400
     static constexpr int NT_COL = 320, NT_ROW = 320;
 };
 struct Plan1440k {
     static constexpr long long L = 1440000;
     using Col = RadixList<10, 10, 6>;    // M1 = 600
-    using Row = RadixList<16, 10, 15>;   // M2 = 2400
+    using Row = RadixList<10, 16, 15>;   // M2 = 2400
     static constexpr int NT_COL = 320, NT_ROW = 320;
 };
 
@@ -114,7 +116,8 @@ inline cplx unit_root(long long a, long long base) {   // exp(-2*pi*i*a/base)
     return cmake((float)c, (float)(-s));
 }
 
-// Pass tables for an in-place DIF radix list (layout: RadixList::tw_offset).
+// Pass tables for an in-place DIF radix list (layout: RadixList::tw_offset):
+// per pass only the power-of-two multiples exp(-2*pi*i*j*2^i/(s*r)), 2^i < r.
 inline std::vector<cplx> build_pass_tables(const std::vector<int>& radices) {
     long long n = 1;
     for (int r : radices) n *= r;
@@ -123,9 +126,25 @@ inline std::vector<cplx> build_pass_tables(const std::vector<int>& radices) {
     for (size_t p = 0; p < radices.size(); p++) {
         prod *= radices[p];
         const long long s = n / prod, m = s * radices[p];
-        for (int k = 1; k < radices[p]; k++)
+        for (int k = 1; k < radices[p]; k *= 2)
             for (long long j = 0; j < s; j++) t.push_back(unit_root(j * k, m));
     }
+    return t;
+}
+
+// K_A last-pass table: tc[f0][c] = exp(-2*pi*i*c*f0/M), f0 < wt, c < 16.
+inline std::vector<cplx> build_col_tc(long long M, int wt) {
+    std::vector<cplx> t((size_t)wt * COL_T);
+    for (int f0 = 0; f0 < wt; f0++)
+        for (int c = 0; c < COL_T; c++) t[(size_t)f0 * COL_T + c] = unit_root((long long)c * f0, M);
+    return t;
+}
+
+// K_B split/merge table in POSITION order: rev[e] = exp(-2*pi*i*freq_of_pos(e)/(2*M2)).
+template <class RL>
+inline std::vector<cplx> build_row_rev() {
+    std::vector<cplx> t(RL::n);
+    for (int e = 0; e < RL::n; e++) t[e] = unit_root(RL::freq_of_pos(e), 2LL * RL::n);
     return t;
 }
 

@@ -47,7 +47,8 @@ struct SmallXcorrKernel {
         const cplx* wn;       // exp(-2*pi*i*t/2M), t < M
         SmallPlan plan;
     };
-    static size_t smem_bytes(int M) { return (size_t)2 * M * sizeof(cplx); }
+    // two rows of M points + 256 bytes of reduction scratch
+    static size_t smem_bytes(int M) { return (size_t)2 * M * sizeof(cplx) + 256; }
 
     // one in-place radix-R pass over `rows` rows; FWD: DIF (twiddle after the
     // butterfly), else DIT inverse (conjugate twiddle before it).
@@ -112,6 +113,12 @@ struct SmallXcorrKernel {
         const int M = p.plan.M;
         const int np = p.plan.npass;
         const long long pair = ex.bz();
+        ex.phase([&](int tid) {
+            if (tid == 0) {
+                PairPeak z; z.key = 0ull; z.raw_index = 0; z.peak = 0.0; z.resolved = 0; z.pad = 0;
+                p.peaks[pair] = z;
+            }
+        });
         for (int ps = 0; ps < np; ps++) pass_any<true>(ex, p, buf, ps, 2, ps == 0);
         // split + multiply + merge: bins (k, M-k), k = 0 .. M/2, into row 0
         ex.phase([&](int tid) {
@@ -128,18 +135,17 @@ struct SmallXcorrKernel {
         // natural order now: packed point n carries r[2n], r[2n+1]
         ex.phase_argmax(
             [&](int tid) -> unsigned long long {
-                unsigned long long best = 0ull;
+                ArgmaxAcc acc;
                 for (int n = tid; n < M; n += THREADS) {
                     const cplx v = buf[n];
                     const uint32_t i_re = (uint32_t)(2 * n);
-                    unsigned long long k_re = i_re == 0 ? argmax_key_seed(v.x) : argmax_key_abs(v.x, i_re);
-                    unsigned long long k_im = argmax_key_abs(v.y, i_re + 1u);
-                    best = k_re > best ? k_re : best;
-                    best = k_im > best ? k_im : best;
+                    if (n == 0) acc.consider_seed(v.x);
+                    else acc.consider(v.x, i_re);
+                    acc.consider(v.y, i_re + 1u);
                 }
-                return best;
+                return acc.best;
             },
-            &p.peaks[pair].key);
+            &p.peaks[pair].key, buf + 2 * M);
     }
 };
 

@@ -130,16 +130,6 @@ argmax_f64_kernel(const double* __restrict__ r, long long N, PairPeak* __restric
     }
 }
 
-// Resets the per-pair argmax slot before a transform-path wave.
-__global__ void peaks_reset_kernel(PairPeak* __restrict__ peaks, int n)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        PairPeak p; p.key = 0ull; p.raw_index = 0; p.peak = 0.0; p.resolved = 0; p.pad = 0;
-        peaks[i] = p;
-    }
-}
-
 // ---------------------------------------------------------------------------
 // Pearson coefficient of the aligned windows (reference
 // src/cross_correlation.c:74-116 on the windows of :256-271).
@@ -152,43 +142,62 @@ __global__ void peaks_reset_kernel(PairPeak* __restrict__ peaks, int n)
 // give cov == varx == vary bit for bit and the quotient is exactly +-1.0, as
 // the reference's two-pass form does (tests/test_pearson_coefficient.c).
 //
-//   partial: grid = (n_chunks, n_pairs), block = 256; chunk c covers window
-//            elements [c * PEARSON_CHUNK, (c + 1) * PEARSON_CHUNK).
-//   final  : grid = n_pairs, block = 32; sums the chunk partials in index
-//            order and writes the audiosync_cuda_result record.
+//   grid = (n_chunks, n_pairs), block = 256; chunk c covers window elements
+//   [c * PEARSON_CHUNK, (c + 1) * PEARSON_CHUNK).
 // ---------------------------------------------------------------------------
 constexpr int PEARSON_CHUNK = 16384;
 constexpr int PEARSON_THREADS = 256;
 
 struct PearsonPartial { double sx, sy, sxx, syy, sxy; };
 
-template <typename T>
-__device__ __forceinline__ void pearson_window(const PairPeak* peaks, int pair, long long L,
-                                               long long explicit_n, Window& w)
+// Finishes one pair from the summed statistics (thread 0 of the finishing CTA).
+__device__ __forceinline__ void pearson_finish(const PearsonPartial& s, const Window& w, long long raw,
+                                               double peak, audiosync_cuda_result* __restrict__ out)
 {
-    if (peaks == nullptr) {           // explicit window: whole arrays of length explicit_n
-        w.lag = 0; w.xoff = 0; w.yoff = 0; w.n = explicit_n;
-        return;
-    }
-    PairPeak p = peaks[pair];
-    long long idx = p.resolved ? p.raw_index : (long long)argmax_key_index(p.key);
-    w = fold_index(idx, L);
+    // n == 0 -> 0/0 = NaN, like the reference's empty pointer range.
+    const double n = (double)w.n;
+    const double cov = s.sxy - s.sx * s.sy / n;
+    const double vx = s.sxx - s.sx * s.sx / n;
+    const double vy = s.syy - s.sy * s.sy / n;
+    const double coef = cov / sqrt(vx * vy);
+    audiosync_cuda_result r;
+    r.lag = w.lag;
+    r.coef = coef;
+    r.peak = peak;
+    r.ret = (coef != coef) ? -1 : 0;                       // src/cross_correlation.c:276
+    r.success = (r.ret == 0 && coef >= 0.95) ? 1 : 0;       // src/audiosync.c:254
+    r.raw_index = raw;
+    *out = r;
 }
 
+// grid = (n_chunks, n_pairs).  The last CTA of a pair to finish (ticket counter,
+// self-resetting) sums the chunk partials in a fixed order and writes the result
+// record, so the whole Pearson step is one launch.
 template <typename T>
 __global__ void __launch_bounds__(PEARSON_THREADS)
-pearson_partial_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
-                       long long src_pitch, long long smp_pitch, long long L,
-                       const PairPeak* __restrict__ peaks, long long explicit_n,
-                       PearsonPartial* __restrict__ partials, int n_chunks)
+pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
+               long long src_pitch, long long smp_pitch, long long L,
+               const PairPeak* __restrict__ peaks, long long explicit_n,
+               PearsonPartial* __restrict__ partials, unsigned int* __restrict__ tickets,
+               int n_chunks, audiosync_cuda_result* __restrict__ results)
 {
     __shared__ double s_piv[2];
     __shared__ double s_red[PEARSON_THREADS / 32][5];
+    __shared__ int s_last;
     const int pair = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
     Window w;
-    pearson_window<T>(peaks, pair, L, explicit_n, w);
-    const T* x = sources + (size_t)pair * (size_t)src_pitch + w.xoff;
-    const T* y = samples + (size_t)pair * (size_t)smp_pitch + w.yoff;
+    long long raw = 0;
+    double peak = 0.0;
+    if (peaks == nullptr) {           // explicit window: whole arrays of length explicit_n
+        w.lag = 0; w.xoff = 0; w.yoff = 0; w.n = explicit_n;
+    } else {
+        const PairPeak p = peaks[pair];
+        raw = p.resolved ? p.raw_index : (long long)argmax_key_index(p.key);
+        peak = p.resolved ? p.peak : (double)argmax_key_value(p.key);
+        w = fold_index(raw, L);
+    }
+    const T* __restrict__ x = sources + (size_t)pair * (size_t)src_pitch + w.xoff;
+    const T* __restrict__ y = samples + (size_t)pair * (size_t)smp_pitch + w.yoff;
 
     PearsonPartial acc = {0.0, 0.0, 0.0, 0.0, 0.0};
     const long long lo = (long long)chunk * PEARSON_CHUNK;
@@ -206,14 +215,23 @@ pearson_partial_kernel(const T* __restrict__ sources, const T* __restrict__ samp
         const double px = s_piv[0], py = s_piv[1];
         long long hi = lo + PEARSON_CHUNK;
         if (hi > w.n) hi = w.n;
-        for (long long i = lo + t; i < hi; i += PEARSON_THREADS) {
-            double dx = (double)x[i] - px;
-            double dy = (double)y[i] - py;
-            acc.sx += dx;
-            acc.sy += dy;
-            acc.sxx = fma(dx, dx, acc.sxx);
-            acc.syy = fma(dy, dy, acc.syy);
-            acc.sxy = fma(dx, dy, acc.sxy);
+        constexpr int UN = 8;
+        long long i = lo + t;
+        for (; i + (UN - 1) * PEARSON_THREADS < hi; i += UN * PEARSON_THREADS) {
+            T xv[UN], yv[UN];
+#pragma unroll
+            for (int u = 0; u < UN; u++) { xv[u] = x[i + u * PEARSON_THREADS]; yv[u] = y[i + u * PEARSON_THREADS]; }
+#pragma unroll
+            for (int u = 0; u < UN; u++) {
+                const double dx = (double)xv[u] - px, dy = (double)yv[u] - py;
+                acc.sx += dx; acc.sy += dy;
+                acc.sxx = fma(dx, dx, acc.sxx); acc.syy = fma(dy, dy, acc.syy); acc.sxy = fma(dx, dy, acc.sxy);
+            }
+        }
+        for (; i < hi; i += PEARSON_THREADS) {
+            const double dx = (double)x[i] - px, dy = (double)y[i] - py;
+            acc.sx += dx; acc.sy += dy;
+            acc.sxx = fma(dx, dx, acc.sxx); acc.syy = fma(dy, dy, acc.syy); acc.sxy = fma(dx, dy, acc.sxy);
         }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -236,46 +254,33 @@ pearson_partial_kernel(const T* __restrict__ sources, const T* __restrict__ samp
             o.syy += s_red[k][3]; o.sxy += s_red[k][4];
         }
         partials[(size_t)pair * n_chunks + chunk] = o;
+        __threadfence();
+        const unsigned int ticket = atomicAdd(&tickets[pair], 1u);
+        s_last = (ticket == (unsigned int)(n_chunks - 1)) ? 1 : 0;
     }
-}
-
-__global__ void __launch_bounds__(32)
-pearson_final_kernel(const PearsonPartial* __restrict__ partials, int n_chunks, long long L,
-                     const PairPeak* __restrict__ peaks, long long explicit_n,
-                     audiosync_cuda_result* __restrict__ results)
-{
-    const int pair = blockIdx.x;
-    if (threadIdx.x != 0) return;
-    Window w;
-    long long raw = 0;
-    double peak = 0.0;
-    if (peaks == nullptr) {
-        w.lag = 0; w.xoff = 0; w.yoff = 0; w.n = explicit_n;
-    } else {
-        PairPeak p = peaks[pair];
-        raw = p.resolved ? p.raw_index : (long long)argmax_key_index(p.key);
-        peak = p.resolved ? p.peak : (double)argmax_key_value(p.key);
-        w = fold_index(raw, L);
+    __syncthreads();
+    if (s_last && t < 32) {
+        __threadfence();
+        // lane l sums chunks l, l+32, ... in ascending order; then a fixed xor tree
+        PearsonPartial s = {0.0, 0.0, 0.0, 0.0, 0.0};
+        const double* base = reinterpret_cast<const double*>(partials + (size_t)pair * n_chunks);
+        for (int c = t; c < n_chunks; c += 32) {
+            s.sx += __ldcg(base + 5 * c + 0); s.sy += __ldcg(base + 5 * c + 1);
+            s.sxx += __ldcg(base + 5 * c + 2); s.syy += __ldcg(base + 5 * c + 3);
+            s.sxy += __ldcg(base + 5 * c + 4);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            s.sx += __shfl_xor_sync(0xffffffffu, s.sx, o);
+            s.sy += __shfl_xor_sync(0xffffffffu, s.sy, o);
+            s.sxx += __shfl_xor_sync(0xffffffffu, s.sxx, o);
+            s.syy += __shfl_xor_sync(0xffffffffu, s.syy, o);
+            s.sxy += __shfl_xor_sync(0xffffffffu, s.sxy, o);
+        }
+        if (t == 0) {
+            pearson_finish(s, w, raw, peak, results + pair);
+            tickets[pair] = 0u;       // ready for the next wave
+        }
     }
-    PearsonPartial s = {0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int c = 0; c < n_chunks; c++) {
-        PearsonPartial q = partials[(size_t)pair * n_chunks + c];
-        s.sx += q.sx; s.sy += q.sy; s.sxx += q.sxx; s.syy += q.syy; s.sxy += q.sxy;
-    }
-    // n == 0 -> 0/0 = NaN, like the reference's empty pointer range.
-    const double n = (double)w.n;
-    const double cov = s.sxy - s.sx * s.sy / n;
-    const double vx = s.sxx - s.sx * s.sx / n;
-    const double vy = s.syy - s.sy * s.sy / n;
-    const double coef = cov / sqrt(vx * vy);
-    audiosync_cuda_result r;
-    r.lag = w.lag;
-    r.coef = coef;
-    r.peak = peak;
-    r.ret = (coef != coef) ? -1 : 0;                       // src/cross_correlation.c:276
-    r.success = (r.ret == 0 && coef >= 0.95) ? 1 : 0;       // src/audiosync.c:254
-    r.raw_index = raw;
-    results[pair] = r;
 }
 
 }  // namespace asc

@@ -24,7 +24,7 @@ struct HostExec {
         for (int t = 0; t < nt; t++) f(t);
     }
     template <class F>
-    void phase_argmax(F&& f, unsigned long long* dst) {
+    void phase_argmax(F&& f, unsigned long long* dst, void* /*scratch*/) {
         unsigned long long best = 0;
         for (int t = 0; t < nt; t++) {
             unsigned long long k = f(t);
@@ -43,14 +43,16 @@ static int run_static(const InT* source, const InT* sample, PairPeak* peak, cplx
     std::vector<cplx> planes(2 * M);
     std::vector<cplx> col_tw = build_pass_tables(radix_vector<Col>());
     std::vector<cplx> row_tw = build_pass_tables(radix_vector<Row>());
+    std::vector<cplx> col_tc = build_col_tc(M, Col::weight(Col::count - 1));
+    std::vector<cplx> row_rev = build_row_rev<Row>();
     std::vector<cplx> m_lo, m_hi, n_lo, n_hi;
     build_two_level(M, M - 1, m_lo, m_hi);
     build_two_level(2 * M, M, n_lo, n_hi);
-    peak->key = 0; peak->resolved = 0; peak->raw_index = 0; peak->peak = 0;
+    peak->key = 12345ull;   // garbage: K_A must clear it
 
     {
         using K = ColFwdKernel<Col, P::NT_COL, InT>;
-        typename K::Params p{source, sample, planes.data(), col_tw.data(), m_lo.data(), m_hi.data(), M, M2};
+        typename K::Params p{source, sample, planes.data(), peak, col_tw.data(), col_tc.data(), m_lo.data(), m_hi.data(), M, M2};
         std::vector<cplx> smem(K::SMEM / sizeof(cplx));
         for (int sig = 0; sig < 2; sig++)
             for (int tile = 0; tile < M2 / COL_T; tile++) {
@@ -60,7 +62,7 @@ static int run_static(const InT* source, const InT* sample, PairPeak* peak, cplx
     }
     {
         using K = RowFusedKernel<Row, P::NT_ROW>;
-        typename K::Params p{planes.data(), row_tw.data(), m_lo.data(), m_hi.data(), n_lo.data(), n_hi.data(), M, M1};
+        typename K::Params p{planes.data(), row_tw.data(), row_rev.data(), m_lo.data(), m_hi.data(), n_lo.data(), n_hi.data(), M, M1};
         std::vector<cplx> smem(K::SMEM / sizeof(cplx));
         for (int r = 0; r <= M1 / 2; r++) {
             HostExec ex{r, 0, 0, K::THREADS};
@@ -88,7 +90,7 @@ static int run_small(const InT* source, const InT* sample, long long L, PairPeak
     using K = SmallXcorrKernel<InT>;
     typename K::Params p{source, sample, peak, wm.data(), wn.data(), pl};
     std::vector<cplx> smem(K::smem_bytes((int)L) / sizeof(cplx));
-    peak->key = 0; peak->resolved = 0;
+    peak->key = 12345ull;   // garbage: the kernel must clear it
     HostExec ex{0, 0, 0, K::THREADS};
     K::run(ex, p, smem.data());
     return 0;

@@ -359,5 +359,5 @@ def test_profile_and_launch_accounting(ac, capi):
         res, _, _ = _batch_on_device(ac, c, SEED, 0, n, L)
         prof = c.profile_read()
         assert c.launch_count() > before
-    for k in ("col_fwd", "row_fused", "col_inv_argmax", "pearson_partial", "pearson_final"):
+    for k in ("col_fwd", "row_fused", "col_inv_argmax", "pearson"):
         assert prof[k][0] >= 1 and prof[k][1] > 0.0, (k, prof)
