@@ -239,7 +239,10 @@ def main():
     d_src = torch.empty(n * 2 * L, dtype=torch.float32, device=dev)
     d_smp = torch.empty(n * L, dtype=torch.float32, device=dev)
     d_res = torch.zeros(n * ac.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    stream = torch.cuda.current_stream(dev)
+    # A dedicated (non-default) stream: the library maps a NULL stream handle to its own
+    # internal stream, so events recorded on torch's default stream would not bracket the kernels.
+    stream = torch.cuda.Stream(dev)
+    assert stream.cuda_stream != 0
     ctx.synth_pairs(local, SEED, first_pair, n, L, ac.F32, d_src.data_ptr(), d_smp.data_ptr(),
                     stream.cuda_stream)
     torch.cuda.synchronize(dev)
