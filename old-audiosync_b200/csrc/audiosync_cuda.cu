@@ -148,20 +148,25 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
     const cplx* n_lo = static_cast<const cplx*>(plan->n_lo.p);
     const cplx* n_hi = static_cast<const cplx*>(plan->n_hi.p);
     const dim3 grid_a(M2 / COL_T, 2, pairs);
+    auto col_fwd = [&](auto KK, const auto* s_in, const auto* m_in) -> int {
+        using K = decltype(KK);
+        typename K::Params p{s_in, m_in, planes, peaks, col_tw, col_tc, m_lo, m_hi, P::L, M2};
+        return launch(ctx, d, KC_COL_FWD, st, [&] {
+            fft_kernel_entry<K><<<grid_a, K::THREADS, K::SMEM, st>>>(p);
+        });
+    };
     if (dtype == AUDIOSYNC_CUDA_F32) {
-        using K = ColFwdKernel<Col, P::NT_COL, float>;
-        typename K::Params p{static_cast<const float*>(src), static_cast<const float*>(smp), planes,
-                             peaks, col_tw, col_tc, m_lo, m_hi, P::L, M2};
-        if (launch(ctx, d, KC_COL_FWD, st, [&] {
-                fft_kernel_entry<K><<<grid_a, K::THREADS, K::SMEM, st>>>(p);
-            }) != 0) return -1;
+        // cp.async staging needs 16-byte aligned rows: every pair / row offset is a multiple
+        // of 16 bytes, so only the base pointers decide.
+        const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(smp)) & 15u) == 0;
+        const float* s_in = static_cast<const float*>(src);
+        const float* m_in = static_cast<const float*>(smp);
+        const int rc = aligned ? col_fwd(ColFwdKernel<Col, P::NT_COL, float, true>{}, s_in, m_in)
+                               : col_fwd(ColFwdKernel<Col, P::NT_COL, float, false>{}, s_in, m_in);
+        if (rc != 0) return -1;
     } else {
-        using K = ColFwdKernel<Col, P::NT_COL, double>;
-        typename K::Params p{static_cast<const double*>(src), static_cast<const double*>(smp), planes,
-                             peaks, col_tw, col_tc, m_lo, m_hi, P::L, M2};
-        if (launch(ctx, d, KC_COL_FWD, st, [&] {
-                fft_kernel_entry<K><<<grid_a, K::THREADS, K::SMEM, st>>>(p);
-            }) != 0) return -1;
+        if (col_fwd(ColFwdKernel<Col, P::NT_COL, double, false>{}, static_cast<const double*>(src),
+                    static_cast<const double*>(smp)) != 0) return -1;
     }
     {
         using K = RowFusedKernel<Row, P::NT_ROW>;
@@ -208,8 +213,9 @@ static int build_static_plan(FftPlan* plan) {
         upload(plan->m_lo, m_lo) != 0 || upload(plan->m_hi, m_hi) != 0 ||
         upload(plan->n_lo, n_lo) != 0 || upload(plan->n_hi, n_hi) != 0)
         return -1;
-    if (prepare_kernel<ColFwdKernel<Col, P::NT_COL, float>>(ColFwdKernel<Col, P::NT_COL, float>::SMEM) != 0 ||
-        prepare_kernel<ColFwdKernel<Col, P::NT_COL, double>>(ColFwdKernel<Col, P::NT_COL, double>::SMEM) != 0 ||
+    if (prepare_kernel<ColFwdKernel<Col, P::NT_COL, float, true>>(ColFwdKernel<Col, P::NT_COL, float, true>::SMEM) != 0 ||
+        prepare_kernel<ColFwdKernel<Col, P::NT_COL, float, false>>(ColFwdKernel<Col, P::NT_COL, float, false>::SMEM) != 0 ||
+        prepare_kernel<ColFwdKernel<Col, P::NT_COL, double, false>>(ColFwdKernel<Col, P::NT_COL, double, false>::SMEM) != 0 ||
         prepare_kernel<RowFusedKernel<Row, P::NT_ROW>>(RowFusedKernel<Row, P::NT_ROW>::SMEM) != 0 ||
         prepare_kernel<ColInvKernel<Col, P::NT_COL>>(ColInvKernel<Col, P::NT_COL>::SMEM) != 0)
         return -1;
@@ -315,8 +321,11 @@ static FftPlan* get_plan(audiosync_cuda_ctx* ctx, DeviceState& d, long long L) {
 static int default_wave_pairs(const FftPlan* plan, size_t n_pairs) {
     long long w;
     if (plan->kind == PATH_STATIC_FFT) {
-        w = (8LL * 1440000) / plan->L;
-        w = std::max(8LL, std::min(256LL, w));
+        // Enough pairs per launch that the partial last wave of CTAs is a few percent of the
+        // launch (64 pairs at L = 1.44M: ~43 waves of the 3-CTA/SM kernels); the workspace
+        // stays at ~1.5 GB whatever the length.
+        w = (64LL * 1440000) / plan->L;
+        w = std::max(16LL, std::min(1024LL, w));
     } else if (plan->kind == PATH_SMALL_FFT) {
         w = 16384;
     } else {

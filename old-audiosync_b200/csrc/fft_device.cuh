@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string.h>
+
 #include <type_traits>
 #include <utility>
 
@@ -21,18 +23,105 @@ namespace asc {
 typedef float2 cplx;
 
 ASC_HD cplx cmake(float a, float b) { cplx r; r.x = a; r.y = b; return r; }
-ASC_HD cplx cadd(cplx a, cplx b) { return cmake(a.x + b.x, a.y + b.y); }
-ASC_HD cplx csub(cplx a, cplx b) { return cmake(a.x - b.x, a.y - b.y); }
-ASC_HD cplx cconj(cplx a) { return cmake(a.x, -a.y); }
-ASC_HD cplx cscale(cplx a, float s) { return cmake(a.x * s, a.y * s); }
-// a * b
+
+// Complex arithmetic.  On the device every operation is written with the
+// sm_100 packed-fp32 instructions (FADD2 / FMUL2 / FFMA2: one issue slot for
+// both halves of a float2 register pair).  ptxas folds the swaps and per-half
+// sign flips below into operand modifiers (R.F32x2.LO_HI, .NP, scalar
+// broadcast R.F32), so a complex add is one instruction and a complex multiply
+// two.  The host versions (CPU emulator) compute the same values with scalar
+// fmaf in the same association order.
+#if defined(__CUDA_ARCH__)
+#define ASC_PACKED 1
+#else
+#define ASC_PACKED 0
+#endif
+ASC_HD cplx cadd(cplx a, cplx b) {
+#if ASC_PACKED
+    return __fadd2_rn(a, b);
+#else
+    return cmake(a.x + b.x, a.y + b.y);
+#endif
+}
+ASC_HD cplx csub(cplx a, cplx b) {
+#if ASC_PACKED
+    return __fadd2_rn(a, cmake(-b.x, -b.y));
+#else
+    return cmake(a.x - b.x, a.y - b.y);
+#endif
+}
+ASC_HD cplx cscale(cplx a, float s) {
+#if ASC_PACKED
+    return __fmul2_rn(a, cmake(s, s));
+#else
+    return cmake(a.x * s, a.y * s);
+#endif
+}
+// a + s * b
+ASC_HD cplx caxpy(float s, cplx b, cplx a) {
+#if ASC_PACKED
+    return __ffma2_rn(b, cmake(s, s), a);
+#else
+    return cmake(fmaf(b.x, s, a.x), fmaf(b.y, s, a.y));
+#endif
+}
+// a * b = a * b.x + (i a) * b.y, evaluated as fma(a, b.x, (-t.x, t.y)) with t = (a.y, a.x) * b.y
 ASC_HD cplx cmul(cplx a, cplx b) {
-    return cmake(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
+#if ASC_PACKED
+    const cplx t = __fmul2_rn(cmake(a.y, a.x), cmake(b.y, b.y));
+    return __ffma2_rn(a, cmake(b.x, b.x), cmake(-t.x, t.y));
+#else
+    return cmake(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.y, b.x, a.x * b.y));
+#endif
 }
 // a * conj(b)
 ASC_HD cplx cmulc(cplx a, cplx b) {
+#if ASC_PACKED
+    const cplx t = __fmul2_rn(cmake(a.y, a.x), cmake(b.y, b.y));
+    return __ffma2_rn(a, cmake(b.x, b.x), cmake(t.x, -t.y));
+#else
     return cmake(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -(a.x * b.y)));
+#endif
 }
+// a + i*b, a - i*b
+ASC_HD cplx cadd_i(cplx a, cplx b) {
+#if ASC_PACKED
+    return __fadd2_rn(a, cmake(-b.y, b.x));
+#else
+    return cmake(a.x - b.y, a.y + b.x);
+#endif
+}
+ASC_HD cplx csub_i(cplx a, cplx b) {
+#if ASC_PACKED
+    return __fadd2_rn(a, cmake(b.y, -b.x));
+#else
+    return cmake(a.x + b.y, a.y - b.x);
+#endif
+}
+// a + s * (i*b), a - s * (i*b)
+ASC_HD cplx caxpy_i(float s, cplx b, cplx a) {
+#if ASC_PACKED
+    return __ffma2_rn(cmake(-b.y, b.x), cmake(s, s), a);
+#else
+    return cmake(fmaf(-b.y, s, a.x), fmaf(b.x, s, a.y));
+#endif
+}
+ASC_HD cplx caxmy_i(float s, cplx b, cplx a) {
+#if ASC_PACKED
+    return __ffma2_rn(cmake(b.y, -b.x), cmake(s, s), a);
+#else
+    return cmake(fmaf(b.y, s, a.x), fmaf(-b.x, s, a.y));
+#endif
+}
+// v * (wr + i wi) with compile-time-known wr, wi (immediates in the SASS)
+ASC_HD cplx cmul_const(cplx v, float wr, float wi) {
+#if ASC_PACKED
+    return __ffma2_rn(cmake(-v.y, v.x), cmake(wi, wi), __fmul2_rn(v, cmake(wr, wr)));
+#else
+    return cmake(fmaf(-v.y, wi, v.x * wr), fmaf(v.x, wi, v.y * wr));
+#endif
+}
+ASC_HD cplx cconj(cplx a) { return cmake(a.x, -a.y); }
 // multiply by +i / -i
 ASC_HD cplx cmul_pi(cplx a) { return cmake(-a.y, a.x); }
 ASC_HD cplx cmul_ni(cplx a) { return cmake(a.y, -a.x); }
@@ -43,6 +132,54 @@ ASC_HD T ldg(const T* p) {
     return __ldg(p);
 #else
     return *p;
+#endif
+}
+
+// ------------------------------------------------------- asynchronous staging
+// Global -> shared copies that bypass the register file (LDGSTS / cp.async,
+// 16 bytes per thread, L1 bypass) and the shared -> global bulk store of the
+// TMA unit (cp.async.bulk, one instruction for a whole row).  The host versions
+// (CPU emulator) are plain copies.
+ASC_HD void cp_async16(void* smem_dst, const void* gmem_src) {
+#if defined(__CUDA_ARCH__)
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+#else
+    memcpy(smem_dst, gmem_src, 16);
+#endif
+}
+ASC_HD void cp_async_wait_all() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+ASC_HD void smem_zero16(void* smem_dst) {
+    *reinterpret_cast<float4*>(smem_dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// Makes this thread's earlier shared-memory writes visible to the async proxy
+// (required between st.shared and a bulk store that reads the same bytes).
+ASC_HD void fence_async_proxy() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+}
+// One thread: shared -> global bulk copy, bytes % 16 == 0, both 16-byte aligned.
+ASC_HD void bulk_store(void* gmem_dst, const void* smem_src, unsigned bytes) {
+#if defined(__CUDA_ARCH__)
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_src);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(sa), "r"(bytes)
+                 : "memory");
+#else
+    memcpy(gmem_dst, smem_src, bytes);
+#endif
+}
+// Same thread: commit, then wait until the source bytes have been read out of
+// shared memory (the CTA may exit / reuse the buffer; global visibility follows
+// at kernel completion).
+ASC_HD void bulk_store_commit_and_drain() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #endif
 }
 
@@ -134,13 +271,13 @@ ASC_HD cplx mul_root(cplx v) {
         constexpr ct::cd w = ct::unit((long long)DIR * t, R);
         constexpr float wr = (float)w.re, wi = (float)w.im;
         if constexpr (8 * t == R || 8 * t == 3 * R || 8 * t == 5 * R || 8 * t == 7 * R) {
-            // |wr| == |wi| == sqrt(1/2)
+            // |wr| == |wi| == sqrt(1/2): (sr + i si) v = sr v + si (i v), then one scale
             constexpr float h = 0.70710678118654752440f;
-            constexpr float sr = wr > 0 ? 1.f : -1.f, si = wi > 0 ? 1.f : -1.f;
-            // (x + iy)(sr*h + i*si*h) = h*[(sr*x - si*y) + i(si*x + sr*y)]
-            return cmake(h * (sr * v.x - si * v.y), h * (si * v.x + sr * v.y));
+            constexpr bool same = (wr > 0) == (wi > 0);
+            const cplx u = same ? cadd_i(v, v) : csub_i(v, v);     // v +- i v
+            return cscale(u, wr > 0 ? h : -h);
         } else {
-            return cmake(fmaf(v.x, wr, -(v.y * wi)), fmaf(v.x, wi, v.y * wr));
+            return cmul_const(v, wr, wi);
         }
     }
 }
@@ -169,27 +306,25 @@ template <int DIR>
 struct DftReg<3, DIR> {
     static ASC_HD void run(cplx (&v)[3]) {
         constexpr float s60 = (DIR > 0 ? 1.f : -1.f) * 0.86602540378443864676f;
-        cplx a = v[0], b = v[1], c = v[2];
-        cplx t1 = cadd(b, c);
-        cplx t2 = cmake(fmaf(-0.5f, t1.x, a.x), fmaf(-0.5f, t1.y, a.y));
-        cplx d = csub(b, c);
-        cplx t3 = cmake(s60 * d.x, s60 * d.y);
+        const cplx a = v[0], b = v[1], c = v[2];
+        const cplx t1 = cadd(b, c);
+        const cplx t2 = caxpy(-0.5f, t1, a);
+        const cplx d = csub(b, c);
         v[0] = cadd(a, t1);
-        v[1] = cmake(t2.x - t3.y, t2.y + t3.x);
-        v[2] = cmake(t2.x + t3.y, t2.y - t3.x);
+        v[1] = caxpy_i(s60, d, t2);      // t2 + i s60 d
+        v[2] = caxmy_i(s60, d, t2);      // t2 - i s60 d
     }
 };
 
 template <int DIR>
 struct DftReg<4, DIR> {
     static ASC_HD void run(cplx (&v)[4]) {
-        cplx s0 = cadd(v[0], v[2]), s1 = csub(v[0], v[2]);
-        cplx s2 = cadd(v[1], v[3]), s3 = csub(v[1], v[3]);
-        cplx r3 = DIR > 0 ? cmul_pi(s3) : cmul_ni(s3);
+        const cplx s0 = cadd(v[0], v[2]), s1 = csub(v[0], v[2]);
+        const cplx s2 = cadd(v[1], v[3]), s3 = csub(v[1], v[3]);
         v[0] = cadd(s0, s2);
-        v[1] = cadd(s1, r3);
         v[2] = csub(s0, s2);
-        v[3] = csub(s1, r3);
+        if constexpr (DIR > 0) { v[1] = cadd_i(s1, s3); v[3] = csub_i(s1, s3); }
+        else { v[1] = csub_i(s1, s3); v[3] = cadd_i(s1, s3); }
     }
 };
 
@@ -201,18 +336,18 @@ struct DftReg<5, DIR> {
         constexpr float sg = DIR > 0 ? 1.f : -1.f;
         constexpr float s1 = sg * 0.95105651629515357212f;  // sin(2pi/5)
         constexpr float s2 = sg * 0.58778525229247312917f;  // sin(4pi/5)
-        cplx x0 = v[0];
-        cplx a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
-        cplx a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
-        cplx p1 = cmake(fmaf(c2, a2.x, fmaf(c1, a1.x, x0.x)), fmaf(c2, a2.y, fmaf(c1, a1.y, x0.y)));
-        cplx p2 = cmake(fmaf(c1, a2.x, fmaf(c2, a1.x, x0.x)), fmaf(c1, a2.y, fmaf(c2, a1.y, x0.y)));
-        cplx u1 = cmake(fmaf(s2, b2.x, s1 * b1.x), fmaf(s2, b2.y, s1 * b1.y));
-        cplx u2 = cmake(fmaf(-s1, b2.x, s2 * b1.x), fmaf(-s1, b2.y, s2 * b1.y));
-        v[0] = cmake(x0.x + a1.x + a2.x, x0.y + a1.y + a2.y);
-        v[1] = cmake(p1.x - u1.y, p1.y + u1.x);
-        v[4] = cmake(p1.x + u1.y, p1.y - u1.x);
-        v[2] = cmake(p2.x - u2.y, p2.y + u2.x);
-        v[3] = cmake(p2.x + u2.y, p2.y - u2.x);
+        const cplx x0 = v[0];
+        const cplx a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
+        const cplx a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
+        const cplx p1 = caxpy(c2, a2, caxpy(c1, a1, x0));
+        const cplx p2 = caxpy(c1, a2, caxpy(c2, a1, x0));
+        const cplx u1 = caxpy(s2, b2, cscale(b1, s1));
+        const cplx u2 = caxpy(-s1, b2, cscale(b1, s2));
+        v[0] = cadd(cadd(x0, a1), a2);
+        v[1] = cadd_i(p1, u1);
+        v[4] = csub_i(p1, u1);
+        v[2] = cadd_i(p2, u2);
+        v[3] = csub_i(p2, u2);
     }
 };
 

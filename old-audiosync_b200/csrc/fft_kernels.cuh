@@ -17,8 +17,12 @@
 //        the correlation itself is never written to memory.
 //
 // All passes are in-place radix passes in shared memory (decimation in
-// frequency forward, decimation in time for the inverse rows), the first pass
-// fused with the global load and the last with the global store / epilogue.
+// frequency forward, decimation in time for the inverse rows).  Tiles and rows
+// are staged global -> shared with cp.async (LDGSTS, 16 bytes per thread, no
+// registers, every request of the CTA in flight at once) so that the load of
+// one CTA overlaps the butterflies of the other CTAs on the SM; K_B's product
+// rows leave through the TMA unit (cp.async.bulk shared -> global).  The last
+// pass is fused with the global store / epilogue.
 //
 // Kernel bodies are written against an executor (DeviceExec on the GPU,
 // tests/emu's HostExec on the CPU) that runs one "phase" for every thread and
@@ -72,7 +76,10 @@ struct ArgmaxAcc {
 };
 
 // --------------------------------------------------------------------- K_A
-template <class RL, int NT, typename InT>
+// ASYNC (fp32 input, 16-byte aligned): the tile is staged with cp.async and the
+// zero half of the padded sample is written as zeros; otherwise (fp64 input or
+// unaligned pointers) the first pass loads, converts and packs through registers.
+template <class RL, int NT, typename InT, bool ASYNC>
 struct ColFwdKernel {
     static constexpr int M1 = RL::n;
     static constexpr int P = RL::count;
@@ -80,6 +87,8 @@ struct ColFwdKernel {
     static constexpr size_t SMEM = (size_t)M1 * COL_T * sizeof(cplx);
     static_assert(NT % COL_T == 0, "a thread must keep its column across items");
     static_assert(P >= 2, "column plans need at least two passes");
+    static_assert(!ASYNC || sizeof(InT) == 4, "async staging copies packed fp32 pairs verbatim");
+    static_assert(M1 % 2 == 0, "the zero half of the sample must be whole tile rows");
 
     struct Params {
         const InT* sources;      // [pair][2L] reals
@@ -108,14 +117,34 @@ struct ColFwdKernel {
         cplx* __restrict__ out = p.planes + (pair * 2 + sig) * M;
         const bool clears_peak = ex.bx() == 0 && sig == 0;
 
+        if constexpr (ASYNC) {
+            // tile row n1 = 16 packed points = 128 bytes = 8 chunks; shared tile has the same pitch
+            ex.phase([&](int tid) {
+                if (clears_peak && tid == 0) {
+                    PairPeak z; z.key = 0ull; z.raw_index = 0; z.peak = 0.0; z.resolved = 0; z.pad = 0;
+                    p.peaks[pair] = z;
+                }
+                const int rows_valid = sig == 0 ? M1 : M1 / 2;
+                const char* __restrict__ g = reinterpret_cast<const char*>(x) + (size_t)c0 * sizeof(cplx);
+                char* __restrict__ sm = reinterpret_cast<char*>(buf);
+                for (int q = tid; q < M1 * 8; q += NT) {
+                    const int row = q >> 3, part = q & 7;
+                    if (row < rows_valid) cp_async16(sm + q * 16, g + (size_t)row * M2 * sizeof(cplx) + part * 16);
+                    else smem_zero16(sm + q * 16);
+                }
+                cp_async_wait_all();
+            });
+        }
+
         static_for<0, P>([&](auto PP) {
             constexpr int ps = decltype(PP)::value;
             constexpr int R = RL::r(ps);
             constexpr int S = RL::stride(ps);
             constexpr bool first = ps == 0, last = ps == P - 1;
+            constexpr bool from_global = first && !ASYNC;
             constexpr int items = (M1 / R) * COL_T;
             ex.phase([&](int tid) {
-                if (first && clears_peak && tid == 0) {
+                if (from_global && clears_peak && tid == 0) {
                     PairPeak z; z.key = 0ull; z.raw_index = 0; z.peak = 0.0; z.resolved = 0; z.pad = 0;
                     p.peaks[pair] = z;
                 }
@@ -127,7 +156,7 @@ struct ColFwdKernel {
                         const int j = bf - blk * S;
                         const int i0 = blk * (S * R) + j;
                         cplx v[R];
-                        if constexpr (first) {
+                        if constexpr (from_global) {
                             static_for<0, R>([&](auto Q) {
                                 constexpr int q = decltype(Q)::value;
                                 const long long n = (long long)(i0 + q * S) * M2 + c0 + c;
@@ -191,6 +220,7 @@ struct ColInvKernel {
     static constexpr int THREADS = NT;
     static constexpr size_t SMEM = (size_t)M1 * COL_T * sizeof(cplx);
     static_assert(NT % COL_T == 0, "a thread must keep its column across items");
+    static_assert(NT % 32 == 0, "the argmax epilogue votes per warp");
     static_assert(P >= 2, "column plans need at least two passes");
 
     struct Params {
@@ -210,11 +240,19 @@ struct ColInvKernel {
         const int M2 = p.M2;
         const cplx* __restrict__ in = p.planes + pair * 2 * M;
 
+        // stage the tile: row n1 = 128 bytes = 8 chunks of 16 bytes
+        ex.phase([&](int tid) {
+            const char* __restrict__ g = reinterpret_cast<const char*>(in + c0);
+            char* __restrict__ sm = reinterpret_cast<char*>(buf);
+            for (int q = tid; q < M1 * 8; q += NT)
+                cp_async16(sm + q * 16, g + (size_t)(q >> 3) * M2 * sizeof(cplx) + (q & 7) * 16);
+            cp_async_wait_all();
+        });
+
         static_for<0, P - 1>([&](auto PP) {
             constexpr int ps = decltype(PP)::value;
             constexpr int R = RL::r(ps);
             constexpr int S = RL::stride(ps);
-            constexpr bool first = ps == 0;
             constexpr int items = (M1 / R) * COL_T;
             ex.phase([&](int tid) {
                 const int c = tid & (COL_T - 1);
@@ -226,8 +264,7 @@ struct ColInvKernel {
                     cplx v[R];
                     static_for<0, R>([&](auto Q) {
                         constexpr int q = decltype(Q)::value;
-                        if constexpr (first) v[q] = ldg(in + (long long)(i0 + q * S) * M2 + c0 + c);
-                        else v[q] = buf[(i0 + q * S) * COL_T + c];
+                        v[q] = buf[(i0 + q * S) * COL_T + c];
                     });
                     dft_reg<R, +1>(v);
                     cplx t[R];
@@ -243,6 +280,13 @@ struct ColInvKernel {
 
         // last pass + argmax epilogue: packed point n = n1*M2 + n2 carries
         // r[2n] (real part) and r[2n+1] (imaginary part).
+        //
+        // Only values that reach the best magnitude seen so far can matter, so a
+        // butterfly's 2R outputs are first reduced with fmax and compared with a
+        // threshold; the exact key logic runs only when the test passes.  The
+        // threshold starts from the pair's running maximum in global memory
+        // (earlier CTAs of this launch) and is shared across the warp after
+        // every hit, so the slow path is taken O(log) times per warp.
         {
             constexpr int ps = P - 1;
             constexpr int R = RL::r(ps);
@@ -251,10 +295,14 @@ struct ColInvKernel {
             ex.phase_argmax(
                 [&](int tid) -> unsigned long long {
                     ArgmaxAcc acc;
+                    const unsigned long long seen = ex.peek_key(&p.peaks[pair].key);
+                    if (seen != 0ull) acc.mag = float_from_order_bits((uint32_t)(seen >> 32));
                     const int c = tid & (COL_T - 1);
                     const bool col0 = (c0 + c) == 0;
-                    for (int w = tid; w < items; w += NT) {
-                        const int blk = w >> 4;
+                    for (int w0 = 0; w0 < items; w0 += NT) {      // warp-uniform trip count
+                        const int w = w0 + tid;
+                        const bool act = w < items;
+                        const int blk = (act ? w : 0) >> 4;
                         const int i0 = blk * R;
                         cplx v[R];
                         static_for<0, R>([&](auto Q) {
@@ -262,15 +310,27 @@ struct ColInvKernel {
                             v[q] = buf[(i0 + q) * COL_T + c];
                         });
                         dft_reg<R, +1>(v);
-                        const int f0 = RL::freq_of_pos(i0);
-                        static_for<0, R>([&](auto K) {
+                        float gm = fmaxf(fabsf(v[0].x), fabsf(v[0].y));
+                        static_for<1, R>([&](auto K) {
                             constexpr int k = decltype(K)::value;
-                            const int n1 = f0 + k * Wt;
-                            const uint32_t i_re = 2u * (uint32_t)((long long)n1 * M2 + c0 + c);
-                            if (col0 && n1 == 0) acc.consider_seed(v[k].x);
-                            else acc.consider(v[k].x, i_re);
-                            acc.consider(v[k].y, i_re + 1u);
+                            gm = fmaxf(gm, fmaxf(fabsf(v[k].x), fabsf(v[k].y)));
                         });
+                        const bool has_seed = col0 && i0 == 0;      // r[0]: signed seed, exact path always
+                        const bool need = act && (gm >= acc.mag || has_seed);
+                        if (ex.any(need)) {
+                            if (need) {
+                                const int f0 = RL::freq_of_pos(i0);
+                                static_for<0, R>([&](auto K) {
+                                    constexpr int k = decltype(K)::value;
+                                    const int n1 = f0 + k * Wt;
+                                    const uint32_t i_re = 2u * (uint32_t)((long long)n1 * M2 + c0 + c);
+                                    if (has_seed && n1 == 0) acc.consider_seed(v[k].x);
+                                    else acc.consider(v[k].x, i_re);
+                                    acc.consider(v[k].y, i_re + 1u);
+                                });
+                            }
+                            acc.mag = ex.warp_max(acc.mag);
+                        }
                     }
                     return acc.best;
                 },
@@ -313,7 +373,7 @@ struct RowFusedKernel {
     static constexpr size_t SMEM = (size_t)4 * RP * sizeof(cplx);
     static constexpr int R0 = RL::r(0);
     static constexpr int S0 = RL::stride(0);
-    static_assert(M2 % 2 == 0, "row length must be even");
+    static_assert(M2 % 2 == 0, "row length must be even (16-byte chunks, bulk store size)");
     static_assert(P >= 2, "row plans need at least two passes");
     static_assert(2 * (S0 + R0) <= 2 * RP, "final-pass twiddle tables must fit the dead sample rows");
 
@@ -350,13 +410,28 @@ struct RowFusedKernel {
         cplx* __restrict__ tab_ab = buf + 2 * RP;             // [2][S0]: W_M^(j*k1)
         cplx* __restrict__ tab_g = buf + 2 * RP + 2 * S0;     // [2][R0]: W_M^(k*S0*k1)
 
-        // ---- forward DIF on 2*nrows rows.  smem slots: 0,1 source rows; 2,3 sample rows.
+        // ---- stage the 2*nrows rows.  smem slots: 0,1 source rows; 2,3 sample rows.
+        ex.phase([&](int tid) {
+            constexpr int cpr = M2 / 2;                       // 16-byte chunks per row
+            const int chunks = cpr * 2 * nrows;
+            for (int q = tid; q < chunks; q += NT) {
+                const int b = q / cpr;
+                const int part = q - b * cpr;
+                const int is_smp = b >= nrows ? 1 : 0;
+                const int rr = b - is_smp * nrows;
+                const cplx* __restrict__ g = (is_smp ? plane_p : plane_s) + (long long)(rr ? k1b : k1a) * M2;
+                cp_async16(reinterpret_cast<char*>(buf + (is_smp * 2 + rr) * RP) + part * 16,
+                           reinterpret_cast<const char*>(g) + part * 16);
+            }
+            cp_async_wait_all();
+        });
+
+        // ---- forward DIF on 2*nrows rows.
         static_for<0, P>([&](auto PP) {
             constexpr int ps = decltype(PP)::value;
             constexpr int R = RL::r(ps);
             constexpr int S = RL::stride(ps);
             constexpr int SL = slots(S);
-            constexpr bool first = ps == 0;
             constexpr int per_row = (M2 / (S * R)) * SL;
             const int items = per_row * 2 * nrows;
             ex.phase([&](int tid) {
@@ -371,19 +446,10 @@ struct RowFusedKernel {
                     cplx* __restrict__ row = buf + (is_smp * 2 + rr) * RP;
                     const int i0 = blk * (S * R) + j;
                     cplx v[R];
-                    if constexpr (first) {
-                        const cplx* __restrict__ g =
-                            (is_smp ? plane_p : plane_s) + (long long)(rr ? k1b : k1a) * M2;
-                        static_for<0, R>([&](auto Q) {
-                            constexpr int q = decltype(Q)::value;
-                            v[q] = g[i0 + q * S];
-                        });
-                    } else {
-                        static_for<0, R>([&](auto Q) {
-                            constexpr int q = decltype(Q)::value;
-                            v[q] = row[i0 + q * S];
-                        });
-                    }
+                    static_for<0, R>([&](auto Q) {
+                        constexpr int q = decltype(Q)::value;
+                        v[q] = row[i0 + q * S];
+                    });
                     dft_reg<R, -1>(v);
                     row[i0] = v[0];
                     if constexpr (S > 1) {
@@ -486,17 +552,23 @@ struct RowFusedKernel {
                         });
                     } else {
                         // natural order n2 = j + k*S0; conj W_M^(n2*k1) = conj(ab[j] * g[k]); in place
-                        const unsigned k1 = (unsigned)(rr ? k1b : k1a);
-                        cplx* __restrict__ g = plane_s + (long long)k1 * M2;
                         const cplx t0 = tab_ab[rr * S0 + j];
-                        g[j] = cmulc(v[0], t0);
+                        row[j] = cmulc(v[0], t0);
                         static_for<1, R>([&](auto K) {
                             constexpr int k = decltype(K)::value;
-                            g[j + k * S] = cmulc(v[k], cmul(t0, tab_g[rr * R0 + k]));
+                            row[j + k * S] = cmulc(v[k], cmul(t0, tab_g[rr * R0 + k]));
                         });
                     }
                 }
+                if constexpr (last) fence_async_proxy();   // rows are read by the bulk store below
             });
+        });
+
+        // ---- the product rows leave through the TMA unit, back in place (row k1 of plane 0).
+        ex.single([&]() {
+            bulk_store(plane_s + (long long)k1a * M2, buf, (unsigned)(M2 * sizeof(cplx)));
+            if (two) bulk_store(plane_s + (long long)k1b * M2, buf + RP, (unsigned)(M2 * sizeof(cplx)));
+            bulk_store_commit_and_drain();
         });
     }
 };
@@ -532,6 +604,37 @@ struct DeviceExec {
 #if defined(__CUDA_ARCH__)
         f((int)threadIdx.x);
         __syncthreads();
+#endif
+    }
+    // f() on one thread of the CTA, after the barrier of the preceding phase.
+    template <class F>
+    ASC_HD void single(F&& f) {
+#if defined(__CUDA_ARCH__)
+        if (threadIdx.x == 0) f();
+#endif
+    }
+    // warp vote / warp maximum of a non-negative threshold (negative or NaN counts as 0);
+    // every lane of the warp must call them.
+    ASC_HD bool any(bool b) const {
+#if defined(__CUDA_ARCH__)
+        return __any_sync(0xffffffffu, b);
+#else
+        return b;
+#endif
+    }
+    ASC_HD float warp_max(float m) const {
+#if defined(__CUDA_ARCH__)
+        return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(m, 0.0f))));
+#else
+        return m;
+#endif
+    }
+    // current value of a key other CTAs of this launch update with atomicMax
+    ASC_HD unsigned long long peek_key(const unsigned long long* k) const {
+#if defined(__CUDA_ARCH__)
+        return __ldcg(k);
+#else
+        return *k;
 #endif
     }
     // CTA-wide maximum of a per-thread key, then one atomicMax on *dst.

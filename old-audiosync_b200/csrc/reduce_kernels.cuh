@@ -215,23 +215,67 @@ pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
         const double px = s_piv[0], py = s_piv[1];
         long long hi = lo + PEARSON_CHUNK;
         if (hi > w.n) hi = w.n;
-        constexpr int UN = 8;
-        long long i = lo + t;
-        for (; i + (UN - 1) * PEARSON_THREADS < hi; i += UN * PEARSON_THREADS) {
-            T xv[UN], yv[UN];
+        if constexpr (sizeof(T) == 4) {
+            // fp32 inputs: shifted values and products in fp32, 16 elements per thread and
+            // iteration summed in fp32 (every term is < 4, so the partial is good to ~1e-7
+            // relative), then folded into the fp64 accumulators -- 5 conversions per 16
+            // elements instead of 2 per element.  The three product sums share one
+            // instruction sequence, so identical windows still give cov == varx == vary.
+            const float pxf = (float)px, pyf = (float)py;
+            const bool xv = (reinterpret_cast<uintptr_t>(x + lo) & 15u) == 0;
+            const bool yv = (reinterpret_cast<uintptr_t>(y + lo) & 15u) == 0;
+            constexpr int VPT = 4;                                   // float4 groups per thread and iteration
+            constexpr long long STEP = 4LL * PEARSON_THREADS;        // elements per group row
+            auto load4 = [](const float* __restrict__ p, bool vec) -> float4 {
+                if (vec) return __ldg(reinterpret_cast<const float4*>(p));
+                return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+            };
+            long long i = lo + 4LL * t;
+            for (; i + (VPT - 1) * STEP + 3 < hi; i += VPT * STEP) {
+                float4 xq[VPT], yq[VPT];
 #pragma unroll
-            for (int u = 0; u < UN; u++) { xv[u] = x[i + u * PEARSON_THREADS]; yv[u] = y[i + u * PEARSON_THREADS]; }
+                for (int u = 0; u < VPT; u++) { xq[u] = load4(x + i + u * STEP, xv); yq[u] = load4(y + i + u * STEP, yv); }
+                float fsx = 0.f, fsy = 0.f, fsxx = 0.f, fsyy = 0.f, fsxy = 0.f;
 #pragma unroll
-            for (int u = 0; u < UN; u++) {
-                const double dx = (double)xv[u] - px, dy = (double)yv[u] - py;
+                for (int u = 0; u < VPT; u++) {
+                    const float dx[4] = {xq[u].x - pxf, xq[u].y - pxf, xq[u].z - pxf, xq[u].w - pxf};
+                    const float dy[4] = {yq[u].x - pyf, yq[u].y - pyf, yq[u].z - pyf, yq[u].w - pyf};
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        fsx += dx[e]; fsy += dy[e];
+                        fsxx = fmaf(dx[e], dx[e], fsxx); fsyy = fmaf(dy[e], dy[e], fsyy); fsxy = fmaf(dx[e], dy[e], fsxy);
+                    }
+                }
+                acc.sx += (double)fsx; acc.sy += (double)fsy;
+                acc.sxx += (double)fsxx; acc.syy += (double)fsyy; acc.sxy += (double)fsxy;
+            }
+            // remainder of the chunk (window tail): element-wise, same fp32 shift
+            for (long long k = i; k < hi; k += STEP) {
+                for (int e = 0; e < 4 && k + e < hi; e++) {
+                    const float dx = (float)x[k + e] - pxf, dy = (float)y[k + e] - pyf;
+                    acc.sx += (double)dx; acc.sy += (double)dy;
+                    acc.sxx += (double)(dx * dx); acc.syy += (double)(dy * dy); acc.sxy += (double)(dx * dy);
+                }
+            }
+        } else {
+            constexpr int UN = 8;
+            long long i = lo + t;
+            for (; i + (UN - 1) * PEARSON_THREADS < hi; i += UN * PEARSON_THREADS) {
+                T xv[UN], yv[UN];
+#pragma unroll
+                for (int u = 0; u < UN; u++) { xv[u] = x[i + u * PEARSON_THREADS]; yv[u] = y[i + u * PEARSON_THREADS]; }
+#pragma unroll
+                for (int u = 0; u < UN; u++) {
+                    const double dx = (double)xv[u] - px, dy = (double)yv[u] - py;
+                    acc.sx += dx; acc.sy += dy;
+                    acc.sxx = fma(dx, dx, acc.sxx); acc.syy = fma(dy, dy, acc.syy); acc.sxy = fma(dx, dy, acc.sxy);
+                }
+            }
+            for (; i < hi; i += PEARSON_THREADS) {
+                const double dx = (double)x[i] - px, dy = (double)y[i] - py;
                 acc.sx += dx; acc.sy += dy;
                 acc.sxx = fma(dx, dx, acc.sxx); acc.syy = fma(dy, dy, acc.syy); acc.sxy = fma(dx, dy, acc.sxy);
             }
-        }
-        for (; i < hi; i += PEARSON_THREADS) {
-            const double dx = (double)x[i] - px, dy = (double)y[i] - py;
-            acc.sx += dx; acc.sy += dy;
-            acc.sxx = fma(dx, dx, acc.sxx); acc.syy = fma(dy, dy, acc.syy); acc.sxy = fma(dx, dy, acc.sxy);
         }
     }
     for (int o = 16; o > 0; o >>= 1) {

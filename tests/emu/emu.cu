@@ -24,6 +24,11 @@ struct HostExec {
         for (int t = 0; t < nt; t++) f(t);
     }
     template <class F>
+    void single(F&& f) { f(); }
+    bool any(bool b) const { return b; }
+    float warp_max(float m) const { return m; }
+    unsigned long long peek_key(const unsigned long long* k) const { return *k; }
+    template <class F>
     void phase_argmax(F&& f, unsigned long long* dst, void* /*scratch*/) {
         unsigned long long best = 0;
         for (int t = 0; t < nt; t++) {
@@ -51,7 +56,7 @@ static int run_static(const InT* source, const InT* sample, PairPeak* peak, cplx
     peak->key = 12345ull;   // garbage: K_A must clear it
 
     {
-        using K = ColFwdKernel<Col, P::NT_COL, InT>;
+        using K = ColFwdKernel<Col, P::NT_COL, InT, sizeof(InT) == 4>;
         typename K::Params p{source, sample, planes.data(), peak, col_tw.data(), col_tc.data(), m_lo.data(), m_hi.data(), M, M2};
         std::vector<cplx> smem(K::SMEM / sizeof(cplx));
         for (int sig = 0; sig < 2; sig++)

@@ -111,12 +111,13 @@ def test_small_path_against_oracle(emu, L):
 
 def test_kat_sine_cases_through_emulator(emu):
     # reference tests/test_cross_correlation.c T7, T8 (L = 1000)
-    # T7 (sin(i) vs sin(i)) has peaks at 0 and 710 (= 113 * 2pi + 6e-5) that differ by
-    # 1.2e-9 relative: only the fp64 direct path, AUTO's choice at L = 1000, can
-    # separate them.  The fp32 transform must still land on one of the two.
+    # T7 (sin(i) vs sin(i)) has peaks at 0, 710 (= 113 * 2pi + 6e-5) and, negated, 355
+    # (= 113 * pi + 3e-5) whose magnitudes differ by ~1e-9 relative: only the fp64 direct
+    # path, AUTO's choice at L = 1000, can separate them.  The fp32 transform must still
+    # land on one of the three.
     p7 = np.sin(np.arange(1000.0))
     idx, _, _ = run_emu(emu, np.sin(np.arange(2000.0)), p7, f64=True)
-    assert idx in (0, 710)
+    assert idx in (0, 355, 710)
     s8 = np.concatenate([np.sin(np.arange(1000.0) + 180), np.zeros(1000)])
     idx, peak, _ = run_emu(emu, s8, p7, f64=True)
     assert idx == 1999 and peak < 0               # lag -1, negative correlation

@@ -35,3 +35,14 @@ for k, lines in per.items():
         agg = {h: sum(num(l.get(h, 0)) for l in lines) for h in reasons}
         s = sum(agg.values()) or 1
         print("stall reasons:", ", ".join("%s %.1f%%" % (h[6:], 100 * v / s) for h, v in sorted(agg.items(), key=lambda kv: -kv[1])[:8]))
+    # phase view: SASS order split at barriers (kernels are fully unrolled pass by pass)
+    seg = []; cur = {"i": 0.0, "s": 0.0, "n": 0, "ldg": 0.0, "fp": 0.0}
+    for l in lines:
+        m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)", l["Source"]); op = m.group(2) if m else "?"
+        cur["i"] += num(l["Instructions Executed"]); cur["s"] += num(l["# Samples"]); cur["n"] += 1
+        if op in ("LDG", "STG", "LDGSTS"): cur["ldg"] += num(l["Instructions Executed"])
+        if op in ("FADD2", "FMUL2", "FFMA2", "FADD", "FMUL", "FFMA"): cur["fp"] += num(l["Instructions Executed"])
+        if op == "BAR":
+            seg.append(cur); cur = {"i": 0.0, "s": 0.0, "n": 0, "ldg": 0.0, "fp": 0.0}
+    seg.append(cur)
+    print("phases (between barriers): " + " | ".join("%d: %.1f%%t %.1fMi fp%.1fM g%.2fM" % (j, 100 * g["s"] / max(1, tot_s), g["i"] / 1e6, g["fp"] / 1e6, g["ldg"] / 1e6) for j, g in enumerate(seg)))
