@@ -150,7 +150,7 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
     const dim3 grid_a(M2 / COL_T, 2, pairs);
     auto col_fwd = [&](auto KK, const auto* s_in, const auto* m_in) -> int {
         using K = decltype(KK);
-        typename K::Params p{s_in, m_in, planes, peaks, col_tw, col_tc, m_lo, m_hi, P::L, M2};
+        typename K::Params p{s_in, m_in, planes, peaks, col_tw, col_tc, m_lo, m_hi, P::L};
         return launch(ctx, d, KC_COL_FWD, st, [&] {
             fft_kernel_entry<K><<<grid_a, K::THREADS, K::SMEM, st>>>(p);
         });
@@ -161,25 +161,25 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
         const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(smp)) & 15u) == 0;
         const float* s_in = static_cast<const float*>(src);
         const float* m_in = static_cast<const float*>(smp);
-        const int rc = aligned ? col_fwd(ColFwdKernel<Col, P::NT_COL, float, true>{}, s_in, m_in)
-                               : col_fwd(ColFwdKernel<Col, P::NT_COL, float, false>{}, s_in, m_in);
+        const int rc = aligned ? col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, float, true>{}, s_in, m_in)
+                               : col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, float, false>{}, s_in, m_in);
         if (rc != 0) return -1;
     } else {
-        if (col_fwd(ColFwdKernel<Col, P::NT_COL, double, false>{}, static_cast<const double*>(src),
+        if (col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, double, false>{}, static_cast<const double*>(src),
                     static_cast<const double*>(smp)) != 0) return -1;
     }
     {
-        using K = RowFusedKernel<Row, P::NT_ROW>;
-        typename K::Params p{planes, row_tw, row_rev, m_lo, m_hi, n_lo, n_hi, P::L, M1};
+        using K = RowFusedKernel<Row, Col::n, P::NT_ROW>;
+        typename K::Params p{planes, row_tw, row_rev, m_lo, m_hi, n_lo, n_hi, P::L};
         const dim3 grid(M1 / 2 + 1, 1, pairs);
         if (launch(ctx, d, KC_ROW_FUSED, st, [&] {
                 fft_kernel_entry<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
             }) != 0) return -1;
     }
     {
-        using K = ColInvKernel<Col, P::NT_COL>;
-        typename K::Params p{planes, peaks, col_tw, P::L, M2};
-        const dim3 grid(M2 / COL_T, 1, pairs);
+        using K = ColInvKernel<Col, Row::n, P::NT_COL>;
+        typename K::Params p{planes, peaks, col_tw, P::L};
+        const dim3 grid(pairs, M2 / COL_T, 1);
         if (launch(ctx, d, KC_COL_INV, st, [&] {
                 fft_kernel_entry<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
             }) != 0) return -1;
@@ -213,11 +213,11 @@ static int build_static_plan(FftPlan* plan) {
         upload(plan->m_lo, m_lo) != 0 || upload(plan->m_hi, m_hi) != 0 ||
         upload(plan->n_lo, n_lo) != 0 || upload(plan->n_hi, n_hi) != 0)
         return -1;
-    if (prepare_kernel<ColFwdKernel<Col, P::NT_COL, float, true>>(ColFwdKernel<Col, P::NT_COL, float, true>::SMEM) != 0 ||
-        prepare_kernel<ColFwdKernel<Col, P::NT_COL, float, false>>(ColFwdKernel<Col, P::NT_COL, float, false>::SMEM) != 0 ||
-        prepare_kernel<ColFwdKernel<Col, P::NT_COL, double, false>>(ColFwdKernel<Col, P::NT_COL, double, false>::SMEM) != 0 ||
-        prepare_kernel<RowFusedKernel<Row, P::NT_ROW>>(RowFusedKernel<Row, P::NT_ROW>::SMEM) != 0 ||
-        prepare_kernel<ColInvKernel<Col, P::NT_COL>>(ColInvKernel<Col, P::NT_COL>::SMEM) != 0)
+    if (prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, true>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, true>::SMEM) != 0 ||
+        prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, false>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, false>::SMEM) != 0 ||
+        prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, double, false>>(ColFwdKernel<Col, Row::n, P::NT_COL, double, false>::SMEM) != 0 ||
+        prepare_kernel<RowFusedKernel<Row, Col::n, P::NT_ROW>>(RowFusedKernel<Row, Col::n, P::NT_ROW>::SMEM) != 0 ||
+        prepare_kernel<ColInvKernel<Col, Row::n, P::NT_COL>>(ColInvKernel<Col, Row::n, P::NT_COL>::SMEM) != 0)
         return -1;
     plan->run_wave = [plan](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
                             int dtype, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {

@@ -79,9 +79,11 @@ struct ArgmaxAcc {
 // ASYNC (fp32 input, 16-byte aligned): the tile is staged with cp.async and the
 // zero half of the padded sample is written as zeros; otherwise (fp64 input or
 // unaligned pointers) the first pass loads, converts and packs through registers.
-template <class RL, int NT, typename InT, bool ASYNC>
+template <class RL, int M2_, int NT, typename InT, bool ASYNC>
 struct ColFwdKernel {
+    static constexpr int MIN_CTAS = 3;
     static constexpr int M1 = RL::n;
+    static constexpr int M2 = M2_;                  // row length (compile time: index products fold)
     static constexpr int P = RL::count;
     static constexpr int THREADS = NT;
     static constexpr size_t SMEM = (size_t)M1 * COL_T * sizeof(cplx);
@@ -99,8 +101,7 @@ struct ColFwdKernel {
         const cplx* tc;          // [M1/R_last][16]: W_M^(c*f0)
         const cplx* m_lo;        // W_M two-level tables
         const cplx* m_hi;
-        long long L;             // sample_len == M
-        int M2;
+        long long L;             // sample_len == M = M1 * M2
     };
 
     // grid = (M2 / 16, 2, pairs)
@@ -110,7 +111,6 @@ struct ColFwdKernel {
         const int sig = ex.by();
         const long long pair = ex.bz();
         const long long M = p.L;
-        const int M2 = p.M2;
         const InT* __restrict__ x = sig == 0 ? p.sources + pair * 2 * M : p.samples + pair * M;
         // number of valid packed points: source M, sample M/2 (upper half is the zero pad)
         const long long nvalid = sig == 0 ? M : M / 2;
@@ -200,10 +200,11 @@ struct ColFwdKernel {
                         const int f0 = RL::freq_of_pos(i0);
                         const cplx t0 = cmul(ldg(p.tc + f0 * COL_T + c),
                                              tw2(p.m_lo, p.m_hi, (unsigned)c0 * (unsigned)f0));
-                        out[(long long)f0 * M2 + n2] = cmul(v[0], t0);
+                        cplx* __restrict__ o = out + ((unsigned)f0 * (unsigned)M2 + n2);   // < M < 2^31
+                        o[0] = cmul(v[0], t0);
                         static_for<1, R>([&](auto K) {
                             constexpr int k = decltype(K)::value;
-                            out[(long long)(f0 + k * Wt) * M2 + n2] = cmul(v[k], cmul(t0, g[k]));
+                            o[(size_t)k * Wt * M2] = cmul(v[k], cmul(t0, g[k]));
                         });
                     }
                 }
@@ -213,9 +214,11 @@ struct ColFwdKernel {
 };
 
 // --------------------------------------------------------------------- K_C
-template <class RL, int NT>
+template <class RL, int M2_, int NT>
 struct ColInvKernel {
+    static constexpr int MIN_CTAS = 3;
     static constexpr int M1 = RL::n;
+    static constexpr int M2 = M2_;
     static constexpr int P = RL::count;
     static constexpr int THREADS = NT;
     static constexpr size_t SMEM = (size_t)M1 * COL_T * sizeof(cplx);
@@ -228,16 +231,15 @@ struct ColInvKernel {
         PairPeak* peaks;         // [pair]
         const cplx* tw;          // RL pass tables (forward sign; conjugated here)
         long long L;
-        int M2;
     };
 
-    // grid = (M2 / 16, 1, pairs)
+    // grid = (pairs, M2 / 16): the pair index runs fastest, so the tiles of one pair are
+    // spread over the launch and later tiles see the running maximum of earlier ones.
     template <class Ex>
     static ASC_HD void run(Ex& ex, const Params& p, cplx* __restrict__ buf) {
-        const int c0 = ex.bx() * COL_T;
-        const long long pair = ex.bz();
+        const int c0 = ex.by() * COL_T;
+        const long long pair = ex.bx();
         const long long M = p.L;
-        const int M2 = p.M2;
         const cplx* __restrict__ in = p.planes + pair * 2 * M;
 
         // stage the tile: row n1 = 128 bytes = 8 chunks of 16 bytes
@@ -323,7 +325,7 @@ struct ColInvKernel {
                                 static_for<0, R>([&](auto K) {
                                     constexpr int k = decltype(K)::value;
                                     const int n1 = f0 + k * Wt;
-                                    const uint32_t i_re = 2u * (uint32_t)((long long)n1 * M2 + c0 + c);
+                                    const uint32_t i_re = 2u * ((uint32_t)n1 * (uint32_t)M2 + (uint32_t)(c0 + c));
                                     if (has_seed && n1 == 0) acc.consider_seed(v[k].x);
                                     else acc.consider(v[k].x, i_re);
                                     acc.consider(v[k].y, i_re + 1u);
@@ -364,9 +366,11 @@ ASC_HD void split_mul_merge(cplx a, cplx b, cplx c, cplx d, cplx w, cplx& qk, cp
     qmk = cmake(0.25f * (g.x - h.x), -0.25f * (g.y - h.y));
 }
 
-template <class RL, int NT>
+template <class RL, int M1_, int NT>
 struct RowFusedKernel {
+    static constexpr int MIN_CTAS = 3;
     static constexpr int M2 = RL::n;
+    static constexpr int M1 = M1_;
     static constexpr int P = RL::count;
     static constexpr int THREADS = NT;
     static constexpr int RP = M2;   // row pitch in shared memory
@@ -391,7 +395,6 @@ struct RowFusedKernel {
         const cplx* n_lo;        // W_N = W_2M tables
         const cplx* n_hi;
         long long L;
-        int M1;
     };
 
     // grid = (M1/2 + 1, 1, pairs); CTA r owns rows r and M1 - r.
@@ -400,7 +403,6 @@ struct RowFusedKernel {
         const int r = ex.bx();
         const long long pair = ex.bz();
         const long long M = p.L;
-        const int M1 = p.M1;
         const bool two = (r != 0) && (2 * r != M1);
         const int nrows = two ? 2 : 1;
         const int k1a = r, k1b = M1 - r;   // k1b unused when !two
@@ -669,8 +671,15 @@ struct DeviceExec {
 };
 
 #if defined(__CUDACC__)
+// Resident CTAs per SM the register allocation must allow: the static four-step kernels are
+// sized (shared memory) for 3 CTAs per SM; kernels without a MIN_CTAS member ask for 1.
+template <class K, class = void>
+struct min_ctas_of { static constexpr int value = 1; };
 template <class K>
-__global__ void __launch_bounds__(K::THREADS) fft_kernel_entry(const typename K::Params p) {
+struct min_ctas_of<K, std::void_t<decltype(K::MIN_CTAS)>> { static constexpr int value = K::MIN_CTAS; };
+
+template <class K>
+__global__ void __launch_bounds__(K::THREADS, min_ctas_of<K>::value) fft_kernel_entry(const typename K::Params p) {
     extern __shared__ __align__(16) unsigned char asc_smem[];
     DeviceExec ex;
     K::run(ex, p, reinterpret_cast<cplx*>(asc_smem));

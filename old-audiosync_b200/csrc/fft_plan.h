@@ -51,11 +51,17 @@ struct Plan960k {
     using Row = RadixList<10, 16, 15>;   // M2 = 2400
     static constexpr int NT_COL = 320, NT_ROW = 320;
 };
+#ifndef ASC_NT_COL_1440K
+#define ASC_NT_COL_1440K 320
+#endif
+#ifndef ASC_NT_ROW_1440K
+#define ASC_NT_ROW_1440K 320
+#endif
 struct Plan1440k {
     static constexpr long long L = 1440000;
     using Col = RadixList<10, 10, 6>;    // M1 = 600
     using Row = RadixList<10, 16, 15>;   // M2 = 2400
-    static constexpr int NT_COL = 320, NT_ROW = 320;
+    static constexpr int NT_COL = ASC_NT_COL_1440K, NT_ROW = ASC_NT_ROW_1440K;
 };
 
 using StaticPlans = std::tuple<Plan144k, Plan288k, Plan480k, Plan720k, Plan960k, Plan1440k>;

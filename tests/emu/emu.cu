@@ -56,8 +56,8 @@ static int run_static(const InT* source, const InT* sample, PairPeak* peak, cplx
     peak->key = 12345ull;   // garbage: K_A must clear it
 
     {
-        using K = ColFwdKernel<Col, P::NT_COL, InT, sizeof(InT) == 4>;
-        typename K::Params p{source, sample, planes.data(), peak, col_tw.data(), col_tc.data(), m_lo.data(), m_hi.data(), M, M2};
+        using K = ColFwdKernel<Col, Row::n, P::NT_COL, InT, sizeof(InT) == 4>;
+        typename K::Params p{source, sample, planes.data(), peak, col_tw.data(), col_tc.data(), m_lo.data(), m_hi.data(), M};
         std::vector<cplx> smem(K::SMEM / sizeof(cplx));
         for (int sig = 0; sig < 2; sig++)
             for (int tile = 0; tile < M2 / COL_T; tile++) {
@@ -66,8 +66,8 @@ static int run_static(const InT* source, const InT* sample, PairPeak* peak, cplx
             }
     }
     {
-        using K = RowFusedKernel<Row, P::NT_ROW>;
-        typename K::Params p{planes.data(), row_tw.data(), row_rev.data(), m_lo.data(), m_hi.data(), n_lo.data(), n_hi.data(), M, M1};
+        using K = RowFusedKernel<Row, Col::n, P::NT_ROW>;
+        typename K::Params p{planes.data(), row_tw.data(), row_rev.data(), m_lo.data(), m_hi.data(), n_lo.data(), n_hi.data(), M};
         std::vector<cplx> smem(K::SMEM / sizeof(cplx));
         for (int r = 0; r <= M1 / 2; r++) {
             HostExec ex{r, 0, 0, K::THREADS};
@@ -76,11 +76,11 @@ static int run_static(const InT* source, const InT* sample, PairPeak* peak, cplx
     }
     if (planes_out) memcpy(planes_out, planes.data(), sizeof(cplx) * M);
     {
-        using K = ColInvKernel<Col, P::NT_COL>;
-        typename K::Params p{planes.data(), peak, col_tw.data(), M, M2};
+        using K = ColInvKernel<Col, Row::n, P::NT_COL>;
+        typename K::Params p{planes.data(), peak, col_tw.data(), M};
         std::vector<cplx> smem(K::SMEM / sizeof(cplx));
         for (int tile = 0; tile < M2 / COL_T; tile++) {
-            HostExec ex{tile, 0, 0, K::THREADS};
+            HostExec ex{0, tile, 0, K::THREADS};      // K_C grid = (pairs, tiles)
             K::run(ex, p, smem.data());
         }
     }
