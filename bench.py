@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--wave", type=int, default=0, help="pairs per kernel wave (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     return ap.parse_args()
 
 
@@ -78,81 +79,83 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled (NVML, every 50 ms) while the timed region runs."""
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.on, self.s, self.t, self.h, self.nv = index, False, [], None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
         except Exception:
-            self.proc = None
+            self.nv = None
+            return
+        self.on = True
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        while self.on:
+            try:
+                self.s.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM),
+                               nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                               nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception:
+                break
+            time.sleep(0.05)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); smax = float(f[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        # samples under load = upper half of the observed clocks
-        sm_load = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": statistics.median(sm_load) if sm_load else None, "sm_max_mhz": smax,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.on = False
+        self.t.join(timeout=2)
+        nv = self.nv
+        smax = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        # the first sample can predate the load: drop it when there are others
+        s = self.s[1:] if len(self.s) > 2 else self.s
+        clk = sorted(x[0] for x in s)
+        pw = sorted(x[1] for x in s)
+        reasons = sorted(k for k, bit in names.items() if any(x[2] & bit for x in s))
+        return {"sm_mhz": statistics.median(clk) if clk else None, "sm_min_mhz": clk[0] if clk else None,
+                "sm_max_mhz": smax, "power_w_median": statistics.median(pw) if pw else None,
+                "reasons": reasons, "samples": len(s)}
 
 
 # ------------------------------------------------------------------ reference arm / CPU baseline
 
-def cpu_reference_run(sample_len: int, n_pairs: int, threads: int, seed: int):
+def cpu_reference_run(sample_len: int, n_pairs: int, threads: int, seed: int, distinct: int = 0):
     """Times the reference's CPU path on n_pairs seeded pairs with `threads` concurrent callers.
 
     Uses oracle/_ref (the reference's own src/cross_correlation.c compiled against the
-    FFT shim; kind "reference") when that build is present, else the restatement
-    (kind "port").  Returns (seconds, kind, backend, lags).
+    FFT stand-in; kind "reference") when that build is present, else the restatement
+    (kind "port").  Only `distinct` (default: all) different pairs are generated and they
+    are cycled through, so a many-second sample does not need gigabytes of inputs.
+    Returns (seconds, kind, backend, lags).
     """
-    import numpy as np
     from oracle import capi
     ref = capi.ref_lib()
     kind = "reference" if ref is not None else "port"
+    distinct = min(n_pairs, distinct or n_pairs)
     lags = [None] * n_pairs
-    inputs = [capi.synth_pair(seed, i, sample_len) for i in range(n_pairs)]   # outside the timing
+    inputs = [capi.synth_pair(seed, i, sample_len) for i in range(distinct)]   # outside the timing
 
     def work(tid):
         for i in range(tid, n_pairs, threads):
-            s, p = inputs[i]
+            s, p = inputs[i % distinct]
             if ref is not None:
                 lags[i] = capi.ref_cross_correlation(s, p)[1]
             else:
                 lags[i] = capi.cross_correlation(s, p)["lag"]
 
-    if n_pairs:                       # warm the shim's twiddle cache like a long-lived process
+    if n_pairs:                       # warm the stand-in's twiddle cache like a long-lived process
         s, p = inputs[0]
         (capi.ref_cross_correlation if ref is not None else capi.cross_correlation)(s, p)
     t0 = time.perf_counter()
@@ -161,8 +164,24 @@ def cpu_reference_run(sample_len: int, n_pairs: int, threads: int, seed: int):
     [t.join() for t in th]
     dt = time.perf_counter() - t0
     for i in range(n_pairs):
-        assert lags[i] == capi.synth_true_lag(seed, i, sample_len), "CPU reference lost a lag"
+        assert lags[i] == capi.synth_true_lag(seed, i % distinct, sample_len), "CPU reference lost a lag"
     return dt, kind, capi.backend(), lags
+
+
+def cpu_baseline_sample(sample_len: int, seed: int, target_s: float = 12.0):
+    """About `target_s` seconds of the reference's CPU path with every host core busy."""
+    cores = os.cpu_count() or 1
+    callers = max(1, cores // 2)          # the reference runs two FFT threads per call
+    probe = max(callers, 4)
+    dt, kind, backend, _ = cpu_reference_run(sample_len, probe, callers, seed)
+    rate = probe / dt
+    npairs = int(max(2 * callers, min(4096, rate * target_s)))
+    npairs -= npairs % callers
+    dt, kind, backend, _ = cpu_reference_run(sample_len, npairs, callers, seed, distinct=2 * callers)
+    return {"value": npairs / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d pairs (%d distinct, cycled) of the same workload, %d concurrent callers x 2 FFT "
+                      "threads, %.1f s wall, FFT backend %s (stand-in for FFTW3, which is not installed)"
+                      % (npairs, min(npairs, 2 * callers), callers, dt, backend)}
 
 
 def run_reference_arm(args):
@@ -201,6 +220,53 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ single-pair latency
+
+def measure_latency(ctx, ac, torch, dev, local, stream, d_src, d_smp, d_res, n, L, reps=200):
+    """BASELINE config 3: one L-frame pair per call.
+
+    (i) device-resident fp32 inputs, CUDA events around each call on the launching stream; the
+    calls rotate through 16 different resident pairs (276 MB at L = 1.44M > L2), so no call finds
+    its inputs in cache.  (ii) the unchanged C signature `cross_correlation(double*, double*, ...)`
+    on pinned host doubles: wall clock, upload of 34.56 MB and the 24-byte answer included.
+    """
+    import numpy as np
+    out = {}
+    rot = min(16, n)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i in range(20 + reps):
+        k = i % rot
+        if i >= 20:
+            ev[i - 20][0].record(stream)
+        ctx.xcorr_batch_device(local, d_src.data_ptr() + k * 2 * L * 4, d_smp.data_ptr() + k * L * 4, 1, L,
+                               ac.F32, d_res.data_ptr(), stream.cuda_stream)
+        if i >= 20:
+            ev[i - 20][1].record(stream)
+    torch.cuda.synchronize(dev)
+    t = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
+    out["device_resident_f32_us"] = {"p50": t[len(t) // 2], "p95": t[int(len(t) * 0.95)], "calls": reps,
+                                     "launches_per_call": 4}
+    # (ii) drop-in C ABI on host doubles (buffers from the library's pinned fftw_alloc_real)
+    lib = ac.lib()
+    import ctypes as C
+    ps, pm = lib.fftw_alloc_real(2 * L), lib.fftw_alloc_real(L)
+    hs = np.ctypeslib.as_array(C.cast(ps, C.POINTER(C.c_double)), shape=(2 * L,))
+    hm = np.ctypeslib.as_array(C.cast(pm, C.POINTER(C.c_double)), shape=(L,))
+    hs[:] = d_src[: 2 * L].cpu().numpy(); hm[:] = d_smp[:L].cpu().numpy()
+    lag, coef = C.c_long(0), C.c_double(0.0)
+    wall = []
+    for i in range(5 + 30):
+        t0 = time.perf_counter()
+        rc = lib.cross_correlation(ps, pm, L, C.byref(lag), C.byref(coef))
+        if i >= 5:
+            wall.append((time.perf_counter() - t0) * 1e3)
+    wall.sort()
+    out["c_abi_host_f64_ms"] = {"p50": wall[len(wall) // 2], "p95": wall[int(len(wall) * 0.95)], "calls": len(wall),
+                                "h2d_bytes_per_call": 3 * L * 8, "ret": rc, "lag": lag.value}
+    lib.fftw_free(ps); lib.fftw_free(pm)
+    return out
+
+
 # ------------------------------------------------------------------ our arm
 
 def main():
@@ -230,7 +296,8 @@ def main():
 
     L, n = args.sample_len, args.pairs
     U = L * 4
-    first_pair = rank * n                      # contiguous block split of the pair ids
+    first_pair, _n = ac.shard_pairs(world * n, world, rank)   # contiguous block split of the pair ids
+    assert _n == n
     ctx = ac.Context([local])
     if args.wave:
         ctx.set_wave_pairs(args.wave)
@@ -312,8 +379,14 @@ def main():
         e2e = {"value": world * ne * reps / float(tt[0]), "unit": UNIT,
                "h2d_bytes_per_step": ne * 3 * L * 4, "d2h_bytes_per_step": ne * ac.RESULT_DTYPE.itemsize,
                "pairs_per_step": ne, "host_dtype": "f32", "host_memory": "pinned",
+               "h2d_gbs_per_gpu": ne * 3 * L * 4 * reps / float(tt[0]) / 1e9, "bound": "pcie (host->device copy of 17.28 MB per pair)",
                "api": "audiosync_cuda_xcorr_batch(memspace=HOST)"}
         del h_src, h_smp
+
+    # ---- config 3: single-pair latency at this length (rank 0 only) --------------------------
+    latency = None
+    if rank == 0 and not args.no_latency:
+        latency = measure_latency(ctx, ac, torch, dev, local, stream, d_src, d_smp, d_res, n, L)
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
@@ -356,15 +429,10 @@ def main():
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "check": {"lag_mismatches": bad, "success_flags": ok_flags, "pairs_checked_per_rank": min(n, 256)},
         }
+        if latency is not None:
+            line["latency"] = latency
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            callers = max(1, cores // 2)
-            npairs = max(2 * callers, 8)
-            dt, kind, backend, _ = cpu_reference_run(L, npairs, callers, SEED)
-            line["cpu_baseline"] = {
-                "value": npairs / dt, "unit": UNIT, "cores": cores, "kind": kind,
-                "sample": "%d pairs of the same workload, %d concurrent callers x 2 FFT threads, %.1f s wall, "
-                          "FFT backend %s (stand-in for FFTW3, not installed)" % (npairs, callers, dt, backend)}
+            line["cpu_baseline"] = cpu_baseline_sample(L, SEED)
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

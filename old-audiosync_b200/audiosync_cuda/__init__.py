@@ -23,7 +23,7 @@ __all__ = [
     "AudiosyncCudaError", "lib", "lib_path", "cross_correlation", "pearson_coefficient",
     "interval_loop", "Context", "RESULT_DTYPE", "MIN_CONFIDENCE", "SAMPLE_RATE",
     "INTERV_SAMPLE", "frames_to_ms", "F32", "F64", "HOST", "DEVICE",
-    "PATH_AUTO", "PATH_FFT", "PATH_DIRECT", "EXPORTED_SYMBOLS",
+    "PATH_AUTO", "PATH_FFT", "PATH_DIRECT", "EXPORTED_SYMBOLS", "shard_pairs", "gather_results",
 ]
 
 F32, F64 = 0, 1
@@ -134,6 +134,67 @@ def frames_to_ms(lag_frames: int) -> int:
     import math
     x = lag_frames * (1000.0 / SAMPLE_RATE)
     return int(math.copysign(math.floor(abs(x) + 0.5), x))   # C round(): half away from zero
+
+
+# ------------------------------------------------------------ multi-GPU sharding
+
+def shard_pairs(n_pairs: int, world: int, rank: int):
+    """Contiguous block split of pair ids over ``world`` devices / ranks.
+
+    Returns ``(first, count)``: ``n_pairs // world`` each, the remainder going to
+    the low ranks -- the same split the in-library dispatcher applies to its
+    devices (``audiosync_cuda_xcorr_batch``, HOST memspace).  Pairs are
+    independent, so there is no data-path collective: every rank works on its
+    own block and only the 40-byte result records are gathered on the host.
+    """
+    if world <= 0 or not 0 <= rank < world or n_pairs < 0:
+        raise ValueError("bad shard request")
+    base, rem = divmod(n_pairs, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def gather_results(local: np.ndarray, n_pairs: int, dst: int = 0, group=None):
+    """Host gather of the per-pair result records (``RESULT_DTYPE``) of every rank.
+
+    ``local`` holds this rank's block, in pair order; rank ``dst`` returns the
+    ``n_pairs`` records in global pair order, the others return ``None``.  Works on
+    any ``torch.distributed`` backend (the records travel as CPU byte tensors
+    through ``gather_object``-free point-to-point ``gather``); with no process
+    group it is the identity.
+    """
+    import torch
+    import torch.distributed as dist
+    local = np.ascontiguousarray(local, dtype=RESULT_DTYPE)
+    if not (dist.is_available() and dist.is_initialized()):
+        if local.shape[0] != n_pairs:
+            raise ValueError("single process must hold every pair")
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    first, count = shard_pairs(n_pairs, world, rank)
+    if local.shape[0] != count:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} records, its shard has {count}")
+    # equal-size payloads: pad every block to the largest shard
+    width = (n_pairs + world - 1) // world * RESULT_DTYPE.itemsize
+    buf = torch.zeros(max(width, 1), dtype=torch.uint8)
+    raw = torch.from_numpy(local.view(np.uint8).reshape(-1).copy())
+    buf[: raw.numel()] = raw
+    backend = dist.get_backend(group)
+    if backend == "nccl":                       # NCCL moves device memory only
+        dev = torch.device("cuda", torch.cuda.current_device())
+        parts = [torch.empty_like(buf, device=dev) for _ in range(world)]
+        dist.all_gather(parts, buf.to(dev), group=group)
+        parts = [p.cpu() for p in parts] if rank == dst else None
+    else:
+        parts = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+        dist.gather(buf, parts, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = np.empty(n_pairs, dtype=RESULT_DTYPE)
+    for r in range(world):
+        f, c = shard_pairs(n_pairs, world, r)
+        out[f:f + c] = parts[r].numpy()[: c * RESULT_DTYPE.itemsize].view(RESULT_DTYPE)
+    return out
 
 
 # ----------------------------------------------------------- drop-in functions
