@@ -281,6 +281,27 @@ def test_host_batch_multi_chunk_and_wave_sizes(ac, capi):
                 assert np.array_equal(base[k], r[k], equal_nan=True)   # deterministic
 
 
+def test_multi_device_dispatcher_matches_single_device(ac, capi):
+    """the in-library dispatcher shards contiguous pair blocks over every visible
+    GPU (one host thread + stream per device, host gather); results must be identical to the
+    single-device run, in pair order.  Needs >= 2 GPUs (the 1-GPU box skips it)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    L, n = 144000, 11                                   # odd count: uneven blocks
+    srcs = np.empty((n, 2 * L), np.float32); smps = np.empty((n, L), np.float32)
+    for i in range(n):
+        srcs[i], smps[i] = capi.synth_pair(SEED + 5, i, L, np.float32)
+    with ac.Context([0]) as c:
+        one = c.xcorr_batch(srcs, smps)
+    with ac.Context(None) as c:
+        assert c.device_count() == torch.cuda.device_count()
+        many = c.xcorr_batch(srcs, smps)
+    for k in one:
+        assert np.array_equal(one[k], many[k], equal_nan=True), k
+    assert [int(x) for x in many["lags"]] == [capi.synth_true_lag(SEED + 5, i, L) for i in range(n)]
+
+
 # ------------------------------------------------------------------ full-size properties
 
 def test_full_size_batch_recovers_injected_lags(ac, ctx, capi):
