@@ -48,7 +48,9 @@ UNIT = "pairs/s"
 #   row_fused reads 4U (both planes), writes 2U (product rows, in place)           = 6 U
 #   col_inv   reads 2U                                                             = 2 U
 #   pearson   reads 2U (the two windows)                                           = 2 U
-KERNEL_U = {"col_fwd": 7, "row_fused": 6, "col_inv_argmax": 2, "pearson": 2}
+#   xcorr_pipeline: one launch = all four stages, each on its own wave of pairs; per pair
+#             of throughput it is the whole path, accounted with SURVEY 8(d)'s 21 U          = 21 U
+KERNEL_U = {"col_fwd": 7, "row_fused": 6, "col_inv_argmax": 2, "pearson": 2, "xcorr_pipeline": 21}
 PATH_U = 21
 
 
@@ -62,6 +64,7 @@ def parse():
     ap.add_argument("--sample-len", type=int, default=L_HEADLINE)
     ap.add_argument("--e2e-pairs", type=int, default=192)
     ap.add_argument("--wave", type=int, default=0, help="pairs per kernel wave (0 = library default)")
+    ap.add_argument("--no-pipeline", action="store_true", help="one launch per stage instead of the wave pipeline kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
@@ -301,6 +304,8 @@ def main():
     ctx = ac.Context([local])
     if args.wave:
         ctx.set_wave_pairs(args.wave)
+    if args.no_pipeline:
+        ctx.set_pipeline(False)
     plan = ctx.describe_plan(L)
 
     d_src = torch.empty(n * 2 * L, dtype=torch.float32, device=dev)

@@ -144,6 +144,13 @@ int audiosync_cuda_synchronize(audiosync_cuda_ctx *ctx, int device);
 int  audiosync_cuda_set_path(audiosync_cuda_ctx *ctx, int path);          /* AUTO / FFT / DIRECT */
 int  audiosync_cuda_set_wave_pairs(audiosync_cuda_ctx *ctx, int pairs);   /* pairs per kernel wave, 0 = auto */
 void audiosync_cuda_set_debug(int on);                                    /* same effect as global_debug */
+/* Optional wave pipeline kernel: batches of more than one wave of the L = 1,440,000 plan run as
+ * one launch per wave (forward columns of wave k, fused rows of wave k-1, inverse columns +
+ * argmax of wave k-2, Pearson of wave k-3 as interleaved CTA roles) instead of one launch per
+ * stage.  Same lag / raw index / peak bit for bit.  Default off: on B200 the stages' bottlenecks
+ * do not complement each other and it measured 2-4 % slower; env AUDIOSYNC_CUDA_PIPELINE=1 or
+ * this call turns it on. */
+int  audiosync_cuda_set_pipeline(audiosync_cuda_ctx *ctx, int on);
 
 /* Describes the plan for a length, e.g.
  * "fft L=1440000 M1=600 M2=2400 col=6x10x10 row=8x10x30 static". Returns the

@@ -47,6 +47,7 @@ EXPORTED_SYMBOLS = [
     "audiosync_cuda_xcorr_batch", "audiosync_cuda_xcorr_batch_device",
     "audiosync_cuda_synth_pairs", "audiosync_cuda_synchronize",
     "audiosync_cuda_set_path", "audiosync_cuda_set_wave_pairs", "audiosync_cuda_set_debug",
+    "audiosync_cuda_set_pipeline",
     "audiosync_cuda_describe_plan", "audiosync_cuda_launch_count",
     "audiosync_cuda_profile_enable", "audiosync_cuda_profile_reset",
     "audiosync_cuda_profile_read", "audiosync_cuda_last_error", "audiosync_cuda_version",
@@ -107,6 +108,8 @@ def lib() -> C.CDLL:
     L.audiosync_cuda_set_path.argtypes = [vp, i32]
     L.audiosync_cuda_set_wave_pairs.restype = i32
     L.audiosync_cuda_set_wave_pairs.argtypes = [vp, i32]
+    L.audiosync_cuda_set_pipeline.restype = i32
+    L.audiosync_cuda_set_pipeline.argtypes = [vp, i32]
     L.audiosync_cuda_set_debug.restype = None
     L.audiosync_cuda_set_debug.argtypes = [i32]
     L.audiosync_cuda_describe_plan.restype = i32
@@ -307,6 +310,10 @@ class Context:
 
     def set_wave_pairs(self, pairs: int):
         self._check(lib().audiosync_cuda_set_wave_pairs(self._h, pairs), "set_wave_pairs")
+
+    def set_pipeline(self, on: bool):
+        """Wave pipeline kernel for multi-wave batches (default off = one launch per stage)."""
+        self._check(lib().audiosync_cuda_set_pipeline(self._h, 1 if on else 0), "set_pipeline")
 
     def describe_plan(self, sample_len: int) -> str:
         buf = C.create_string_buffer(512)

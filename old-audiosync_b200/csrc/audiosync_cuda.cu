@@ -20,6 +20,7 @@
 #include "fft_kernels.cuh"
 #include "fft_plan.h"
 #include "fft_small.cuh"
+#include "pipeline.cuh"
 #include "reduce_kernels.cuh"
 
 // The reference defines `volatile int global_debug` in src/audiosync.c:37 and its
@@ -49,7 +50,7 @@ static bool debug_on() { return g_debug_flag || (&global_debug != nullptr && glo
 const char* kernel_class_name(int k) {
     static const char* names[KC_COUNT] = {
         "synth", "direct_corr", "argmax_f64", "col_fwd", "row_fused",
-        "col_inv_argmax", "small_fft", "pearson"};
+        "col_inv_argmax", "small_fft", "pearson", "xcorr_pipeline"};
     return (k >= 0 && k < KC_COUNT) ? names[k] : "?";
 }
 
@@ -84,15 +85,20 @@ struct FftPlan {
     int M1 = 0, M2 = 0;
     std::string desc;
     size_t ws_bytes_per_pair = 0;
-    DevBuf col_tw, col_tc, row_tw, row_rev, m_lo, m_hi, n_lo, n_hi;   // static four-step
+    DevBuf col_tw, col_tc, row_tw, row_rev, m_lo, m_hi;   // static four-step
     DevBuf wm, wn;                                   // short-length kernel
     SmallPlan small;
+    DevBuf sched;                                    // wave pipeline: role schedule of one pair
+    PipeShape shape{};
+    // whole batches through the wave pipeline kernel (static plans with one block size only)
+    std::function<int(audiosync_cuda_ctx*, DeviceState&, const void*, const void*, int, size_t,
+                      audiosync_cuda_result*, int, cudaStream_t)> run_pipelined;
     // enqueues the transform kernels for `pairs` pairs (planes/r in ws)
     std::function<int(audiosync_cuda_ctx*, DeviceState&, const void*, const void*, int, void*,
                       PairPeak*, int, cudaStream_t)> run_wave;
     ~FftPlan() {
         col_tw.release(); col_tc.release(); row_tw.release(); row_rev.release(); m_lo.release(); m_hi.release();
-        n_lo.release(); n_hi.release(); wm.release(); wn.release();
+        wm.release(); wn.release(); sched.release();
     }
 };
 
@@ -145,8 +151,6 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
     const cplx* row_rev = static_cast<const cplx*>(plan->row_rev.p);
     const cplx* m_lo = static_cast<const cplx*>(plan->m_lo.p);
     const cplx* m_hi = static_cast<const cplx*>(plan->m_hi.p);
-    const cplx* n_lo = static_cast<const cplx*>(plan->n_lo.p);
-    const cplx* n_hi = static_cast<const cplx*>(plan->n_hi.p);
     const dim3 grid_a(M2 / COL_T, 2, pairs);
     auto col_fwd = [&](auto KK, const auto* s_in, const auto* m_in) -> int {
         using K = decltype(KK);
@@ -158,7 +162,8 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
     if (dtype == AUDIOSYNC_CUDA_F32) {
         // cp.async staging needs 16-byte aligned rows: every pair / row offset is a multiple
         // of 16 bytes, so only the base pointers decide.
-        const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(smp)) & 15u) == 0;
+        static const bool no_async = getenv("AUDIOSYNC_CUDA_NOASYNC") != nullptr;   // experiment knob
+        const bool aligned = !no_async && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(smp)) & 15u) == 0;
         const float* s_in = static_cast<const float*>(src);
         const float* m_in = static_cast<const float*>(smp);
         const int rc = aligned ? col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, float, true>{}, s_in, m_in)
@@ -170,7 +175,7 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
     }
     {
         using K = RowFusedKernel<Row, Col::n, P::NT_ROW>;
-        typename K::Params p{planes, row_tw, row_rev, m_lo, m_hi, n_lo, n_hi, P::L};
+        typename K::Params p{planes, row_tw, row_rev, m_lo, m_hi, P::L};
         const dim3 grid(M1 / 2 + 1, 1, pairs);
         if (launch(ctx, d, KC_ROW_FUSED, st, [&] {
                 fft_kernel_entry<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
@@ -184,6 +189,93 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
                 fft_kernel_entry<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
             }) != 0) return -1;
     }
+    return 0;
+}
+
+
+// ---------------------------------------------------------- wave pipeline
+// Launch k runs K_A on wave k, K_B on wave k-1, K_C on wave k-2 and K_P on wave k-3
+// (pipeline.cuh).  Workspace rings: planes x3 (A writes, B in place, C reads), peaks x4
+// (A clears, C atomicMax, P reads).  Stream order between launches carries the dependencies.
+template <class P, typename InT>
+static int run_static_pipelined(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d, const InT* src,
+                                const InT* smp, size_t n_pairs, audiosync_cuda_result* d_results,
+                                int wave, cudaStream_t st) {
+    using Col = typename P::Col;
+    using Row = typename P::Row;
+    constexpr int NT = P::NT_COL;
+    using KA = ColFwdKernel<Col, Row::n, NT, InT, sizeof(InT) == 4>;
+    using KB = RowFusedKernel<Row, Col::n, NT>;
+    using KC = ColInvKernel<Col, Row::n, NT>;
+    constexpr size_t SMEM = std::max(std::max(KA::SMEM, KB::SMEM), std::max(KC::SMEM, sizeof(PearsonShared<NT>)));
+    const long long L = P::L;
+    const PipeShape& shape = plan->shape;
+    const int n_chunks = shape.items[ROLE_P];
+    const size_t plane_elems = (size_t)2 * L * (size_t)wave;          // cplx per ring slot
+    if (d.ws.ensure(3 * plane_elems * sizeof(cplx) + 256) != 0) return -1;
+    if (d.peaks.ensure(sizeof(PairPeak) * 4 * (size_t)wave) != 0) return -1;
+    if (d.partials.ensure(sizeof(PearsonPartial) * (size_t)wave * n_chunks) != 0) return -1;
+    {
+        const size_t need = sizeof(unsigned int) * (size_t)wave;
+        if (need > d.tickets.bytes) {
+            ASC_CUDA_OK(cudaDeviceSynchronize());
+            if (d.tickets.ensure(need) != 0) return -1;
+            ASC_CUDA_OK(cudaMemset(d.tickets.p, 0, d.tickets.bytes));
+        }
+    }
+    cplx* ws = static_cast<cplx*>(d.ws.p);
+    PairPeak* peaks = static_cast<PairPeak*>(d.peaks.p);
+    const cplx* col_tw = static_cast<const cplx*>(plan->col_tw.p);
+    const cplx* row_tw = static_cast<const cplx*>(plan->row_tw.p);
+    const cplx* col_tc = static_cast<const cplx*>(plan->col_tc.p);
+    const cplx* row_rev = static_cast<const cplx*>(plan->row_rev.p);
+    const cplx* m_lo = static_cast<const cplx*>(plan->m_lo.p);
+    const cplx* m_hi = static_cast<const cplx*>(plan->m_hi.p);
+    const long long n_waves = (long long)((n_pairs + (size_t)wave - 1) / (size_t)wave);
+    auto pairs_of = [&](long long w) -> int {
+        if (w < 0 || w >= n_waves) return 0;
+        return (int)std::min<size_t>((size_t)wave, n_pairs - (size_t)w * (size_t)wave);
+    };
+    auto clampw = [&](long long w) -> long long { return std::min(std::max(w, 0LL), n_waves - 1); };
+    for (long long k = 0; k < n_waves + 3; k++) {
+        const long long wa = clampw(k), wb = clampw(k - 1), wc = clampw(k - 2), wp = clampw(k - 3);
+        PipelineParams<KA, KB, KC, InT> q{};
+        q.pairs[ROLE_A] = pairs_of(k);
+        q.pairs[ROLE_B] = pairs_of(k - 1);
+        q.pairs[ROLE_C] = pairs_of(k - 2);
+        q.pairs[ROLE_P] = pairs_of(k - 3);
+        q.a = typename KA::Params{src + (size_t)wa * wave * (size_t)(2 * L), smp + (size_t)wa * wave * (size_t)L,
+                                  ws + (size_t)(wa % 3) * plane_elems, peaks + (size_t)(wa % 4) * wave,
+                                  col_tw, col_tc, m_lo, m_hi, L};
+        q.b = typename KB::Params{ws + (size_t)(wb % 3) * plane_elems, row_tw, row_rev, m_lo, m_hi, L};
+        q.c = typename KC::Params{ws + (size_t)(wc % 3) * plane_elems, peaks + (size_t)(wc % 4) * wave, col_tw, L};
+        q.p = PearsonArgs<InT>{src + (size_t)wp * wave * (size_t)(2 * L), smp + (size_t)wp * wave * (size_t)L, L,
+                               peaks + (size_t)(wp % 4) * wave, static_cast<PearsonPartial*>(d.partials.p),
+                               static_cast<unsigned int*>(d.tickets.p), n_chunks,
+                               d_results + (size_t)wp * wave};
+        q.sched = static_cast<const uint16_t*>(plan->sched.p);
+        q.period = shape.period();
+        const int G = std::max(std::max(q.pairs[0], q.pairs[1]), std::max(q.pairs[2], q.pairs[3]));
+        const unsigned grid = (unsigned)G * (unsigned)q.period;
+        if (launch(ctx, d, KC_PIPELINE, st, [&] {
+                pipeline_entry<KA, KB, KC, InT, NT><<<grid, NT, SMEM, st>>>(q);
+            }) != 0) return -1;
+    }
+    return 0;
+}
+
+template <class P, typename InT>
+static int prepare_pipeline() {
+    using Col = typename P::Col;
+    using Row = typename P::Row;
+    constexpr int NT = P::NT_COL;
+    using KA = ColFwdKernel<Col, Row::n, NT, InT, sizeof(InT) == 4>;
+    using KB = RowFusedKernel<Row, Col::n, NT>;
+    using KC = ColInvKernel<Col, Row::n, NT>;
+    constexpr size_t SMEM = std::max(std::max(KA::SMEM, KB::SMEM), std::max(KC::SMEM, sizeof(PearsonShared<NT>)));
+    if (SMEM > 48 * 1024)
+        ASC_CUDA_OK(cudaFuncSetAttribute(pipeline_entry<KA, KB, KC, InT, NT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     return 0;
 }
 
@@ -203,15 +295,13 @@ static int build_static_plan(FftPlan* plan) {
     for (int i = 0; i < Row::count; i++) d += (i ? "x" : "") + std::to_string(Row::r(i));
     d += " static four-step fp32";
     plan->desc = d;
-    std::vector<cplx> m_lo, m_hi, n_lo, n_hi;
+    std::vector<cplx> m_lo, m_hi;
     build_two_level(P::L, P::L - 1, m_lo, m_hi);
-    build_two_level(2 * P::L, P::L, n_lo, n_hi);
     if (upload(plan->col_tw, build_pass_tables(radix_vector<Col>())) != 0 ||
         upload(plan->row_tw, build_pass_tables(radix_vector<Row>())) != 0 ||
         upload(plan->col_tc, build_col_tc(P::L, Col::weight(Col::count - 1))) != 0 ||
         upload(plan->row_rev, build_row_rev<Row>()) != 0 ||
-        upload(plan->m_lo, m_lo) != 0 || upload(plan->m_hi, m_hi) != 0 ||
-        upload(plan->n_lo, n_lo) != 0 || upload(plan->n_hi, n_hi) != 0)
+        upload(plan->m_lo, m_lo) != 0 || upload(plan->m_hi, m_hi) != 0)
         return -1;
     if (prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, true>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, true>::SMEM) != 0 ||
         prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, false>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, false>::SMEM) != 0 ||
@@ -223,6 +313,22 @@ static int build_static_plan(FftPlan* plan) {
                             int dtype, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
         return run_static_wave<P>(plan, ctx, d, src, smp, dtype, ws, peaks, pairs, st);
     };
+    if constexpr (P::NT_COL == P::NT_ROW && P::PIPELINE) {
+        plan->shape = pipe_shape(Col::n, Row::n, P::L, P::NT_COL);
+        const std::vector<uint16_t> sched = build_pipe_schedule(plan->shape);
+        if (plan->sched.ensure(sched.size() * sizeof(uint16_t)) != 0) return -1;
+        ASC_CUDA_OK(cudaMemcpy(plan->sched.p, sched.data(), sched.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        if (prepare_pipeline<P, float>() != 0 || prepare_pipeline<P, double>() != 0) return -1;
+        plan->run_pipelined = [plan](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
+                                     int dtype, size_t n_pairs, audiosync_cuda_result* d_results, int wave,
+                                     cudaStream_t st) {
+            return dtype == AUDIOSYNC_CUDA_F32
+                       ? run_static_pipelined<P, float>(plan, ctx, d, static_cast<const float*>(src),
+                                                        static_cast<const float*>(smp), n_pairs, d_results, wave, st)
+                       : run_static_pipelined<P, double>(plan, ctx, d, static_cast<const double*>(src),
+                                                         static_cast<const double*>(smp), n_pairs, d_results, wave, st);
+        };
+    }
     return 0;
 }
 
@@ -358,6 +464,12 @@ static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, const void* sr
     int wave = ctx->wave_pairs > 0 ? ctx->wave_pairs : default_wave_pairs(plan, n_pairs);
     wave = (int)std::min<size_t>((size_t)wave, n_pairs);
     wave = std::min(wave, 65535);
+    // More than one wave of a static plan: the wave pipeline kernel (cp.async staging of fp32
+    // tiles needs 16-byte aligned inputs; anything else takes the launch-per-stage path below).
+    if (ctx->pipeline && plan->run_pipelined && n_pairs > (size_t)wave &&
+        (dtype == AUDIOSYNC_CUDA_F64 ||
+         ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(smp)) & 15u) == 0))
+        return plan->run_pipelined(ctx, d, src, smp, dtype, n_pairs, d_results, wave, st);
     const int n_chunks = (int)((L + PEARSON_CHUNK - 1) / PEARSON_CHUNK);
     if (d.ws.ensure(plan->ws_bytes_per_pair * (size_t)wave + 256) != 0) return -1;
     if (d.peaks.ensure(sizeof(PairPeak) * (size_t)wave) != 0) return -1;
@@ -532,6 +644,8 @@ int audiosync_cuda_create(audiosync_cuda_ctx** out, const int* devices, int n_de
     }
     const char* w = getenv("AUDIOSYNC_CUDA_WAVE_PAIRS");
     if (w) ctx->wave_pairs = atoi(w);
+    const char* pl = getenv("AUDIOSYNC_CUDA_PIPELINE");
+    if (pl) ctx->pipeline = atoi(pl) != 0;
     *out = ctx;
     return 0;
 }
@@ -553,6 +667,12 @@ int audiosync_cuda_set_path(audiosync_cuda_ctx* ctx, int path) {
 int audiosync_cuda_set_wave_pairs(audiosync_cuda_ctx* ctx, int pairs) {
     if (!ctx || pairs < 0) return -1;
     ctx->wave_pairs = pairs;
+    return 0;
+}
+
+int audiosync_cuda_set_pipeline(audiosync_cuda_ctx* ctx, int on) {
+    if (!ctx) return -1;
+    ctx->pipeline = on != 0;
     return 0;
 }
 

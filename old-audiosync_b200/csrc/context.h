@@ -40,6 +40,7 @@ enum KernelClass {
     KC_COL_INV,      // K_C  inverse column pass + |r| argmax epilogue
     KC_SMALL_FFT,    // single-CTA transform for short lengths
     KC_PEARSON,      // window statistics + coefficient + result record
+    KC_PIPELINE,     // wave pipeline: K_A, K_B, K_C, K_P of four consecutive waves in one launch
     KC_COUNT
 };
 
@@ -95,6 +96,7 @@ struct audiosync_cuda_ctx {
     int path = AUDIOSYNC_CUDA_PATH_AUTO;
     int wave_pairs = 0;
     bool profile = false;
+    bool pipeline = false;    // wave pipeline kernel for multi-wave batches (measured 2-4 % slower than a launch per stage)
     std::atomic<uint64_t> launches{0};
 
     asc::DeviceState* find(int device);

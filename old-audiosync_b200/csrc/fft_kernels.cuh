@@ -124,13 +124,20 @@ struct ColFwdKernel {
                     PairPeak z; z.key = 0ull; z.raw_index = 0; z.peak = 0.0; z.resolved = 0; z.pad = 0;
                     p.peaks[pair] = z;
                 }
+                // thread -> (row tid/8 + i*NT/8, 16-byte part tid%8): both pointers advance by
+                // compile-time constants, so the unrolled loop is one LDGSTS per chunk
+                static_assert(NT % 8 == 0, "a thread keeps its 16-byte part across rows");
+                constexpr int RSTEP = NT / 8;
                 const int rows_valid = sig == 0 ? M1 : M1 / 2;
-                const char* __restrict__ g = reinterpret_cast<const char*>(x) + (size_t)c0 * sizeof(cplx);
-                char* __restrict__ sm = reinterpret_cast<char*>(buf);
-                for (int q = tid; q < M1 * 8; q += NT) {
-                    const int row = q >> 3, part = q & 7;
-                    if (row < rows_valid) cp_async16(sm + q * 16, g + (size_t)row * M2 * sizeof(cplx) + part * 16);
-                    else smem_zero16(sm + q * 16);
+                const int row0 = tid >> 3;
+                const char* __restrict__ g = reinterpret_cast<const char*>(x) + (size_t)c0 * sizeof(cplx) +
+                                             (size_t)row0 * (M2 * sizeof(cplx)) + (tid & 7) * 16;
+                char* __restrict__ sm = reinterpret_cast<char*>(buf) + tid * 16;
+#pragma unroll
+                for (int i = 0; i < (M1 + RSTEP - 1) / RSTEP; i++) {
+                    const int row = row0 + i * RSTEP;
+                    if (row < rows_valid) cp_async16(sm + i * (NT * 16), g + (size_t)i * (RSTEP * M2 * sizeof(cplx)));
+                    else if (row < M1) smem_zero16(sm + i * (NT * 16));
                 }
                 cp_async_wait_all();
             });
@@ -244,10 +251,15 @@ struct ColInvKernel {
 
         // stage the tile: row n1 = 128 bytes = 8 chunks of 16 bytes
         ex.phase([&](int tid) {
-            const char* __restrict__ g = reinterpret_cast<const char*>(in + c0);
-            char* __restrict__ sm = reinterpret_cast<char*>(buf);
-            for (int q = tid; q < M1 * 8; q += NT)
-                cp_async16(sm + q * 16, g + (size_t)(q >> 3) * M2 * sizeof(cplx) + (q & 7) * 16);
+            static_assert(NT % 8 == 0, "a thread keeps its 16-byte part across rows");
+            constexpr int RSTEP = NT / 8;
+            const int row0 = tid >> 3;
+            const char* __restrict__ g = reinterpret_cast<const char*>(in + c0) +
+                                         (size_t)row0 * (M2 * sizeof(cplx)) + (tid & 7) * 16;
+            char* __restrict__ sm = reinterpret_cast<char*>(buf) + tid * 16;
+#pragma unroll
+            for (int i = 0; i < (M1 + RSTEP - 1) / RSTEP; i++)
+                if (row0 + i * RSTEP < M1) cp_async16(sm + i * (NT * 16), g + (size_t)i * (RSTEP * M2 * sizeof(cplx)));
             cp_async_wait_all();
         });
 
@@ -366,6 +378,55 @@ ASC_HD void split_mul_merge(cplx a, cplx b, cplx c, cplx d, cplx w, cplx& qk, cp
     qmk = cmake(0.25f * (g.x - h.x), -0.25f * (g.y - h.y));
 }
 
+// The same step with the twiddle folded: with s = a + conj b, t = a - conj b (and s', t' from
+// c, d), u = -i w t gives u conj(u') = t conj(t') and
+//   (p1 + p2) / 2 = G = s conj(s') + t conj(t')
+//   i conj(w) (p1 - p2) / 2 = H = t conj(s') - conj(w^2) s conj(t')
+// so only w^2 = exp(-2*pi*i*k/M) is needed.  Returns 2 Q[k] = G + H and 2 Q[M-k] = conj(G - H):
+// the caller folds the factor 1/2 into a later twiddle.  18 packed instructions instead of 34.
+ASC_HD cplx cconj_add(cplx a, cplx b) {   // a + conj(b)
+#if ASC_PACKED
+    return __fadd2_rn(a, cmake(b.x, -b.y));
+#else
+    return cmake(a.x + b.x, a.y - b.y);
+#endif
+}
+ASC_HD cplx cconj_sub(cplx a, cplx b) {   // a - conj(b)
+#if ASC_PACKED
+    return __fadd2_rn(a, cmake(-b.x, b.y));
+#else
+    return cmake(a.x - b.x, a.y + b.y);
+#endif
+}
+// acc + a * conj(b)
+ASC_HD cplx cmulc_acc(cplx a, cplx b, cplx acc) {
+#if ASC_PACKED
+    const cplx t = __ffma2_rn(cmake(a.y, -a.x), cmake(b.y, b.y), acc);
+    return __ffma2_rn(a, cmake(b.x, b.x), t);
+#else
+    return cmake(fmaf(a.x, b.x, fmaf(a.y, b.y, acc.x)), fmaf(a.y, b.x, fmaf(-a.x, b.y, acc.y)));
+#endif
+}
+// acc - a * conj(b)
+ASC_HD cplx cmulc_nacc(cplx a, cplx b, cplx acc) {
+#if ASC_PACKED
+    const cplx t = __ffma2_rn(cmake(-a.y, a.x), cmake(b.y, b.y), acc);
+    return __ffma2_rn(a, cmake(-b.x, -b.x), t);
+#else
+    return cmake(fmaf(-a.x, b.x, fmaf(-a.y, b.y, acc.x)), fmaf(-a.y, b.x, fmaf(a.x, b.y, acc.y)));
+#endif
+}
+ASC_HD void split_mul_merge_w2(cplx a, cplx b, cplx c, cplx d, cplx w2, cplx& qk2, cplx& qmk2) {
+    const cplx s = cconj_add(a, b), t = cconj_sub(a, b);
+    const cplx s2 = cconj_add(c, d), t2 = cconj_sub(c, d);
+    const cplx g = cmulc_acc(t, t2, cmulc(s, s2));
+    const cplx x = cmulc(s, t2);
+    const cplx h = cmulc_nacc(x, w2, cmulc(t, s2));
+    qk2 = cadd(g, h);
+    const cplx e = csub(g, h);
+    qmk2 = cmake(e.x, -e.y);
+}
+
 template <class RL, int M1_, int NT>
 struct RowFusedKernel {
     static constexpr int MIN_CTAS = 3;
@@ -389,11 +450,9 @@ struct RowFusedKernel {
     struct Params {
         cplx* planes;            // [pair][2][M1*M2]
         const cplx* tw;          // RL pass tables (forward sign, power-of-two multiples)
-        const cplx* rev;         // [M2]: exp(-2*pi*i*freq_of_pos(e)/(2*M2)), position order
+        const cplx* rev;         // [M2]: exp(-2*pi*i*freq_of_pos(e)/M2), position order
         const cplx* m_lo;        // W_M tables
         const cplx* m_hi;
-        const cplx* n_lo;        // W_N = W_2M tables
-        const cplx* n_hi;
         long long L;
     };
 
@@ -415,16 +474,18 @@ struct RowFusedKernel {
         // ---- stage the 2*nrows rows.  smem slots: 0,1 source rows; 2,3 sample rows.
         ex.phase([&](int tid) {
             constexpr int cpr = M2 / 2;                       // 16-byte chunks per row
-            const int chunks = cpr * 2 * nrows;
-            for (int q = tid; q < chunks; q += NT) {
-                const int b = q / cpr;
-                const int part = q - b * cpr;
-                const int is_smp = b >= nrows ? 1 : 0;
-                const int rr = b - is_smp * nrows;
-                const cplx* __restrict__ g = (is_smp ? plane_p : plane_s) + (long long)(rr ? k1b : k1a) * M2;
-                cp_async16(reinterpret_cast<char*>(buf + (is_smp * 2 + rr) * RP) + part * 16,
-                           reinterpret_cast<const char*>(g) + part * 16);
-            }
+            static_for<0, 4>([&](auto B) {
+                constexpr int slot = decltype(B)::value;      // 0,1 source rows; 2,3 sample rows
+                constexpr int rr = slot & 1;
+                if (rr == 0 || two) {
+                    const cplx* __restrict__ g = (slot >= 2 ? plane_p : plane_s) + (long long)(rr ? k1b : k1a) * M2;
+                    const char* __restrict__ gs = reinterpret_cast<const char*>(g) + tid * 16;
+                    char* __restrict__ sm = reinterpret_cast<char*>(buf + slot * RP) + tid * 16;
+#pragma unroll
+                    for (int i = 0; i < (cpr + NT - 1) / NT; i++)
+                        if (tid + i * NT < cpr) cp_async16(sm + i * (NT * 16), gs + i * (NT * 16));
+                }
+            });
             cp_async_wait_all();
         });
 
@@ -473,31 +534,44 @@ struct RowFusedKernel {
 
         // ---- split + conj-multiply + merge, in place into the source rows.
         {
-            // items: two rows -> every position e of row a pairs with position
-            // M2-1-e of row b (bin M2-1-k2); row M1/2 alone -> same map inside
-            // one row, e < M2/2; row 0 alone -> bins (k2, M2-k2), e <= M2/2.
-            // exp(-2*pi*i*(k1a + M1*k2)/N) = W_N^k1a * rev[position of k2].
-            const int items = two ? M2 : (r == 0 ? M2 / 2 + 1 : M2 / 2);
-            cplx* __restrict__ zs_a = buf;
-            cplx* __restrict__ zs_b = buf + (two ? RP : 0);
-            cplx* __restrict__ zp_a = buf + 2 * RP;
-            cplx* __restrict__ zp_b = buf + (two ? 3 * RP : 2 * RP);
+            // two rows -> every position e of row a pairs with position M2-1-e of row b
+            // (bin M2-1-k2); row M1/2 alone -> same map inside one row, e < M2/2; row 0
+            // alone -> bins (k2, M2-k2), e <= M2/2.
+            // w^2 = exp(-2*pi*i*(k1a + M1*k2)/M) = W_M^k1a * rev[position of k2].
             ex.phase([&](int tid) {
-                const cplx wk1 = tw2(p.n_lo, p.n_hi, (unsigned)k1a);
-                for (int e = tid; e < items; e += NT) {
-                    int pa, pb;
-                    if (r == 0) {
-                        pa = RL::pos_of_freq(e);
-                        pb = RL::pos_of_freq(e == 0 ? 0 : M2 - e);
-                    } else {
-                        pa = e;
-                        pb = M2 - 1 - e;
+                const cplx wk1 = tw2(p.m_lo, p.m_hi, (unsigned)k1a);
+                if (two) {
+                    cplx* __restrict__ zs_a = buf;
+                    cplx* __restrict__ zs_b = buf + RP;
+                    cplx* __restrict__ zp_a = buf + 2 * RP;
+                    cplx* __restrict__ zp_b = buf + 3 * RP;
+                    for (int e = tid; e < M2; e += NT) {
+                        const int pb = M2 - 1 - e;
+                        const cplx w2 = cmul(ldg(p.rev + e), wk1);
+                        cplx qk, qmk;
+                        split_mul_merge_w2(zs_a[e], zs_b[pb], zp_a[e], zp_b[pb], w2, qk, qmk);
+                        zs_a[e] = qk;
+                        zs_b[pb] = qmk;
                     }
-                    const cplx w = cmul(ldg(p.rev + pa), wk1);
-                    cplx qk, qmk;
-                    split_mul_merge(zs_a[pa], zs_b[pb], zp_a[pa], zp_b[pb], w, qk, qmk);
-                    zs_a[pa] = qk;
-                    if (pa != pb || two) zs_b[pb] = qmk;
+                } else {
+                    cplx* __restrict__ zs = buf;
+                    cplx* __restrict__ zp = buf + 2 * RP;
+                    const int items = r == 0 ? M2 / 2 + 1 : M2 / 2;
+                    for (int e = tid; e < items; e += NT) {
+                        int pa, pb;
+                        if (r == 0) {
+                            pa = RL::pos_of_freq(e);
+                            pb = RL::pos_of_freq(e == 0 ? 0 : M2 - e);
+                        } else {
+                            pa = e;
+                            pb = M2 - 1 - e;
+                        }
+                        const cplx w2 = cmul(ldg(p.rev + pa), wk1);
+                        cplx qk, qmk;
+                        split_mul_merge_w2(zs[pa], zs[pb], zp[pa], zp[pb], w2, qk, qmk);
+                        zs[pa] = qk;
+                        if (pa != pb) zs[pb] = qmk;
+                    }
                 }
             });
         }
@@ -519,7 +593,8 @@ struct RowFusedKernel {
                         const int rr = e / (S0 + R0);
                         const int i = e - rr * (S0 + R0);
                         const unsigned k1 = (unsigned)(rr ? k1b : k1a);
-                        if (i < S0) tab_ab[rr * S0 + i] = tw2(p.m_lo, p.m_hi, (unsigned)i * k1);
+                        // the factor 1/2 of the merge step rides on this table (exact)
+                        if (i < S0) tab_ab[rr * S0 + i] = cscale(tw2(p.m_lo, p.m_hi, (unsigned)i * k1), 0.5f);
                         else tab_g[rr * R0 + (i - S0)] = tw2(p.m_lo, p.m_hi, (unsigned)((i - S0) * S0) * k1);
                     }
                 }
@@ -580,27 +655,12 @@ struct RowFusedKernel {
 // kernel bodies (shared with the CPU emulator) instantiate cleanly; the host
 // side of them is never called.
 struct DeviceExec {
-    ASC_HD int bx() const {
-#if defined(__CUDA_ARCH__)
-        return blockIdx.x;
-#else
-        return 0;
-#endif
-    }
-    ASC_HD int by() const {
-#if defined(__CUDA_ARCH__)
-        return blockIdx.y;
-#else
-        return 0;
-#endif
-    }
-    ASC_HD int bz() const {
-#if defined(__CUDA_ARCH__)
-        return blockIdx.z;
-#else
-        return 0;
-#endif
-    }
+    // Block coordinates the kernel body sees.  The plain entry copies blockIdx; the wave
+    // pipeline kernel (pipeline.cuh) assigns them from its role schedule.
+    int x_ = 0, y_ = 0, z_ = 0;
+    ASC_HD int bx() const { return x_; }
+    ASC_HD int by() const { return y_; }
+    ASC_HD int bz() const { return z_; }
     template <class F>
     ASC_HD void phase(F&& f) {
 #if defined(__CUDA_ARCH__)
@@ -682,6 +742,7 @@ template <class K>
 __global__ void __launch_bounds__(K::THREADS, min_ctas_of<K>::value) fft_kernel_entry(const typename K::Params p) {
     extern __shared__ __align__(16) unsigned char asc_smem[];
     DeviceExec ex;
+    ex.x_ = (int)blockIdx.x; ex.y_ = (int)blockIdx.y; ex.z_ = (int)blockIdx.z;
     K::run(ex, p, reinterpret_cast<cplx*>(asc_smem));
 }
 #endif

@@ -26,30 +26,35 @@ struct Plan144k {
     using Col = RadixList<10, 6, 5>;     // M1 = 300
     using Row = RadixList<4, 8, 15>;     // M2 = 480
     static constexpr int NT_COL = 160, NT_ROW = 128;
+    static constexpr bool PIPELINE = false;
 };
 struct Plan288k {
     static constexpr long long L = 288000;
     using Col = RadixList<10, 6, 5>;     // M1 = 300
     using Row = RadixList<4, 16, 15>;    // M2 = 960
     static constexpr int NT_COL = 160, NT_ROW = 256;
+    static constexpr bool PIPELINE = false;
 };
 struct Plan480k {
     static constexpr long long L = 480000;
     using Col = RadixList<10, 10, 4>;    // M1 = 400
     using Row = RadixList<5, 16, 15>;    // M2 = 1200
     static constexpr int NT_COL = 320, NT_ROW = 320;
+    static constexpr bool PIPELINE = false;
 };
 struct Plan720k {
     static constexpr long long L = 720000;
     using Col = RadixList<10, 10, 6>;    // M1 = 600
     using Row = RadixList<5, 16, 15>;    // M2 = 1200
     static constexpr int NT_COL = 320, NT_ROW = 320;
+    static constexpr bool PIPELINE = false;
 };
 struct Plan960k {
     static constexpr long long L = 960000;
     using Col = RadixList<10, 10, 4>;    // M1 = 400
     using Row = RadixList<10, 16, 15>;   // M2 = 2400
     static constexpr int NT_COL = 320, NT_ROW = 320;
+    static constexpr bool PIPELINE = false;
 };
 #ifndef ASC_NT_COL_1440K
 #define ASC_NT_COL_1440K 320
@@ -62,6 +67,7 @@ struct Plan1440k {
     using Col = RadixList<10, 10, 6>;    // M1 = 600
     using Row = RadixList<10, 16, 15>;   // M2 = 2400
     static constexpr int NT_COL = ASC_NT_COL_1440K, NT_ROW = ASC_NT_ROW_1440K;
+    static constexpr bool PIPELINE = true;
 };
 
 using StaticPlans = std::tuple<Plan144k, Plan288k, Plan480k, Plan720k, Plan960k, Plan1440k>;
@@ -146,11 +152,12 @@ inline std::vector<cplx> build_col_tc(long long M, int wt) {
     return t;
 }
 
-// K_B split/merge table in POSITION order: rev[e] = exp(-2*pi*i*freq_of_pos(e)/(2*M2)).
+// K_B split/merge table in POSITION order: rev[e] = exp(-2*pi*i*freq_of_pos(e)/M2)
+// (the M1*k2 part of w^2 = exp(-2*pi*i*(k1 + M1*k2)/M), see split_mul_merge_w2).
 template <class RL>
 inline std::vector<cplx> build_row_rev() {
     std::vector<cplx> t(RL::n);
-    for (int e = 0; e < RL::n; e++) t[e] = unit_root(RL::freq_of_pos(e), 2LL * RL::n);
+    for (int e = 0; e < RL::n; e++) t[e] = unit_root(RL::freq_of_pos(e), (long long)RL::n);
     return t;
 }
 

@@ -145,10 +145,20 @@ argmax_f64_kernel(const double* __restrict__ r, long long N, PairPeak* __restric
 //   grid = (n_chunks, n_pairs), block = 256; chunk c covers window elements
 //   [c * PEARSON_CHUNK, (c + 1) * PEARSON_CHUNK).
 // ---------------------------------------------------------------------------
-constexpr int PEARSON_CHUNK = 16384;
 constexpr int PEARSON_THREADS = 256;
+constexpr int PEARSON_PER_THREAD = 64;                       // window elements per thread and chunk
+constexpr int PEARSON_CHUNK = PEARSON_THREADS * PEARSON_PER_THREAD;   // 16384 (stand-alone kernel)
 
 struct PearsonPartial { double sx, sy, sxx, syy, sxy; };
+
+// Shared scratch of one Pearson CTA (static in the stand-alone kernel, carved
+// from the dynamic buffer in the wave pipeline kernel).
+template <int NTP>
+struct PearsonShared {
+    double piv[2];
+    double red[NTP / 32][5];
+    int last;
+};
 
 // Finishes one pair from the summed statistics (thread 0 of the finishing CTA).
 __device__ __forceinline__ void pearson_finish(const PearsonPartial& s, const Window& w, long long raw,
@@ -170,21 +180,19 @@ __device__ __forceinline__ void pearson_finish(const PearsonPartial& s, const Wi
     *out = r;
 }
 
-// grid = (n_chunks, n_pairs).  The last CTA of a pair to finish (ticket counter,
-// self-resetting) sums the chunk partials in a fixed order and writes the result
-// record, so the whole Pearson step is one launch.
-template <typename T>
-__global__ void __launch_bounds__(PEARSON_THREADS)
-pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
-               long long src_pitch, long long smp_pitch, long long L,
-               const PairPeak* __restrict__ peaks, long long explicit_n,
-               PearsonPartial* __restrict__ partials, unsigned int* __restrict__ tickets,
-               int n_chunks, audiosync_cuda_result* __restrict__ results)
+// One CTA of NTP threads: chunk `chunk` (NTP * 64 window elements) of pair `pair`.  The last
+// CTA of a pair to finish (ticket counter, self-resetting) sums the chunk partials in a fixed
+// order and writes the result record, so the whole Pearson step needs no second launch.
+// Every thread of the CTA must call it (barriers inside).
+template <typename T, int NTP>
+__device__ __forceinline__ void pearson_block(
+    const T* __restrict__ sources, const T* __restrict__ samples,
+    long long src_pitch, long long smp_pitch, long long L,
+    const PairPeak* __restrict__ peaks, long long explicit_n,
+    PearsonPartial* __restrict__ partials, unsigned int* __restrict__ tickets,
+    int n_chunks, audiosync_cuda_result* __restrict__ results,
+    int pair, int chunk, int t, PearsonShared<NTP>& sh)
 {
-    __shared__ double s_piv[2];
-    __shared__ double s_red[PEARSON_THREADS / 32][5];
-    __shared__ int s_last;
-    const int pair = blockIdx.y, chunk = blockIdx.x, t = threadIdx.x;
     Window w;
     long long raw = 0;
     double peak = 0.0;
@@ -200,7 +208,7 @@ pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
     const T* __restrict__ y = samples + (size_t)pair * (size_t)smp_pitch + w.yoff;
 
     PearsonPartial acc = {0.0, 0.0, 0.0, 0.0, 0.0};
-    const long long lo = (long long)chunk * PEARSON_CHUNK;
+    const long long lo = (long long)chunk * (NTP * PEARSON_PER_THREAD);
     if (lo < w.n) {
         if (t < 32) {
             long long k = ((long long)t * w.n) >> 5;
@@ -209,11 +217,11 @@ pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
                 px += __shfl_xor_sync(0xffffffffu, px, o);
                 py += __shfl_xor_sync(0xffffffffu, py, o);
             }
-            if (t == 0) { s_piv[0] = px * (1.0 / 32.0); s_piv[1] = py * (1.0 / 32.0); }
+            if (t == 0) { sh.piv[0] = px * (1.0 / 32.0); sh.piv[1] = py * (1.0 / 32.0); }
         }
         __syncthreads();
-        const double px = s_piv[0], py = s_piv[1];
-        long long hi = lo + PEARSON_CHUNK;
+        const double px = sh.piv[0], py = sh.piv[1];
+        long long hi = lo + (NTP * PEARSON_PER_THREAD);
         if (hi > w.n) hi = w.n;
         if constexpr (sizeof(T) == 4) {
             // fp32 inputs: shifted values and products in fp32, 16 elements per thread and
@@ -225,7 +233,7 @@ pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
             const bool xv = (reinterpret_cast<uintptr_t>(x + lo) & 15u) == 0;
             const bool yv = (reinterpret_cast<uintptr_t>(y + lo) & 15u) == 0;
             constexpr int VPT = 4;                                   // float4 groups per thread and iteration
-            constexpr long long STEP = 4LL * PEARSON_THREADS;        // elements per group row
+            constexpr long long STEP = 4LL * NTP;        // elements per group row
             auto load4 = [](const float* __restrict__ p, bool vec) -> float4 {
                 if (vec) return __ldg(reinterpret_cast<const float4*>(p));
                 return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
@@ -260,10 +268,10 @@ pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
         } else {
             constexpr int UN = 8;
             long long i = lo + t;
-            for (; i + (UN - 1) * PEARSON_THREADS < hi; i += UN * PEARSON_THREADS) {
+            for (; i + (UN - 1) * NTP < hi; i += UN * NTP) {
                 T xv[UN], yv[UN];
 #pragma unroll
-                for (int u = 0; u < UN; u++) { xv[u] = x[i + u * PEARSON_THREADS]; yv[u] = y[i + u * PEARSON_THREADS]; }
+                for (int u = 0; u < UN; u++) { xv[u] = x[i + u * NTP]; yv[u] = y[i + u * NTP]; }
 #pragma unroll
                 for (int u = 0; u < UN; u++) {
                     const double dx = (double)xv[u] - px, dy = (double)yv[u] - py;
@@ -271,7 +279,7 @@ pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
                     acc.sxx = fma(dx, dx, acc.sxx); acc.syy = fma(dy, dy, acc.syy); acc.sxy = fma(dx, dy, acc.sxy);
                 }
             }
-            for (; i < hi; i += PEARSON_THREADS) {
+            for (; i < hi; i += NTP) {
                 const double dx = (double)x[i] - px, dy = (double)y[i] - py;
                 acc.sx += dx; acc.sy += dy;
                 acc.sxx = fma(dx, dx, acc.sxx); acc.syy = fma(dy, dy, acc.syy); acc.sxy = fma(dx, dy, acc.sxy);
@@ -287,23 +295,23 @@ pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
     }
     const int wid = t >> 5, lane = t & 31;
     if (lane == 0) {
-        s_red[wid][0] = acc.sx; s_red[wid][1] = acc.sy; s_red[wid][2] = acc.sxx;
-        s_red[wid][3] = acc.syy; s_red[wid][4] = acc.sxy;
+        sh.red[wid][0] = acc.sx; sh.red[wid][1] = acc.sy; sh.red[wid][2] = acc.sxx;
+        sh.red[wid][3] = acc.syy; sh.red[wid][4] = acc.sxy;
     }
     __syncthreads();
     if (t == 0) {
         PearsonPartial o = {0.0, 0.0, 0.0, 0.0, 0.0};
-        for (int k = 0; k < PEARSON_THREADS / 32; k++) {
-            o.sx += s_red[k][0]; o.sy += s_red[k][1]; o.sxx += s_red[k][2];
-            o.syy += s_red[k][3]; o.sxy += s_red[k][4];
+        for (int k = 0; k < NTP / 32; k++) {
+            o.sx += sh.red[k][0]; o.sy += sh.red[k][1]; o.sxx += sh.red[k][2];
+            o.syy += sh.red[k][3]; o.sxy += sh.red[k][4];
         }
         partials[(size_t)pair * n_chunks + chunk] = o;
         __threadfence();
         const unsigned int ticket = atomicAdd(&tickets[pair], 1u);
-        s_last = (ticket == (unsigned int)(n_chunks - 1)) ? 1 : 0;
+        sh.last = (ticket == (unsigned int)(n_chunks - 1)) ? 1 : 0;
     }
     __syncthreads();
-    if (s_last && t < 32) {
+    if (sh.last && t < 32) {
         __threadfence();
         // lane l sums chunks l, l+32, ... in ascending order; then a fixed xor tree
         PearsonPartial s = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -325,6 +333,21 @@ pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
             tickets[pair] = 0u;       // ready for the next wave
         }
     }
+}
+
+// grid = (n_chunks, n_pairs), block = 256.
+template <typename T>
+__global__ void __launch_bounds__(PEARSON_THREADS)
+pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
+               long long src_pitch, long long smp_pitch, long long L,
+               const PairPeak* __restrict__ peaks, long long explicit_n,
+               PearsonPartial* __restrict__ partials, unsigned int* __restrict__ tickets,
+               int n_chunks, audiosync_cuda_result* __restrict__ results)
+{
+    __shared__ PearsonShared<PEARSON_THREADS> sh;
+    pearson_block<T, PEARSON_THREADS>(sources, samples, src_pitch, smp_pitch, L, peaks, explicit_n, partials,
+                                      tickets, n_chunks, results, (int)blockIdx.y, (int)blockIdx.x,
+                                      (int)threadIdx.x, sh);
 }
 
 }  // namespace asc

@@ -318,6 +318,57 @@ def test_full_size_batch_recovers_injected_lags(ac, ctx, capi):
         assert (0.994 < c < 0.996) if pid % 4 != 3 else (0.79 < c < 0.81)
 
 
+@pytest.mark.parametrize("dtype_name", ["f32", "f64"])
+def test_wave_pipeline_matches_stage_per_launch(ac, capi, dtype_name):
+    """Multi-wave batches of the L = 1,440,000 plan run through the wave pipeline kernel (one
+    launch = K_A of wave k, K_B of wave k-1, K_C of wave k-2, K_P of wave k-3).  The transform
+    and argmax are the same code: raw index, lag and peak must be bit-identical to the
+    launch-per-stage path; the coefficient differs only by the Pearson chunking (fp32 partial
+    sums regrouped: 1e-6 relative allowed, 1e-4 is the path's tolerance).
+    Ragged last wave (11 pairs, waves of 3) and golden values are covered too."""
+    import torch
+    L, n = 1440000, 11
+    dtype = ac.F32 if dtype_name == "f32" else ac.F64
+    out = {}
+    for pipe in (False, True):
+        with ac.Context([0]) as c:
+            c.set_wave_pairs(3)
+            c.set_pipeline(pipe)
+            l0 = c.launch_count()
+            res, _, _ = _batch_on_device(ac, c, SEED, 0, n, L, dtype)
+            out[pipe] = (res.copy(), c.launch_count() - l0)
+    a, b = out[False][0], out[True][0]
+    for k in ("raw_index", "lag", "peak", "ret", "success"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.allclose(a["coef"], b["coef"], rtol=1e-6, atol=0)
+    # launches: synth + 4 per wave  vs  synth + (waves + 3)
+    assert out[False][1] == 1 + 4 * 4 and out[True][1] == 1 + 4 + 3
+    gold = {c["pair_id"]: c for c in _pairs() if c["L"] == L}
+    for pid in range(n):
+        assert int(b["lag"][pid]) == capi.synth_true_lag(SEED, pid, L)
+        if pid in gold:
+            g = gold[pid]
+            assert int(b["raw_index"][pid]) == g["raw_index"] and int(b["ret"][pid]) == g["ret"]
+            assert close(float(b["coef"][pid]), g["coef"]) and close(float(b["peak"][pid]), g["peak"])
+
+
+def test_wave_pipeline_repeated_calls_are_deterministic(ac):
+    """Ring buffers, ticket counters and peak slots are reused across calls: three back-to-back
+    pipelined batches (different pair ids, ragged sizes) each equal a fresh context's answer."""
+    L = 1440000
+    with ac.Context([0]) as c:
+        c.set_wave_pairs(2)
+        runs = [(_batch_on_device(ac, c, SEED + 9, first, n, L)[0].copy(), first, n)
+                for first, n in ((0, 7), (3, 5), (1, 9))]
+    for res, first, n in runs:
+        with ac.Context([0]) as c:
+            c.set_pipeline(False)
+            ref = _batch_on_device(ac, c, SEED + 9, first, n, L)[0]
+        for k in ("raw_index", "lag", "peak", "ret", "success"):
+            assert np.array_equal(res[k], ref[k]), (k, first, n)
+        assert np.allclose(res["coef"], ref["coef"], rtol=1e-6, atol=0)
+
+
 def test_scaling_and_negation_properties(ac, ctx, capi):
     """r is bilinear: scaling the sample by a power of two scales the peak exactly and leaves
     lag and coefficient unchanged; negating it flips the peak sign and the coefficient."""
