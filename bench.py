@@ -266,6 +266,26 @@ def measure_latency(ctx, ac, torch, dev, local, stream, d_src, d_smp, d_res, n, 
     wall.sort()
     out["c_abi_host_f64_ms"] = {"p50": wall[len(wall) // 2], "p95": wall[int(len(wall) * 0.95)], "calls": len(wall),
                                 "h2d_bytes_per_call": 3 * L * 8, "ret": rc, "lag": lag.value}
+    # (iii) the reference's interval schedule (src/audiosync.c:226-259): six calls on growing
+    # prefixes of the same two buffers, with and without interval-schedule residency
+    if L == L_HEADLINE:
+        sched = {}
+        for resident in (False, True):
+            lib.audiosync_cuda_set_residency(1 if resident else 0)
+            tot = []
+            b0 = ac.dropin_stats()[1]
+            for rep in range(2 + 10):
+                t0 = time.perf_counter()
+                for Li in ac.INTERV_SAMPLE:
+                    lib.cross_correlation(ps, pm, Li, C.byref(lag), C.byref(coef))
+                if rep >= 2:
+                    tot.append((time.perf_counter() - t0) * 1e3)
+            tot.sort()
+            sched["resident" if resident else "full_upload"] = {
+                "p50_ms_six_calls": tot[len(tot) // 2],
+                "h2d_bytes_six_calls": (ac.dropin_stats()[1] - b0) // 12}
+        lib.audiosync_cuda_set_residency(1)
+        out["c_abi_interval_schedule"] = sched
     lib.fftw_free(ps); lib.fftw_free(pm)
     return out
 

@@ -72,6 +72,21 @@ double *fftw_alloc_real(size_t n);
 void   *fftw_alloc_complex(size_t n);        /* n * 2 doubles */
 void    fftw_free(void *p);
 
+/* Interval-schedule residency.  The reference's loop
+ * (src/audiosync.c:226-259) calls cross_correlation() with the same two buffers and a
+ * growing sample_len while its reader threads only append.  When `source` comes from the
+ * allocators above, the library keeps the fp64 prefixes it has already uploaded on the device
+ * and a call transfers only the frames that arrived since the previous one.  A session is
+ * reused only if both pointers are unchanged, sample_len grew strictly, nothing was freed
+ * through fftw_free in between, and 64 probe values of each cached prefix still match the
+ * host buffers; otherwise everything is uploaded again.  Callers that rewrite a prefix in
+ * place between growing calls must switch it off: audiosync_cuda_set_residency(0) or env
+ * AUDIOSYNC_CUDA_RESIDENT=0.  Results do not depend on the setting. */
+void audiosync_cuda_set_residency(int on);
+/* Counters of the drop-in cross_correlation() since load: calls, host->device bytes, and
+ * calls that reused a resident session.  Any pointer may be NULL. */
+void audiosync_cuda_dropin_stats(uint64_t *calls, uint64_t *h2d_bytes, uint64_t *resident_hits);
+
 /* ------------------------------------------------------------------------
  * Part 3 -- batched / multi-GPU surface (new; not in the reference)
  * ------------------------------------------------------------------------ */

@@ -24,6 +24,7 @@ __all__ = [
     "interval_loop", "Context", "RESULT_DTYPE", "MIN_CONFIDENCE", "SAMPLE_RATE",
     "INTERV_SAMPLE", "frames_to_ms", "F32", "F64", "HOST", "DEVICE",
     "PATH_AUTO", "PATH_FFT", "PATH_DIRECT", "EXPORTED_SYMBOLS", "shard_pairs", "gather_results",
+    "cross_correlation_ptr", "RealBuffer", "set_residency", "dropin_stats",
 ]
 
 F32, F64 = 0, 1
@@ -47,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "audiosync_cuda_xcorr_batch", "audiosync_cuda_xcorr_batch_device",
     "audiosync_cuda_synth_pairs", "audiosync_cuda_synchronize",
     "audiosync_cuda_set_path", "audiosync_cuda_set_wave_pairs", "audiosync_cuda_set_debug",
-    "audiosync_cuda_set_pipeline",
+    "audiosync_cuda_set_pipeline", "audiosync_cuda_set_residency", "audiosync_cuda_dropin_stats",
     "audiosync_cuda_describe_plan", "audiosync_cuda_launch_count",
     "audiosync_cuda_profile_enable", "audiosync_cuda_profile_reset",
     "audiosync_cuda_profile_read", "audiosync_cuda_last_error", "audiosync_cuda_version",
@@ -108,6 +109,10 @@ def lib() -> C.CDLL:
     L.audiosync_cuda_set_path.argtypes = [vp, i32]
     L.audiosync_cuda_set_wave_pairs.restype = i32
     L.audiosync_cuda_set_wave_pairs.argtypes = [vp, i32]
+    L.audiosync_cuda_set_residency.restype = None
+    L.audiosync_cuda_set_residency.argtypes = [i32]
+    L.audiosync_cuda_dropin_stats.restype = None
+    L.audiosync_cuda_dropin_stats.argtypes = [C.POINTER(C.c_uint64)] * 3
     L.audiosync_cuda_set_pipeline.restype = i32
     L.audiosync_cuda_set_pipeline.argtypes = [vp, i32]
     L.audiosync_cuda_set_debug.restype = None
@@ -223,6 +228,53 @@ def cross_correlation(source: np.ndarray, sample: np.ndarray):
     return ret, lag.value, coef.value
 
 
+def cross_correlation_ptr(source_ptr: int, sample_ptr: int, sample_len: int):
+    """The same call on raw host addresses (no NumPy copy): what reference src/audiosync.c:246
+    does with its ``fftw_alloc_real`` source and ``malloc`` sample buffers."""
+    lag = C.c_long(-(2 ** 62))
+    coef = C.c_double(12345.0)
+    ret = lib().cross_correlation(source_ptr, sample_ptr, sample_len, C.byref(lag), C.byref(coef))
+    if ret != 0 and lag.value == -(2 ** 62):
+        raise AudiosyncCudaError("cross_correlation failed: " + last_error())
+    return ret, lag.value, coef.value
+
+
+class RealBuffer:
+    """``fftw_alloc_real(n)`` / ``fftw_free`` of this library (pinned host doubles) as a NumPy view.
+    A source held in one makes the drop-in call eligible for interval-schedule residency."""
+
+    def __init__(self, n: int):
+        self.n = int(n)
+        self.ptr = lib().fftw_alloc_real(self.n)
+        if not self.ptr:
+            raise AudiosyncCudaError("fftw_alloc_real failed")
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_double)), shape=(self.n,))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().fftw_free(self.ptr)
+            self.ptr = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.free()
+
+
+def set_residency(on: bool) -> None:
+    """Interval-schedule residency of the drop-in ``cross_correlation`` (default on)."""
+    lib().audiosync_cuda_set_residency(1 if on else 0)
+
+
+def dropin_stats():
+    """(calls, host->device bytes, resident-session hits) of the drop-in call since load."""
+    a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    lib().audiosync_cuda_dropin_stats(C.byref(a), C.byref(b), C.byref(c))
+    return int(a.value), int(b.value), int(c.value)
+
+
 def pearson_coefficient(x: np.ndarray, y: np.ndarray) -> float:
     """``double pearson_coefficient(start, end, start, end)`` on two equal-length windows."""
     x = np.ascontiguousarray(x, dtype=np.float64)
@@ -234,8 +286,11 @@ def pearson_coefficient(x: np.ndarray, y: np.ndarray) -> float:
                                            y.ctypes.data, y.ctypes.data + 8 * n))
 
 
-def interval_loop(source: np.ndarray, sample: np.ndarray):
+def interval_loop(source: np.ndarray, sample: np.ndarray, call=None):
     """The caller loop of reference src/audiosync.c:226-259 on complete buffers.
+
+    ``call(L) -> (ret, lag, coef)`` replaces the NumPy drop-in wrapper when given (e.g.
+    ``cross_correlation_ptr`` on a ``RealBuffer``, the way the reference holds its source).
 
     Calls the drop-in ``cross_correlation`` on the six interval prefixes, skips
     failed intervals (:247-249), stops at the first ``coef >= 0.95`` (:254-258)
@@ -246,7 +301,10 @@ def interval_loop(source: np.ndarray, sample: np.ndarray):
     rets, lags, coefs, succ = [], [], [], []
     final_ret, lag = -1, 0
     for L in INTERV_SAMPLE:
-        ret, lag_i, coef = cross_correlation(source[:2 * L], sample[:L])
+        if call is not None:
+            ret, lag_i, coef = call(L)
+        else:
+            ret, lag_i, coef = cross_correlation(source[:2 * L], sample[:L])
         lag = lag_i
         ok = ret == 0 and coef >= MIN_CONFIDENCE
         rets.append(ret); lags.append(lag_i); coefs.append(coef); succ.append(int(ok))

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <map>
 #include <thread>
 
 #include "context.h"
@@ -590,6 +591,53 @@ asc::DeviceState* audiosync_cuda_ctx::find(int device) {
     return nullptr;
 }
 
+// ------------------------------------------------- allocator registry / residency
+// Blocks handed out by the FFTW-named allocators below.  cross_correlation() keeps its
+// inputs device-resident across the interval schedule only when the source buffer is one of
+// them (the reference allocates it with fftw_alloc_real, src/audiosync.c:189); any fftw_free
+// bumps the generation and drops the session.
+static std::mutex g_alloc_mu;
+static std::map<const char*, size_t> g_allocs;          // user pointer -> bytes
+static std::atomic<uint64_t> g_alloc_gen{1};
+static std::atomic<int> g_residency{-1};                // -1: read AUDIOSYNC_CUDA_RESIDENT on first use
+static std::atomic<uint64_t> g_dropin_calls{0}, g_dropin_h2d_bytes{0}, g_dropin_resident_hits{0};
+
+static bool residency_enabled() {
+    int v = g_residency.load();
+    if (v < 0) {
+        const char* e = getenv("AUDIOSYNC_CUDA_RESIDENT");
+        v = (e && atoi(e) == 0) ? 0 : 1;
+        g_residency.store(v);
+    }
+    return v != 0;
+}
+
+// bytes of the library allocation that contains [p, p + need), 0 if none
+static size_t library_block_bytes(const void* p, size_t need) {
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    const char* c = static_cast<const char*>(p);
+    auto it = g_allocs.upper_bound(c);
+    if (it == g_allocs.begin()) return 0;
+    --it;
+    if (c < it->first || c + need > it->first + it->second) return 0;
+    return (size_t)(it->first + it->second - c);
+}
+
+static void fingerprint(const double* buf, size_t n, size_t* idx, double* val) {
+    for (int k = 0; k < ResidentSession::NFP; k++) {
+        // evenly spread, odd offsets so a periodic refill cannot dodge every probe
+        const size_t i = n == 0 ? 0 : ((size_t)k * n + (size_t)(37 * k + 11) % (n / ResidentSession::NFP + 1)) /
+                                           ResidentSession::NFP;
+        idx[k] = i < n ? i : (n ? n - 1 : 0);
+        val[k] = n ? buf[idx[k]] : 0.0;
+    }
+}
+static bool fingerprint_matches(const double* buf, const size_t* idx, const double* val) {
+    for (int k = 0; k < ResidentSession::NFP; k++)
+        if (memcmp(&buf[idx[k]], &val[k], sizeof(double)) != 0) return false;
+    return true;
+}
+
 // ===========================================================================
 // C ABI (the only symbols with default visibility)
 // ===========================================================================
@@ -599,6 +647,12 @@ extern "C" {
 const char* audiosync_cuda_last_error(void) { return g_last_error; }
 const char* audiosync_cuda_version(void) { return "audiosync_cuda 0.1 (sm_100a)"; }
 void audiosync_cuda_set_debug(int on) { g_debug_flag = on; }
+void audiosync_cuda_set_residency(int on) { g_residency.store(on ? 1 : 0); }
+void audiosync_cuda_dropin_stats(uint64_t* calls, uint64_t* h2d_bytes, uint64_t* resident_hits) {
+    if (calls) *calls = g_dropin_calls.load();
+    if (h2d_bytes) *h2d_bytes = g_dropin_h2d_bytes.load();
+    if (resident_hits) *resident_hits = g_dropin_resident_hits.load();
+}
 
 int audiosync_cuda_create(audiosync_cuda_ctx** out, const int* devices, int n_devices) {
     if (!out) return -1;
@@ -866,16 +920,58 @@ int cross_correlation(double* source, double* input_sample, const size_t sample_
     DeviceState& d = ctx->devs[0];
     const long long L = (long long)sample_len;
     ASC_CUDA_OK(cudaSetDevice(d.device));
-    if (d.in_src[0].ensure(sizeof(double) * 2 * L) != 0 || d.in_smp[0].ensure(sizeof(double) * L) != 0 ||
-        d.results.ensure(sizeof(audiosync_cuda_result)) != 0 ||
+    if (d.results.ensure(sizeof(audiosync_cuda_result)) != 0 ||
         d.h_results.ensure(sizeof(audiosync_cuda_result)) != 0)
         return -1;
-    // snapshot exactly the prefixes the reference reads (src/cross_correlation.c:164, :204-213)
-    ASC_CUDA_OK(cudaMemcpyAsync(d.in_src[0].p, source, sizeof(double) * 2 * L, cudaMemcpyHostToDevice, d.stream));
-    ASC_CUDA_OK(cudaMemcpyAsync(d.in_smp[0].p, input_sample, sizeof(double) * L, cudaMemcpyHostToDevice, d.stream));
     auto* d_res = static_cast<audiosync_cuda_result*>(d.results.p);
-    if (enqueue_batch(ctx, d, d.in_src[0].p, d.in_smp[0].p, 1, L, AUDIOSYNC_CUDA_F64, d_res, d.stream) != 0)
+    g_dropin_calls.fetch_add(1, std::memory_order_relaxed);
+    const size_t src_n = (size_t)(2 * L), smp_n = (size_t)L;
+    // Residency: the interval loop of src/audiosync.c:226-259 passes the same
+    // buffers with a growing sample_len; only the frames that arrived since the last call are
+    // uploaded.  Taken only for a source from this library's allocator, a strictly larger
+    // sample_len, an unchanged allocator generation and matching fingerprints of both prefixes.
+    const size_t block = residency_enabled() ? library_block_bytes(source, src_n * sizeof(double)) : 0;
+    const void *d_src_in, *d_smp_in;
+    if (block != 0) {
+        ResidentSession& s = ctx->resident;
+        bool hit = s.src == source && s.smp == input_sample && (size_t)L > s.L && s.L != 0 &&
+                   s.alloc_gen == g_alloc_gen.load() && s.src_valid <= src_n && s.smp_valid <= smp_n &&
+                   fingerprint_matches(source, s.fp_idx_src, s.fp_val_src) &&
+                   fingerprint_matches(input_sample, s.fp_idx_smp, s.fp_val_smp);
+        // device mirrors sized for the whole host block, so they never move while a session lives
+        const size_t cap_src = std::max(block, src_n * sizeof(double));
+        const size_t cap_smp = std::max(block / 2, smp_n * sizeof(double));
+        if (cap_src > s.d_src.bytes || cap_smp > s.d_smp.bytes) hit = false;
+        if (!hit) {
+            s.invalidate();
+            if (s.d_src.ensure(cap_src) != 0 || s.d_smp.ensure(cap_smp) != 0) return -1;
+        } else {
+            g_dropin_resident_hits.fetch_add(1, std::memory_order_relaxed);
+        }
+        const size_t new_src = src_n - s.src_valid, new_smp = smp_n - s.smp_valid;
+        ASC_CUDA_OK(cudaMemcpyAsync(static_cast<double*>(s.d_src.p) + s.src_valid, source + s.src_valid,
+                                    sizeof(double) * new_src, cudaMemcpyHostToDevice, d.stream));
+        ASC_CUDA_OK(cudaMemcpyAsync(static_cast<double*>(s.d_smp.p) + s.smp_valid, input_sample + s.smp_valid,
+                                    sizeof(double) * new_smp, cudaMemcpyHostToDevice, d.stream));
+        g_dropin_h2d_bytes.fetch_add(sizeof(double) * (new_src + new_smp), std::memory_order_relaxed);
+        s.src = source; s.smp = input_sample; s.L = (size_t)L; s.src_valid = src_n; s.smp_valid = smp_n;
+        s.alloc_gen = g_alloc_gen.load();
+        fingerprint(source, src_n, s.fp_idx_src, s.fp_val_src);
+        fingerprint(input_sample, smp_n, s.fp_idx_smp, s.fp_val_smp);
+        d_src_in = s.d_src.p; d_smp_in = s.d_smp.p;
+    } else {
+        if (d.in_src[0].ensure(sizeof(double) * src_n) != 0 || d.in_smp[0].ensure(sizeof(double) * smp_n) != 0)
+            return -1;
+        // snapshot exactly the prefixes the reference reads (src/cross_correlation.c:164, :204-213)
+        ASC_CUDA_OK(cudaMemcpyAsync(d.in_src[0].p, source, sizeof(double) * src_n, cudaMemcpyHostToDevice, d.stream));
+        ASC_CUDA_OK(cudaMemcpyAsync(d.in_smp[0].p, input_sample, sizeof(double) * smp_n, cudaMemcpyHostToDevice, d.stream));
+        g_dropin_h2d_bytes.fetch_add(sizeof(double) * (src_n + smp_n), std::memory_order_relaxed);
+        d_src_in = d.in_src[0].p; d_smp_in = d.in_smp[0].p;
+    }
+    if (enqueue_batch(ctx, d, d_src_in, d_smp_in, 1, L, AUDIOSYNC_CUDA_F64, d_res, d.stream) != 0) {
+        ctx->resident.invalidate();
         return -1;
+    }
     ASC_CUDA_OK(cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result), cudaMemcpyDeviceToHost, d.stream));
     ASC_CUDA_OK(cudaStreamSynchronize(d.stream));
     const audiosync_cuda_result r = *static_cast<audiosync_cuda_result*>(d.h_results.p);
@@ -952,6 +1048,10 @@ void* fftw_malloc(size_t n_bytes) {
     }
     AllocHeader* h = reinterpret_cast<AllocHeader*>(static_cast<char*>(base) + 64 - sizeof(AllocHeader));
     h->magic = ALLOC_MAGIC; h->pinned = pinned; h->base = base; h->pad = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_alloc_mu);
+        g_allocs[static_cast<char*>(base) + 64] = n_bytes;
+    }
     return static_cast<char*>(base) + 64;
 }
 
@@ -966,6 +1066,11 @@ void fftw_free(void* p) {
         return;
     }
     h->magic = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_alloc_mu);
+        g_allocs.erase(static_cast<char*>(p));
+        g_alloc_gen.fetch_add(1);          // any resident session built on this block is stale
+    }
     if (h->pinned) cudaFreeHost(h->base); else free(h->base);
 }
 

@@ -88,6 +88,23 @@ struct DeviceState {
     double prof_ms[KC_COUNT] = {0};
 };
 
+// Interval-schedule residency of the drop-in cross_correlation():
+// reference src/audiosync.c:226-259 calls it with the SAME two buffers and a growing
+// sample_len (144,000 -> ... -> 1,440,000) while its reader threads only append.  The device
+// keeps the fp64 prefixes it already has; a call uploads just the newly arrived frames.
+struct ResidentSession {
+    static constexpr int NFP = 64;           // fingerprint samples per buffer
+    const double* src = nullptr;             // host buffers the session mirrors
+    const double* smp = nullptr;
+    size_t L = 0;                            // sample_len of the last call
+    size_t src_valid = 0, smp_valid = 0;     // doubles already on the device
+    uint64_t alloc_gen = 0;                  // allocator generation at the last call
+    size_t fp_idx_src[NFP], fp_idx_smp[NFP];
+    double fp_val_src[NFP], fp_val_smp[NFP];
+    DevBuf d_src, d_smp;
+    void invalidate() { src = smp = nullptr; L = src_valid = smp_valid = 0; }
+};
+
 }  // namespace asc
 
 struct audiosync_cuda_ctx {
@@ -98,6 +115,7 @@ struct audiosync_cuda_ctx {
     bool profile = false;
     bool pipeline = false;    // wave pipeline kernel for multi-wave batches (measured 2-4 % slower than a launch per stage)
     std::atomic<uint64_t> launches{0};
+    asc::ResidentSession resident;           // drop-in cross_correlation() only (default context)
 
     asc::DeviceState* find(int device);
 };

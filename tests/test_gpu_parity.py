@@ -244,6 +244,78 @@ def test_interval_schedule_vs_golden(ac, capi, pid):
             assert lag == c["lag"]
 
 
+# ------------------------------------------------------------------ interval-schedule residency
+
+def _schedule_case(capi, pid):
+    cases = sorted((c for c in SYNTH["cases"] if c["tag"] == "interval-prefix" and c["pair_id"] == pid),
+                   key=lambda c: c["L"])
+    src, smp = capi.synth_pair(cases[0]["seed"], pid, 1440000)
+    assert [c["L"] for c in cases] == [3 * 48000, 6 * 48000, 10 * 48000, 15 * 48000, 20 * 48000, 30 * 48000]
+    return src, smp, cases
+
+
+@pytest.mark.parametrize("pid", [0, 6])
+def test_residency_uploads_only_new_frames_and_matches(ac, capi, pid):
+    """with the source in an fftw_alloc_real buffer (reference
+    src/audiosync.c:189) the six growing calls of the interval loop (:226-259) upload every
+    frame exactly once -- 3 * 1,440,000 doubles in total instead of 3 * sum(L) -- and return
+    exactly what the non-resident calls return."""
+    src, smp, cases = _schedule_case(capi, pid)
+    Ls = ac.INTERV_SAMPLE
+    with ac.RealBuffer(2 * Ls[-1]) as sb, ac.RealBuffer(Ls[-1]) as mb:
+        sb.array[:] = src; mb.array[:] = smp
+        out = {}
+        for resident in (False, True):
+            ac.set_residency(resident)
+            c0, b0, h0 = ac.dropin_stats()
+            res = [ac.cross_correlation_ptr(sb.ptr, mb.ptr, L) for L in Ls]
+            c1, b1, h1 = ac.dropin_stats()
+            out[resident] = (res, c1 - c0, b1 - b0, h1 - h0)
+        ac.set_residency(True)
+    assert out[False][0] == out[True][0]                       # identical (ret, lag, coef), bit for bit
+    assert out[False][1:] == (6, 8 * 3 * sum(Ls), 0)
+    assert out[True][1:] == (6, 8 * 3 * Ls[-1], 5)            # first call opens the session, five reuse it
+    for (ret, lag, coef), c in zip(out[True][0], cases):
+        assert ret == c["ret"] and (ret == 0 and coef >= 0.95) == c["success"]
+        if c["margin"] > 1e-4:
+            assert lag == c["lag"] and close(coef, c["coef"])
+
+
+def test_residency_guards(ac, capi):
+    """A session is reused only for the same buffers, a strictly larger sample_len, an unchanged
+    allocator generation and matching prefix fingerprints; everything else re-uploads."""
+    L1, L2 = 144000, 288000
+    src, smp = capi.synth_pair(SEED, 1, L2)
+    src_b, smp_b = capi.synth_pair(SEED, 2, L2)
+    ac.set_residency(True)
+    with ac.RealBuffer(2 * L2) as sb, ac.RealBuffer(L2) as mb:
+        def hits():
+            return ac.dropin_stats()[2]
+        sb.array[:] = src; mb.array[:] = smp
+        ref1 = ac.cross_correlation(src[:2 * L1], smp[:L1]); ref2 = ac.cross_correlation(src, smp)
+        h = hits()
+        assert ac.cross_correlation_ptr(sb.ptr, mb.ptr, L1) == ref1 and hits() == h
+        assert ac.cross_correlation_ptr(sb.ptr, mb.ptr, L2) == ref2 and hits() == h + 1
+        # same length again / shorter length: no reuse (a new run of the loop starts over)
+        assert ac.cross_correlation_ptr(sb.ptr, mb.ptr, L2) == ref2 and hits() == h + 1
+        assert ac.cross_correlation_ptr(sb.ptr, mb.ptr, L1) == ref1 and hits() == h + 1
+        # the buffers are refilled with another recording between two growing calls
+        sb.array[:] = src_b; mb.array[:] = smp_b
+        assert ac.cross_correlation_ptr(sb.ptr, mb.ptr, L2) == ac.cross_correlation(src_b, smp_b)
+        assert hits() == h + 1
+        # a free anywhere in between bumps the allocator generation
+        assert ac.cross_correlation_ptr(sb.ptr, mb.ptr, L1) == ac.cross_correlation(src_b[:2 * L1], smp_b[:L1])
+        ac.RealBuffer(16).free()
+        assert ac.cross_correlation_ptr(sb.ptr, mb.ptr, L2) == ac.cross_correlation(src_b, smp_b)
+        assert hits() == h + 1
+    # a source that is not a library allocation is never cached
+    h = ac.dropin_stats()[2]
+    a = np.ascontiguousarray(src); b = np.ascontiguousarray(smp)
+    ac.cross_correlation_ptr(a.ctypes.data, b.ctypes.data, L1)
+    ac.cross_correlation_ptr(a.ctypes.data, b.ctypes.data, L2)
+    assert ac.dropin_stats()[2] == h
+
+
 # ------------------------------------------------------------------ host batch API
 
 @pytest.mark.parametrize("npdt", [np.float32, np.float64])
