@@ -103,7 +103,7 @@ enum {
     AUDIOSYNC_CUDA_PATH_DIRECT = 2   /* any length: O(L^2) time-domain correlation, fp64   */
 };
 
-/* One record per pair, 40 bytes, identical on host and device. */
+/* One record per pair, 48 bytes, identical on host and device. */
 typedef struct audiosync_cuda_result {
     int64_t lag;        /* folded lag in frames, [-L, L-1]  (cross_correlation.c:256-271)  */
     double  coef;       /* Pearson coefficient or NaN                                      */
@@ -111,6 +111,9 @@ typedef struct audiosync_cuda_result {
     int32_t ret;        /* 0 / -1 exactly as cross_correlation() would return              */
     int32_t success;    /* ret == 0 && coef >= 0.95   (src/audiosync.c:254)                */
     int64_t raw_index;  /* argmax index before folding, [0, 2L)                            */
+    double  second;     /* second peak: largest |r[i]|, i != raw_index (0 if none); the    */
+                        /* peak is unique when (|peak| - second) / |peak| is well above    */
+                        /* the arithmetic's 1e-6 -- a by-product of the argmax reduction   */
 } audiosync_cuda_result;
 
 /* devices == NULL or n_devices <= 0: use every visible device.
@@ -134,6 +137,14 @@ int audiosync_cuda_xcorr_batch(audiosync_cuda_ctx *ctx,
                                size_t n_pairs, size_t sample_len,
                                int dtype, int memspace,
                                long *lags, double *coefs, int *rets, double *peaks);
+
+/* Same call, whole result records (incl. raw_index and the second peak) instead of
+ * separate arrays.  results: host array of n_pairs audiosync_cuda_result. */
+int audiosync_cuda_xcorr_batch_results(audiosync_cuda_ctx *ctx,
+                                       const void *sources, const void *samples,
+                                       size_t n_pairs, size_t sample_len,
+                                       int dtype, int memspace,
+                                       audiosync_cuda_result *results);
 
 /* Stream-ordered device call: enqueues every kernel for n_pairs device-resident
  * pairs on `stream` (a cudaStream_t passed as void*, NULL = the context's own

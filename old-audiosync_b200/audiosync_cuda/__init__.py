@@ -35,17 +35,17 @@ MIN_CONFIDENCE = 0.95                                             # audiosync.h:
 SAMPLE_RATE = 48000                                               # audiosync.h:14
 INTERV_SAMPLE = [s * SAMPLE_RATE for s in (3, 6, 10, 15, 20, 30)]  # src/audiosync.c:50-57
 
-# mirrors struct audiosync_cuda_result (40 bytes)
+# mirrors struct audiosync_cuda_result (48 bytes)
 RESULT_DTYPE = np.dtype([("lag", "<i8"), ("coef", "<f8"), ("peak", "<f8"),
-                         ("ret", "<i4"), ("success", "<i4"), ("raw_index", "<i8")])
-assert RESULT_DTYPE.itemsize == 40
+                         ("ret", "<i4"), ("success", "<i4"), ("raw_index", "<i8"), ("second", "<f8")])
+assert RESULT_DTYPE.itemsize == 48
 
 # every symbol include/audiosync_cuda.h declares
 EXPORTED_SYMBOLS = [
     "cross_correlation", "pearson_coefficient",
     "fftw_malloc", "fftw_alloc_real", "fftw_alloc_complex", "fftw_free",
     "audiosync_cuda_create", "audiosync_cuda_destroy", "audiosync_cuda_device_count",
-    "audiosync_cuda_xcorr_batch", "audiosync_cuda_xcorr_batch_device",
+    "audiosync_cuda_xcorr_batch", "audiosync_cuda_xcorr_batch_results", "audiosync_cuda_xcorr_batch_device",
     "audiosync_cuda_synth_pairs", "audiosync_cuda_synchronize",
     "audiosync_cuda_set_path", "audiosync_cuda_set_wave_pairs", "audiosync_cuda_set_debug",
     "audiosync_cuda_set_pipeline", "audiosync_cuda_set_residency", "audiosync_cuda_dropin_stats",
@@ -99,6 +99,8 @@ def lib() -> C.CDLL:
     L.audiosync_cuda_device_count.argtypes = [vp]
     L.audiosync_cuda_xcorr_batch.restype = i32
     L.audiosync_cuda_xcorr_batch.argtypes = [vp, vp, vp, sz, sz, i32, i32, vp, vp, vp, vp]
+    L.audiosync_cuda_xcorr_batch_results.restype = i32
+    L.audiosync_cuda_xcorr_batch_results.argtypes = [vp, vp, vp, sz, sz, i32, i32, vp]
     L.audiosync_cuda_xcorr_batch_device.restype = i32
     L.audiosync_cuda_xcorr_batch_device.argtypes = [vp, i32, vp, vp, sz, sz, i32, vp, vp]
     L.audiosync_cuda_synth_pairs.restype = i32
@@ -419,6 +421,56 @@ class Context:
                                               rets.ctypes.data, peaks.ctypes.data)
         self._check(rc, "xcorr_batch")
         return dict(lags=lags, coefs=coefs, rets=rets, peaks=peaks)
+
+    def xcorr_batch_records(self, sources_ptr: int, samples_ptr: int, n_pairs: int, sample_len: int,
+                            dtype: int, memspace: int) -> np.ndarray:
+        """Whole result records (``RESULT_DTYPE``: lag, coef, peak, ret, success, raw_index, second)."""
+        res = np.zeros(n_pairs, RESULT_DTYPE)
+        rc = lib().audiosync_cuda_xcorr_batch_results(self._h, sources_ptr, samples_ptr, n_pairs, sample_len,
+                                                      dtype, memspace, res.ctypes.data)
+        self._check(rc, "xcorr_batch_results")
+        return res
+
+    def xcorr_batch_torch(self, sources, samples, out=None, sync: bool = True):
+        """Zero-copy batch call on torch CUDA tensors.
+
+        ``sources`` [n, 2L] and ``samples`` [n, L]: contiguous float32 or float64 tensors on one
+        device of this context.  The kernels are enqueued on torch's CURRENT stream of that
+        device, reading the tensors in place; the 48-byte records land in ``out`` (a uint8
+        CUDA tensor of n * 48 bytes, allocated when omitted).  With ``sync`` the records come
+        back as a NumPy structured array (``RESULT_DTYPE``); otherwise the device tensor is
+        returned and the caller orders later work on the same stream.
+        """
+        import torch
+        if not (sources.is_cuda and samples.is_cuda) or sources.device != samples.device:
+            raise ValueError("sources and samples must be CUDA tensors on the same device")
+        if sources.dtype != samples.dtype or sources.dtype not in (torch.float32, torch.float64):
+            raise TypeError("sources/samples must both be float32 or float64")
+        if sources.dim() != 2 or samples.dim() != 2 or sources.shape[0] != samples.shape[0] \
+                or sources.shape[1] != 2 * samples.shape[1]:
+            raise ValueError("expected sources [n, 2L] and samples [n, L]")
+        if not (sources.is_contiguous() and samples.is_contiguous()):
+            raise ValueError("tensors must be contiguous (no hidden copies on this path)")
+        n, L = samples.shape
+        dev = sources.device
+        if out is None:
+            out = torch.empty(n * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        elif out.device != dev or out.dtype != torch.uint8 or out.numel() < n * RESULT_DTYPE.itemsize:
+            raise ValueError("out must be a uint8 tensor of n * 48 bytes on the same device")
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        if stream == 0:
+            # a NULL handle would select the library's own stream: order it after torch's default
+            # stream by draining that one first, and synchronise the device afterwards
+            torch.cuda.current_stream(dev).synchronize()
+        dt = F32 if sources.dtype == torch.float32 else F64
+        if n:
+            self.xcorr_batch_device(dev.index, sources.data_ptr(), samples.data_ptr(), n, L, dt,
+                                    out.data_ptr(), stream)
+        if stream == 0:
+            self.synchronize(dev.index)
+        if not sync:
+            return out
+        return out[: n * RESULT_DTYPE.itemsize].cpu().numpy().view(RESULT_DTYPE)
 
     # -- stream-ordered device calls --------------------------------------------
     def xcorr_batch_device(self, device: int, d_sources: int, d_samples: int, n_pairs: int,

@@ -831,16 +831,15 @@ int audiosync_cuda_xcorr_batch_device(audiosync_cuda_ctx* ctx, int device, const
     return enqueue_batch(ctx, *d, d_sources, d_samples, n_pairs, (long long)sample_len, dtype, d_results, st);
 }
 
-int audiosync_cuda_xcorr_batch(audiosync_cuda_ctx* ctx, const void* sources, const void* samples,
-                               size_t n_pairs, size_t sample_len, int dtype, int memspace, long* lags,
-                               double* coefs, int* rets, double* peaks) {
-    if (!ctx || !sources || !samples) { set_last_error("null argument"); return -1; }
+int audiosync_cuda_xcorr_batch_results(audiosync_cuda_ctx* ctx, const void* sources, const void* samples,
+                                       size_t n_pairs, size_t sample_len, int dtype, int memspace,
+                                       audiosync_cuda_result* results) {
+    if (!ctx || !sources || !samples || (!results && n_pairs)) { set_last_error("null argument"); return -1; }
     if (dtype != AUDIOSYNC_CUDA_F32 && dtype != AUDIOSYNC_CUDA_F64) { set_last_error("bad dtype"); return -1; }
     if (n_pairs == 0) return 0;
     if (sample_len == 0) { set_last_error("sample_len must be > 0"); return -1; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     const long long L = (long long)sample_len;
-    std::vector<audiosync_cuda_result> res(n_pairs);
     int rc = 0;
     if (memspace == AUDIOSYNC_CUDA_DEVICE) {
         cudaPointerAttributes at;
@@ -854,7 +853,7 @@ int audiosync_cuda_xcorr_batch(audiosync_cuda_ctx* ctx, const void* sources, con
         if (d->results.ensure(sizeof(audiosync_cuda_result) * n_pairs) != 0) return -1;
         auto* d_res = static_cast<audiosync_cuda_result*>(d->results.p);
         if (enqueue_batch(ctx, *d, sources, samples, n_pairs, L, dtype, d_res, d->stream) != 0) return -1;
-        ASC_CUDA_OK(cudaMemcpyAsync(res.data(), d_res, sizeof(audiosync_cuda_result) * n_pairs,
+        ASC_CUDA_OK(cudaMemcpyAsync(results, d_res, sizeof(audiosync_cuda_result) * n_pairs,
                                     cudaMemcpyDeviceToHost, d->stream));
         ASC_CUDA_OK(cudaStreamSynchronize(d->stream));
     } else {
@@ -871,7 +870,7 @@ int audiosync_cuda_xcorr_batch(audiosync_cuda_ctx* ctx, const void* sources, con
             if (cnt == 0) continue;
             auto work = [&, g, a, b] {
                 rcs[g] = run_host_range(ctx, ctx->devs[g], static_cast<const char*>(sources),
-                                        static_cast<const char*>(samples), a, b, L, dtype, res.data());
+                                        static_cast<const char*>(samples), a, b, L, dtype, results);
             };
             if (G == 1) work(); else th.emplace_back(work);
         }
@@ -879,6 +878,16 @@ int audiosync_cuda_xcorr_batch(audiosync_cuda_ctx* ctx, const void* sources, con
         for (int r : rcs) rc |= r;
         if (rc != 0) return -1;
     }
+    return 0;
+}
+
+int audiosync_cuda_xcorr_batch(audiosync_cuda_ctx* ctx, const void* sources, const void* samples,
+                               size_t n_pairs, size_t sample_len, int dtype, int memspace, long* lags,
+                               double* coefs, int* rets, double* peaks) {
+    std::vector<audiosync_cuda_result> res(n_pairs);
+    if (audiosync_cuda_xcorr_batch_results(ctx, sources, samples, n_pairs, sample_len, dtype, memspace,
+                                           res.data()) != 0)
+        return -1;
     for (size_t i = 0; i < n_pairs; i++) {
         if (lags) lags[i] = (long)res[i].lag;
         if (coefs) coefs[i] = res[i].coef;

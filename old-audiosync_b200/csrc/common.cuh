@@ -74,9 +74,21 @@ struct PairPeak {
     unsigned long long key;   // packed argmax key (fp32 path) -- atomicMax target
     long long raw_index;      // resolved index (direct path writes it directly)
     double peak;              // r[raw_index]
-    int resolved;             // 1 if raw_index/peak are already final
-    int pad;
+    double second;            // resolved second peak (direct path)
+    int resolved;             // 1 if raw_index/peak/second are already final
+    unsigned int second_bits; // fp32 path: order bits of the largest |r[i]|, i != argmax (0: none yet)
 };
+
+__host__ __device__ __forceinline__ PairPeak cleared_peak() {
+    PairPeak z;
+    z.key = 0ull; z.raw_index = 0; z.peak = 0.0; z.second = 0.0; z.resolved = 0; z.second_bits = 0u;
+    return z;
+}
+
+// |value| carried by a packed key (abs keys hold |v|, the seed key holds the signed r[0]).
+__host__ __device__ __forceinline__ float argmax_key_mag(uint64_t key) {
+    return fabsf(float_from_order_bits((uint32_t)(key >> 32)));
+}
 
 // Fold of src/cross_correlation.c:256-271.  Window = x[xoff .. xoff+n) of the
 // source against y[yoff .. yoff+n) of the sample.

@@ -58,21 +58,35 @@ ASC_HD cplx load_packed<double>(const double* __restrict__ x, long long n) {
 }
 
 // Running |r| argmax of one thread (reference src/cross_correlation.c:52-67 as
-// a max over packed keys, see common.cuh).  The packed key is only built for
-// the rare candidates that can still win; a NaN never passes `a >= mag`.
+// a max over packed keys, see common.cuh) plus the SECOND peak: the largest
+// |r[i]| over every entry other than the winner (the oracle's
+// `second`, which makes "the peak is unique" observable).  The packed key is only
+// built for candidates that can still change either; a NaN never passes `a >= thr`.
+struct ArgmaxPair {
+    unsigned long long best;
+    float second;
+};
+
 struct ArgmaxAcc {
     unsigned long long best = 0ull;
-    float mag = -1.0f;               // magnitude a candidate must reach to matter
-    ASC_HD void update(unsigned long long key) {
+    float second = 0.0f;             // largest |v| seen by this thread except `best`
+    float thr = 0.0f;                // lower bound of the pair's final second peak: smaller magnitudes are skipped
+    ASC_HD void update(unsigned long long key, float a) {
         if (key > best) {
+            if (best != 0ull) second = fmaxf(second, argmax_key_mag(best));   // NaN seed: fmaxf drops it
             best = key;
-            mag = float_from_order_bits((uint32_t)(key >> 32));   // NaN seed -> NaN: nothing passes
+        } else {
+            second = fmaxf(second, a);
         }
+        thr = fmaxf(thr, second);    // this thread's own second peak bounds the pair's from below
     }
     ASC_HD void consider(float v, uint32_t index) {   // index >= 1
-        if (fabsf(v) >= mag) update(argmax_key_abs(v, index));
+        const float a = fabsf(v);
+        if (a >= thr) update(argmax_key_abs(v, index), a);
     }
-    ASC_HD void consider_seed(float v) { update(argmax_key_seed(v)); }   // index 0, signed
+    ASC_HD void consider_seed(float v) { update(argmax_key_seed(v), fabsf(v)); }   // index 0, signed
+    ASC_HD float best_mag() const { return best != 0ull ? argmax_key_mag(best) : 0.0f; }
+    ASC_HD ArgmaxPair result() const { ArgmaxPair r; r.best = best; r.second = second; return r; }
 };
 
 // --------------------------------------------------------------------- K_A
@@ -120,10 +134,7 @@ struct ColFwdKernel {
         if constexpr (ASYNC) {
             // tile row n1 = 16 packed points = 128 bytes = 8 chunks; shared tile has the same pitch
             ex.phase([&](int tid) {
-                if (clears_peak && tid == 0) {
-                    PairPeak z; z.key = 0ull; z.raw_index = 0; z.peak = 0.0; z.resolved = 0; z.pad = 0;
-                    p.peaks[pair] = z;
-                }
+                if (clears_peak && tid == 0) p.peaks[pair] = cleared_peak();
                 // thread -> (row tid/8 + i*NT/8, 16-byte part tid%8): both pointers advance by
                 // compile-time constants, so the unrolled loop is one LDGSTS per chunk
                 static_assert(NT % 8 == 0, "a thread keeps its 16-byte part across rows");
@@ -151,10 +162,7 @@ struct ColFwdKernel {
             constexpr bool from_global = first && !ASYNC;
             constexpr int items = (M1 / R) * COL_T;
             ex.phase([&](int tid) {
-                if (from_global && clears_peak && tid == 0) {
-                    PairPeak z; z.key = 0ull; z.raw_index = 0; z.peak = 0.0; z.resolved = 0; z.pad = 0;
-                    p.peaks[pair] = z;
-                }
+                if (from_global && clears_peak && tid == 0) p.peaks[pair] = cleared_peak();
                 const int c = tid & (COL_T - 1);          // fixed column of this thread
                 if constexpr (!last) {
                     for (int w = tid; w < items; w += NT) {
@@ -295,22 +303,22 @@ struct ColInvKernel {
         // last pass + argmax epilogue: packed point n = n1*M2 + n2 carries
         // r[2n] (real part) and r[2n+1] (imaginary part).
         //
-        // Only values that reach the best magnitude seen so far can matter, so a
-        // butterfly's 2R outputs are first reduced with fmax and compared with a
-        // threshold; the exact key logic runs only when the test passes.  The
-        // threshold starts from the pair's running maximum in global memory
-        // (earlier CTAs of this launch) and is shared across the warp after
-        // every hit, so the slow path is taken O(log) times per warp.
+        // Only values that reach the running SECOND peak can matter (they may become the
+        // peak or the second peak), so a butterfly's 2R outputs are first reduced with fmax
+        // and compared with a threshold; the exact key logic runs only when the test passes.
+        // The threshold starts from the pair's running second peak in global memory (earlier
+        // CTAs of this launch) and is raised to the warp's own bound after every hit, so the
+        // slow path is taken O(log) times per warp.
         {
             constexpr int ps = P - 1;
             constexpr int R = RL::r(ps);
             constexpr int Wt = RL::weight(ps);
             constexpr int items = (M1 / R) * COL_T;
             ex.phase_argmax(
-                [&](int tid) -> unsigned long long {
+                [&](int tid) -> ArgmaxPair {
                     ArgmaxAcc acc;
-                    const unsigned long long seen = ex.peek_key(&p.peaks[pair].key);
-                    if (seen != 0ull) acc.mag = float_from_order_bits((uint32_t)(seen >> 32));
+                    const unsigned int seen = ex.peek_bits(&p.peaks[pair].second_bits);
+                    if (seen != 0u) acc.thr = float_from_order_bits(seen);
                     const int c = tid & (COL_T - 1);
                     const bool col0 = (c0 + c) == 0;
                     for (int w0 = 0; w0 < items; w0 += NT) {      // warp-uniform trip count
@@ -330,7 +338,7 @@ struct ColInvKernel {
                             gm = fmaxf(gm, fmaxf(fabsf(v[k].x), fabsf(v[k].y)));
                         });
                         const bool has_seed = col0 && i0 == 0;      // r[0]: signed seed, exact path always
-                        const bool need = act && (gm >= acc.mag || has_seed);
+                        const bool need = act && (gm >= acc.thr || has_seed);
                         if (ex.any(need)) {
                             if (need) {
                                 const int f0 = RL::freq_of_pos(i0);
@@ -343,12 +351,12 @@ struct ColInvKernel {
                                     acc.consider(v[k].y, i_re + 1u);
                                 });
                             }
-                            acc.mag = ex.warp_max(acc.mag);
+                            acc.thr = fmaxf(acc.thr, ex.warp_second(acc.best_mag(), acc.second));
                         }
                     }
-                    return acc.best;
+                    return acc.result();
                 },
-                &p.peaks[pair].key, buf);
+                &p.peaks[pair].key, &p.peaks[pair].second_bits, buf);
         }
     }
 };
@@ -684,14 +692,23 @@ struct DeviceExec {
         return b;
 #endif
     }
-    ASC_HD float warp_max(float m) const {
+    // Second largest of the warp's (best magnitude, second) pairs: the largest value among
+    // every lane's `second` and every lane's best magnitude except ONE lane holding the
+    // warp maximum -- a lower bound of the pair's final second peak.  Inputs are >= 0.
+    ASC_HD float warp_second(float best_mag, float second) const {
 #if defined(__CUDA_ARCH__)
-        return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(m, 0.0f))));
+        const unsigned bm = __float_as_uint(fmaxf(best_mag, 0.0f));
+        const unsigned top = __reduce_max_sync(0xffffffffu, bm);
+        const unsigned holders = __ballot_sync(0xffffffffu, bm == top);
+        const bool winner = (threadIdx.x & 31u) == (unsigned)(__ffs(holders) - 1);
+        const float cand = winner ? second : fmaxf(second, best_mag);
+        return __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(cand, 0.0f))));
 #else
-        return m;
+        (void)best_mag;
+        return second;
 #endif
     }
-    // current value of a key other CTAs of this launch update with atomicMax
+    // current value of a key / bit pattern other CTAs of this launch update with atomicMax
     ASC_HD unsigned long long peek_key(const unsigned long long* k) const {
 #if defined(__CUDA_ARCH__)
         return __ldcg(k);
@@ -699,31 +716,60 @@ struct DeviceExec {
         return *k;
 #endif
     }
-    // CTA-wide maximum of a per-thread key, then one atomicMax on *dst.
-    // `scratch`: at least 32 * 8 bytes of the CTA's dynamic shared memory; it may
-    // alias data f() reads (a barrier separates the two uses).  No static
-    // shared memory, so the column kernels keep 3 CTAs per SM.
-    template <class F>
-    ASC_HD void phase_argmax(F&& f, unsigned long long* dst, void* scratch) {
+    ASC_HD unsigned int peek_bits(const unsigned int* k) const {
 #if defined(__CUDA_ARCH__)
-        unsigned long long* s_best = reinterpret_cast<unsigned long long*>(scratch);
-        unsigned long long best = f((int)threadIdx.x);
+        return __ldcg(k);
+#else
+        return *k;
+#endif
+    }
+    // CTA-wide (peak key, second peak) of the per-thread pairs, then one atomicMax on *dst
+    // and one on *dst_second.  The key the atomicMax displaces (or fails to displace) is a
+    // second-peak candidate too: over all CTAs max(min(old, mine)) is exactly the second
+    // largest CTA peak.  `scratch`: at least 33 * 8 bytes of the CTA's dynamic shared memory;
+    // it may alias data f() reads (a barrier separates the two uses).  No static shared
+    // memory, so the column kernels keep 3 CTAs per SM.
+    template <class F>
+    ASC_HD void phase_argmax(F&& f, unsigned long long* dst, unsigned int* dst_second, void* scratch) {
+#if defined(__CUDA_ARCH__)
+        unsigned long long* s_best = reinterpret_cast<unsigned long long*>(scratch);   // [32] + [1] broadcast
+        unsigned int* s_sec = reinterpret_cast<unsigned int*>(s_best + 33);            // [32]
+        const ArgmaxPair mine = f((int)threadIdx.x);
+        unsigned long long best = mine.best;
         __syncthreads();
         for (int o = 16; o > 0; o >>= 1) {
             unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
             best = other > best ? other : best;
         }
         const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int nw = (blockDim.x + 31) >> 5;
         if (lane == 0) s_best[wid] = best;
         __syncthreads();
         if (wid == 0) {
-            const int nw = (blockDim.x + 31) >> 5;
             best = lane < nw ? s_best[lane] : 0ull;
             for (int o = 16; o > 0; o >>= 1) {
                 unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
                 best = other > best ? other : best;
             }
-            if (lane == 0) atomicMax(dst, best);
+            if (lane == 0) s_best[32] = best;
+        }
+        __syncthreads();
+        const unsigned long long cta_best = s_best[32];
+        // every thread but the winner also offers its own peak as a second-peak candidate
+        float cand = mine.second;
+        if (mine.best != cta_best && mine.best != 0ull) cand = fmaxf(cand, argmax_key_mag(mine.best));
+        unsigned int cb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(cand, 0.0f)));
+        if (lane == 0) s_sec[wid] = cb;
+        __syncthreads();
+        if (wid == 0) {
+            cb = __reduce_max_sync(0xffffffffu, lane < nw ? s_sec[lane] : 0u);
+            if (lane == 0) {
+                const unsigned long long old = atomicMax(dst, cta_best);
+                const unsigned long long loser = old < cta_best ? old : cta_best;
+                float sec = __uint_as_float(cb);
+                if (loser != 0ull && old != cta_best) sec = fmaxf(sec, argmax_key_mag(loser));
+                atomicMax(dst_second, float_order_bits(sec));
+            }
         }
         __syncthreads();
 #endif

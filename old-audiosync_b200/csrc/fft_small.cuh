@@ -47,8 +47,8 @@ struct SmallXcorrKernel {
         const cplx* wn;       // exp(-2*pi*i*t/2M), t < M
         SmallPlan plan;
     };
-    // two rows of M points + 256 bytes of reduction scratch
-    static size_t smem_bytes(int M) { return (size_t)2 * M * sizeof(cplx) + 256; }
+    // two rows of M points + 512 bytes of reduction scratch (phase_argmax needs 392)
+    static size_t smem_bytes(int M) { return (size_t)2 * M * sizeof(cplx) + 512; }
 
     // one in-place radix-R pass over `rows` rows; FWD: DIF (twiddle after the
     // butterfly), else DIT inverse (conjugate twiddle before it).
@@ -114,10 +114,7 @@ struct SmallXcorrKernel {
         const int np = p.plan.npass;
         const long long pair = ex.bz();
         ex.phase([&](int tid) {
-            if (tid == 0) {
-                PairPeak z; z.key = 0ull; z.raw_index = 0; z.peak = 0.0; z.resolved = 0; z.pad = 0;
-                p.peaks[pair] = z;
-            }
+            if (tid == 0) p.peaks[pair] = cleared_peak();
         });
         for (int ps = 0; ps < np; ps++) pass_any<true>(ex, p, buf, ps, 2, ps == 0);
         // split + multiply + merge: bins (k, M-k), k = 0 .. M/2, into row 0
@@ -134,7 +131,7 @@ struct SmallXcorrKernel {
         for (int ps = np - 1; ps >= 0; ps--) pass_any<false>(ex, p, buf, ps, 1, false);
         // natural order now: packed point n carries r[2n], r[2n+1]
         ex.phase_argmax(
-            [&](int tid) -> unsigned long long {
+            [&](int tid) -> ArgmaxPair {
                 ArgmaxAcc acc;
                 for (int n = tid; n < M; n += THREADS) {
                     const cplx v = buf[n];
@@ -143,9 +140,9 @@ struct SmallXcorrKernel {
                     else acc.consider(v.x, i_re);
                     acc.consider(v.y, i_re + 1u);
                 }
-                return acc.best;
+                return acc.result();
             },
-            &p.peaks[pair].key, buf + 2 * M);
+            &p.peaks[pair].key, &p.peaks[pair].second_bits, buf + 2 * M);
     }
 };
 

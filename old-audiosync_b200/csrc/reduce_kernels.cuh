@@ -73,58 +73,70 @@ direct_corr_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
     if (j0 + t < N) r_out[(size_t)blockIdx.y * (size_t)N + j0 + t] = acc * (double)N;
 }
 
-// Argmax over a double array with the reference's semantics (one CTA / pair).
-struct KeyF64 { double v; long long i; };
+// Argmax over a double array with the reference's semantics, plus the second peak
+// (largest |r[i]|, i != argmax; NaNs never count).  One CTA / pair.
+struct KeyF64 {
+    double v;       // compare value: signed r[0] for i == 0, |r[i]| otherwise (NaN handling below)
+    long long i;
+    double a;       // |r[i]| of this candidate (0 for NaN)
+    double s;       // second peak of the set this candidate leads
+};
 
 __device__ __forceinline__ KeyF64 key_better(KeyF64 a, KeyF64 b) {
-    // larger value wins; equal values -> smaller index wins
-    if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
-    return a;
+    // larger value wins; equal values -> smaller index wins; the loser's magnitude and both
+    // sets' second peaks are second-peak candidates of the union
+    const bool pick_b = b.v > a.v || (b.v == a.v && b.i < a.i);
+    KeyF64 w = pick_b ? b : a;
+    const KeyF64 l = pick_b ? a : b;
+    double s = fmax(a.s, b.s);
+    if (l.i != 0x7fffffffffffffffLL) s = fmax(s, l.a);
+    w.s = s;
+    return w;
+}
+
+__device__ __forceinline__ KeyF64 key_shfl_xor(KeyF64 k, int o) {
+    KeyF64 c;
+    c.v = __shfl_xor_sync(0xffffffffu, k.v, o);
+    c.i = __shfl_xor_sync(0xffffffffu, k.i, o);
+    c.a = __shfl_xor_sync(0xffffffffu, k.a, o);
+    c.s = __shfl_xor_sync(0xffffffffu, k.s, o);
+    return c;
 }
 
 __global__ void __launch_bounds__(1024)
 argmax_f64_kernel(const double* __restrict__ r, long long N, PairPeak* __restrict__ peaks)
 {
-    __shared__ double s_v[32];
-    __shared__ long long s_i[32];
+    __shared__ KeyF64 s_k[32];
     const double* rp = r + (size_t)blockIdx.x * (size_t)N;
     const double ninf = -INFINITY, pinf = INFINITY;
-    KeyF64 best; best.v = ninf; best.i = 0x7fffffffffffffffLL;
+    KeyF64 best; best.v = ninf; best.i = 0x7fffffffffffffffLL; best.a = 0.0; best.s = 0.0;
     for (long long i = threadIdx.x; i < N; i += blockDim.x) {
         double x = rp[i];
         KeyF64 c;
         c.i = i;
+        const double a = fabs(x);
+        c.a = (a != a) ? 0.0 : a;
+        c.s = 0.0;
         if (i == 0) c.v = (x != x) ? pinf : x;
-        else { double a = fabs(x); c.v = (a != a) ? ninf : a; }
+        else c.v = (a != a) ? ninf : a;
         // a NaN candidate (ninf) must still lose to a real -inf seed on index order only
         best = key_better(best, c);
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        KeyF64 c;
-        c.v = __shfl_xor_sync(0xffffffffu, best.v, o);
-        c.i = __shfl_xor_sync(0xffffffffu, best.i, o);
-        best = key_better(best, c);
-    }
+    for (int o = 16; o > 0; o >>= 1) best = key_better(best, key_shfl_xor(best, o));
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-    if (l == 0) { s_v[w] = best.v; s_i[w] = best.i; }
+    if (l == 0) s_k[w] = best;
     __syncthreads();
     if (w == 0) {
         const int nw = (blockDim.x + 31) >> 5;
-        best.v = (l < nw) ? s_v[l] : ninf;
-        best.i = (l < nw) ? s_i[l] : 0x7fffffffffffffffLL;
-        for (int o = 16; o > 0; o >>= 1) {
-            KeyF64 c;
-            c.v = __shfl_xor_sync(0xffffffffu, best.v, o);
-            c.i = __shfl_xor_sync(0xffffffffu, best.i, o);
-            best = key_better(best, c);
-        }
+        if (l < nw) best = s_k[l];
+        else { best.v = ninf; best.i = 0x7fffffffffffffffLL; best.a = 0.0; best.s = 0.0; }
+        for (int o = 16; o > 0; o >>= 1) best = key_better(best, key_shfl_xor(best, o));
         if (l == 0) {
-            PairPeak p;
-            p.key = 0ull;
+            PairPeak p = cleared_peak();
             p.raw_index = best.i;
             p.peak = rp[best.i];
+            p.second = best.s;
             p.resolved = 1;
-            p.pad = 0;
             peaks[blockIdx.x] = p;
         }
     }
@@ -162,7 +174,8 @@ struct PearsonShared {
 
 // Finishes one pair from the summed statistics (thread 0 of the finishing CTA).
 __device__ __forceinline__ void pearson_finish(const PearsonPartial& s, const Window& w, long long raw,
-                                               double peak, audiosync_cuda_result* __restrict__ out)
+                                               double peak, double second,
+                                               audiosync_cuda_result* __restrict__ out)
 {
     // n == 0 -> 0/0 = NaN, like the reference's empty pointer range.
     const double n = (double)w.n;
@@ -177,6 +190,7 @@ __device__ __forceinline__ void pearson_finish(const PearsonPartial& s, const Wi
     r.ret = (coef != coef) ? -1 : 0;                       // src/cross_correlation.c:276
     r.success = (r.ret == 0 && coef >= 0.95) ? 1 : 0;       // src/audiosync.c:254
     r.raw_index = raw;
+    r.second = second;
     *out = r;
 }
 
@@ -195,13 +209,15 @@ __device__ __forceinline__ void pearson_block(
 {
     Window w;
     long long raw = 0;
-    double peak = 0.0;
+    double peak = 0.0, second = 0.0;
     if (peaks == nullptr) {           // explicit window: whole arrays of length explicit_n
         w.lag = 0; w.xoff = 0; w.yoff = 0; w.n = explicit_n;
     } else {
         const PairPeak p = peaks[pair];
         raw = p.resolved ? p.raw_index : (long long)argmax_key_index(p.key);
         peak = p.resolved ? p.peak : (double)argmax_key_value(p.key);
+        second = p.resolved ? p.second
+                            : (p.second_bits != 0u ? (double)float_from_order_bits(p.second_bits) : 0.0);
         w = fold_index(raw, L);
     }
     const T* __restrict__ x = sources + (size_t)pair * (size_t)src_pitch + w.xoff;
@@ -329,7 +345,7 @@ __device__ __forceinline__ void pearson_block(
             s.sxy += __shfl_xor_sync(0xffffffffu, s.sxy, o);
         }
         if (t == 0) {
-            pearson_finish(s, w, raw, peak, results + pair);
+            pearson_finish(s, w, raw, peak, second, results + pair);
             tickets[pair] = 0u;       // ready for the next wave
         }
     }

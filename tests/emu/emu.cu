@@ -26,16 +26,28 @@ struct HostExec {
     template <class F>
     void single(F&& f) { f(); }
     bool any(bool b) const { return b; }
-    float warp_max(float m) const { return m; }
+    float warp_second(float /*best_mag*/, float second) const { return second; }
     unsigned long long peek_key(const unsigned long long* k) const { return *k; }
+    unsigned int peek_bits(const unsigned int* k) const { return *k; }
     template <class F>
-    void phase_argmax(F&& f, unsigned long long* dst, void* /*scratch*/) {
+    void phase_argmax(F&& f, unsigned long long* dst, unsigned int* dst_second, void* /*scratch*/) {
+        // the CTA-level merge of (peak key, second peak) pairs, then the grid-level rule of
+        // DeviceExec::phase_argmax (sequentially: max / max-of-min)
         unsigned long long best = 0;
+        float second = 0.0f;
         for (int t = 0; t < nt; t++) {
-            unsigned long long k = f(t);
-            if (k > best) best = k;
+            const ArgmaxPair k = f(t);
+            const unsigned long long lose = k.best > best ? best : k.best;
+            if (k.best > best) best = k.best;
+            if (lose != 0) second = fmaxf(second, argmax_key_mag(lose));
+            second = fmaxf(second, k.second);
         }
-        if (best > *dst) *dst = best;
+        const unsigned long long old = *dst;
+        const unsigned long long loser = old < best ? old : best;
+        if (best > old) *dst = best;
+        if (loser != 0 && old != best) second = fmaxf(second, argmax_key_mag(loser));
+        const unsigned int sb = float_order_bits(second);
+        if (sb > *dst_second) *dst_second = sb;
     }
 };
 
@@ -52,7 +64,7 @@ static int run_static(const InT* source, const InT* sample, PairPeak* peak, cplx
     std::vector<cplx> row_rev = build_row_rev<Row>();
     std::vector<cplx> m_lo, m_hi;
     build_two_level(M, M - 1, m_lo, m_hi);
-    peak->key = 12345ull;   // garbage: K_A must clear it
+    peak->key = 12345ull; peak->second_bits = 777u;   // garbage: K_A must clear both
 
     {
         using K = ColFwdKernel<Col, Row::n, P::NT_COL, InT, sizeof(InT) == 4>;
@@ -94,11 +106,13 @@ static int run_small(const InT* source, const InT* sample, long long L, PairPeak
     using K = SmallXcorrKernel<InT>;
     typename K::Params p{source, sample, peak, wm.data(), wn.data(), pl};
     std::vector<cplx> smem(K::smem_bytes((int)L) / sizeof(cplx));
-    peak->key = 12345ull;   // garbage: the kernel must clear it
+    peak->key = 12345ull; peak->second_bits = 777u;   // garbage: the kernel must clear both
     HostExec ex{0, 0, 0, K::THREADS};
     K::run(ex, p, smem.data());
     return 0;
 }
+
+static double g_last_second = 0.0;   // second peak of the last emu_any call
 
 template <typename InT>
 static int emu_any(const InT* source, const InT* sample, long long L, int forced,
@@ -121,10 +135,13 @@ static int emu_any(const InT* source, const InT* sample, long long L, int forced
     if (rc != 0) return rc;
     *raw_index = (long long)argmax_key_index(pk.key);
     *peak_value = (double)argmax_key_value(pk.key);
+    g_last_second = pk.second_bits ? (double)float_from_order_bits(pk.second_bits) : 0.0;
     return 0;
 }
 
 extern "C" {
+
+double emu_last_second(void) { return g_last_second; }
 
 int emu_xcorr_f32(const float* source, const float* sample, long long L, int forced,
                   long long* raw_index, double* peak_value, int* path) {

@@ -48,6 +48,12 @@ def close(a, b, rtol=RTOL):
     return abs(a - b) <= rtol * max(abs(a), abs(b), 1e-300)
 
 
+def second_close(got, case):
+    """Second peak (largest |r[i]|, i != argmax) vs the oracle's.  The fp32
+    transform's noise is relative to the PEAK: 1e-4 of the second peak + 1e-6 of the peak."""
+    return abs(got - case["second"]) <= RTOL * case["second"] + 1e-6 * abs(case["peak"])
+
+
 def kat_inputs(rec):
     if rec["name"] == "T7":
         return np.sin(np.arange(2000.0)), np.sin(np.arange(1000.0))
@@ -131,6 +137,7 @@ def test_golden_batch_device_f32(ac, ctx, L):
         assert int(r["raw_index"]) == c["raw_index"] and int(r["lag"]) == c["lag"]
         assert int(r["ret"]) == c["ret"] and bool(r["success"]) == c["success"]
         assert close(float(r["coef"]), c["coef"]) and close(float(r["peak"]), c["peak"])
+        assert second_close(float(r["second"]), c)
 
 
 def test_device_generator_is_bit_identical(ac, ctx, capi):
@@ -314,6 +321,65 @@ def test_residency_guards(ac, capi):
     ac.cross_correlation_ptr(a.ctypes.data, b.ctypes.data, L1)
     ac.cross_correlation_ptr(a.ctypes.data, b.ctypes.data, L2)
     assert ac.dropin_stats()[2] == h
+
+
+# ------------------------------------------------------------------ second peak / torch surface
+
+@pytest.mark.parametrize("L", [10, 12, 250, 1000, 3600, 6000, 144000])
+def test_second_peak_all_paths_vs_oracle(ac, capi, L):
+    """direct (fp64), single-CTA FFT and four-step paths all report the oracle's `second`."""
+    n = 4
+    srcs = np.empty((n, 2 * L), np.float64); smps = np.empty((n, L), np.float64)
+    for i in range(n):
+        srcs[i], smps[i] = capi.synth_pair(SEED + 11, i, L)
+    with ac.Context([0]) as c:
+        for path in ((ac.PATH_AUTO, ac.PATH_DIRECT) if L < 144000 else (ac.PATH_AUTO,)):
+            c.set_path(path)
+            rec = c.xcorr_batch_records(srcs.ctypes.data, smps.ctypes.data, n, L, ac.F64, ac.HOST)
+            for i in range(n):
+                o = capi.cross_correlation(srcs[i], smps[i])
+                assert int(rec["raw_index"][i]) == o["raw_index"] and int(rec["lag"][i]) == o["lag"]
+                assert close(float(rec["peak"][i]), o["peak"])
+                assert abs(float(rec["second"][i]) - o["second"]) <= RTOL * o["second"] + 1e-6 * abs(o["peak"])
+
+
+def test_second_peak_of_a_tie_equals_the_peak(ac):
+    """Two equal maxima: the first index wins (reference :52-67) and the second peak equals the
+    peak, i.e. margin 0 -- exactly the case the parity precondition excludes."""
+    L = 8
+    src = np.zeros(2 * L); smp = np.zeros(L)
+    src[3] = 1.0; src[9] = 1.0; smp[0] = 1.0           # r[3] == r[9]
+    with ac.Context([0]) as c:
+        rec = c.xcorr_batch_records(src.ctypes.data, smp.ctypes.data, 1, L, ac.F64, ac.HOST)
+    assert int(rec["raw_index"][0]) == 3 and float(rec["second"][0]) == abs(float(rec["peak"][0])) > 0
+
+
+def test_torch_zero_copy_batch(ac, ctx, capi):
+    """CUDA tensors in, records out, on torch's current stream, no copies."""
+    import torch
+    L, n = 144000, 6
+    gold = {c["pair_id"]: c for c in _pairs() if c["L"] == L}
+    for tdt, dt in ((torch.float32, ac.F32), (torch.float64, ac.F64)):
+        src = torch.empty(n, 2 * L, dtype=tdt, device="cuda:0"); smp = torch.empty(n, L, dtype=tdt, device="cuda:0")
+        ctx.synth_pairs(0, SEED, 0, n, L, dt, src.data_ptr(), smp.data_ptr())
+        ctx.synchronize(0)
+        rec = ctx.xcorr_batch_torch(src, smp)                       # default stream
+        st = torch.cuda.Stream("cuda:0")
+        with torch.cuda.stream(st):
+            out = ctx.xcorr_batch_torch(src, smp, sync=False)        # side stream, stream-ordered
+            host = out.cpu()
+        st.synchronize()
+        rec2 = host.numpy().view(ac.RESULT_DTYPE)
+        for name in ac.RESULT_DTYPE.names:
+            assert np.array_equal(rec[name], rec2[name], equal_nan=True), name
+        for pid, c in gold.items():
+            if pid < n:
+                assert int(rec["lag"][pid]) == c["lag"] and int(rec["ret"][pid]) == c["ret"]
+                assert close(float(rec["coef"][pid]), c["coef"]) and second_close(float(rec["second"][pid]), c)
+    with pytest.raises(ValueError):
+        ctx.xcorr_batch_torch(src[:, ::2], smp[:, ::2])              # non-contiguous: refused, not copied
+    with pytest.raises(TypeError):
+        ctx.xcorr_batch_torch(src.half(), smp.half())
 
 
 # ------------------------------------------------------------------ host batch API
