@@ -409,6 +409,18 @@ ASC_HD void dft_reg(cplx (&v)[R]) { DftReg<R, DIR>::run(v); }
 // entries of one pass (tw points at the pass's table): k = 2^i is a load,
 // any other k is the product w[hb(k)] * w[k - hb(k)] (at most 3 products deep
 // for R <= 16, i.e. a few ulp).  Trades LSU wavefronts for FMA-pipe work.
+// Fills w[k], k not a power of two, from the power-of-two entries already in w.
+template <int R>
+ASC_HD void fill_twiddles(cplx (&w)[R]) {
+    static_for<1, R>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        if constexpr ((k & (k - 1)) != 0) {
+            constexpr int hb = (k >= 16) ? 16 : (k >= 8) ? 8 : (k >= 4) ? 4 : 2;
+            w[k] = cmul(w[hb], w[k - hb]);
+        }
+    });
+}
+
 template <int R>
 ASC_HD void pass_twiddles(const cplx* __restrict__ tw, int S, int j, cplx (&w)[R]) {
     static_for<1, R>([&](auto K) {
@@ -416,11 +428,9 @@ ASC_HD void pass_twiddles(const cplx* __restrict__ tw, int S, int j, cplx (&w)[R
         if constexpr ((k & (k - 1)) == 0) {
             constexpr int i = (k == 1) ? 0 : (k == 2) ? 1 : (k == 4) ? 2 : (k == 8) ? 3 : (k == 16) ? 4 : 5;
             w[k] = ldg(tw + i * S + j);
-        } else {
-            constexpr int hb = (k >= 16) ? 16 : (k >= 8) ? 8 : (k >= 4) ? 4 : 2;
-            w[k] = cmul(w[hb], w[k - hb]);
         }
     });
+    fill_twiddles<R>(w);
 }
 
 // ---------------------------------------------------------------- radix list

@@ -147,8 +147,9 @@ struct ColFwdKernel {
 #pragma unroll
                 for (int i = 0; i < (M1 + RSTEP - 1) / RSTEP; i++) {
                     const int row = row0 + i * RSTEP;
+                    // rows of the zero pad are neither staged nor cleared: pass 0 below treats
+                    // them as zeros in registers and overwrites every position of the tile
                     if (row < rows_valid) cp_async16(sm + i * (NT * 16), g + (size_t)i * (RSTEP * M2 * sizeof(cplx)));
-                    else if (row < M1) smem_zero16(sm + i * (NT * 16));
                 }
                 cp_async_wait_all();
             });
@@ -165,32 +166,45 @@ struct ColFwdKernel {
                 if (from_global && clears_peak && tid == 0) p.peaks[pair] = cleared_peak();
                 const int c = tid & (COL_T - 1);          // fixed column of this thread
                 if constexpr (!last) {
-                    for (int w = tid; w < items; w += NT) {
-                        const int bf = w >> 4;
-                        const int blk = bf / S;
-                        const int j = bf - blk * S;
-                        const int i0 = blk * (S * R) + j;
-                        cplx v[R];
-                        if constexpr (from_global) {
-                            static_for<0, R>([&](auto Q) {
-                                constexpr int q = decltype(Q)::value;
-                                const long long n = (long long)(i0 + q * S) * M2 + c0 + c;
-                                v[q] = n < nvalid ? load_packed<InT>(x, n) : cmake(0.f, 0.f);
-                            });
-                        } else {
-                            static_for<0, R>([&](auto Q) {
-                                constexpr int q = decltype(Q)::value;
-                                v[q] = buf[(i0 + q * S) * COL_T + c];
+                    // HZ: first pass of a staged SAMPLE tile.  Inputs q >= R/2 are rows of the
+                    // zero pad (i0 + q*S >= M1/2): zeros in registers, no shared-memory reads.
+                    auto items_loop = [&](auto HZ) {
+                        constexpr bool hz = decltype(HZ)::value;
+                        cplx t[R];
+                        for (int w = tid; w < items; w += NT) {
+                            const int bf = w >> 4;
+                            const int blk = bf / S;
+                            const int j = bf - blk * S;
+                            const int i0 = blk * (S * R) + j;
+                            cplx v[R];
+                            if constexpr (from_global) {
+                                static_for<0, R>([&](auto Q) {
+                                    constexpr int q = decltype(Q)::value;
+                                    const long long n = (long long)(i0 + q * S) * M2 + c0 + c;
+                                    v[q] = n < nvalid ? load_packed<InT>(x, n) : cmake(0.f, 0.f);
+                                });
+                            } else {
+                                static_for<0, R>([&](auto Q) {
+                                    constexpr int q = decltype(Q)::value;
+                                    if constexpr (hz && 2 * q >= R) v[q] = cmake(0.f, 0.f);
+                                    else v[q] = buf[(i0 + q * S) * COL_T + c];
+                                });
+                            }
+                            dft_reg<R, -1>(v);
+                            pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
+                            buf[i0 * COL_T + c] = v[0];
+                            static_for<1, R>([&](auto K) {
+                                constexpr int k = decltype(K)::value;
+                                buf[(i0 + k * S) * COL_T + c] = cmul(v[k], t[k]);
                             });
                         }
-                        dft_reg<R, -1>(v);
-                        cplx t[R];
-                        pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
-                        buf[i0 * COL_T + c] = v[0];
-                        static_for<1, R>([&](auto K) {
-                            constexpr int k = decltype(K)::value;
-                            buf[(i0 + k * S) * COL_T + c] = cmul(v[k], t[k]);
-                        });
+                    };
+                    if constexpr (first && ASYNC) {
+                        static_assert(R % 2 == 0 && S * R == M1, "zero-pad rows must be the inputs q >= R/2 of pass 0");
+                        if (sig == 1) items_loop(std::true_type{});
+                        else items_loop(std::false_type{});
+                    } else {
+                        items_loop(std::false_type{});
                     }
                 } else {
                     // S == 1: positions i0 .. i0+R-1 hold bins k1 = f0 + k*Wt, f0 < Wt.
@@ -203,23 +217,40 @@ struct ColFwdKernel {
                         constexpr int k = decltype(K)::value;
                         g[k] = tw2(p.m_lo, p.m_hi, n2 * (unsigned)(Wt * k));
                     });
-                    for (int w = tid; w < items; w += NT) {
-                        const int blk = w >> 4;
-                        const int i0 = blk * R;
-                        cplx v[R];
-                        static_for<0, R>([&](auto Q) {
-                            constexpr int q = decltype(Q)::value;
-                            v[q] = buf[(i0 + q) * COL_T + c];
+                    // The twiddle loads of a chunk of items are issued together ahead of the
+                    // butterflies (three dependent table reads per item would otherwise be exposed
+                    // once per item: the tables do not stay in the small L1 left beside the tiles).
+                    constexpr int ITER = (items + NT - 1) / NT;
+                    constexpr int CH = ITER <= 6 ? ITER : 4;
+                    for (int it0 = 0; it0 < ITER; it0 += CH) {
+                        int f0s[CH];
+                        cplx t0s[CH];
+                        static_for<0, CH>([&](auto I) {
+                            constexpr int i = decltype(I)::value;
+                            const int w = tid + (it0 + i) * NT;
+                            f0s[i] = RL::freq_of_pos(((w < items ? w : 0) >> 4) * R);
+                            t0s[i] = cmul(ldg(p.tc + f0s[i] * COL_T + c),
+                                          tw2(p.m_lo, p.m_hi, (unsigned)c0 * (unsigned)f0s[i]));
                         });
-                        dft_reg<R, -1>(v);
-                        const int f0 = RL::freq_of_pos(i0);
-                        const cplx t0 = cmul(ldg(p.tc + f0 * COL_T + c),
-                                             tw2(p.m_lo, p.m_hi, (unsigned)c0 * (unsigned)f0));
-                        cplx* __restrict__ o = out + ((unsigned)f0 * (unsigned)M2 + n2);   // < M < 2^31
-                        o[0] = cmul(v[0], t0);
-                        static_for<1, R>([&](auto K) {
-                            constexpr int k = decltype(K)::value;
-                            o[(size_t)k * Wt * M2] = cmul(v[k], cmul(t0, g[k]));
+                        static_for<0, CH>([&](auto I) {
+                            constexpr int i = decltype(I)::value;
+                            const int w = tid + (it0 + i) * NT;
+                            if (w < items) {
+                                const int i0 = (w >> 4) * R;
+                                cplx v[R];
+                                static_for<0, R>([&](auto Q) {
+                                    constexpr int q = decltype(Q)::value;
+                                    v[q] = buf[(i0 + q) * COL_T + c];
+                                });
+                                dft_reg<R, -1>(v);
+                                const cplx t0 = t0s[i];
+                                cplx* __restrict__ o = out + ((unsigned)f0s[i] * (unsigned)M2 + n2);   // < M < 2^31
+                                o[0] = cmul(v[0], t0);
+                                static_for<1, R>([&](auto K) {
+                                    constexpr int k = decltype(K)::value;
+                                    o[(size_t)k * Wt * M2] = cmul(v[k], cmul(t0, g[k]));
+                                });
+                            }
                         });
                     }
                 }
@@ -278,6 +309,7 @@ struct ColInvKernel {
             constexpr int items = (M1 / R) * COL_T;
             ex.phase([&](int tid) {
                 const int c = tid & (COL_T - 1);
+                cplx t[R];
                 for (int w = tid; w < items; w += NT) {
                     const int bf = w >> 4;
                     const int blk = bf / S;
@@ -289,7 +321,6 @@ struct ColInvKernel {
                         v[q] = buf[(i0 + q * S) * COL_T + c];
                     });
                     dft_reg<R, +1>(v);
-                    cplx t[R];
                     pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
                     buf[i0 * COL_T + c] = v[0];
                     static_for<1, R>([&](auto K) {
