@@ -34,6 +34,11 @@
 
 namespace asc {
 
+#ifndef ASC_SPLIT_UNROLL
+#define ASC_SPLIT_UNROLL 2   // items of the split/multiply/merge loop in flight per thread
+#endif
+constexpr int SPLIT_UNROLL = ASC_SPLIT_UNROLL;
+
 constexpr int COL_T = 16;          // columns per tile: 16 * 8 B = one 128-byte line
 constexpr unsigned TW2_BITS = 10;  // two-level twiddle tables: a = hi * 1024 + lo
 constexpr unsigned TW2_MASK = (1u << TW2_BITS) - 1u;
@@ -584,6 +589,7 @@ struct RowFusedKernel {
                     cplx* __restrict__ zs_b = buf + RP;
                     cplx* __restrict__ zp_a = buf + 2 * RP;
                     cplx* __restrict__ zp_b = buf + 3 * RP;
+#pragma unroll SPLIT_UNROLL
                     for (int e = tid; e < M2; e += NT) {
                         const int pb = M2 - 1 - e;
                         const cplx w2 = cmul(ldg(p.rev + e), wk1);
