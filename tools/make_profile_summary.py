@@ -43,7 +43,11 @@ if os.path.exists(rep):
                ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fp32 pipe %"),
                ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
                ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
+               ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1/shared data pipe %"),
+               ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
                ("smsp__inst_executed.sum", "warp instructions"), ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem wavefronts"),
+               ("l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum", "global-load wavefronts"),
+               ("l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_st.sum", "global-store wavefronts"),
                ("launch__registers_per_thread", "registers"), ("launch__occupancy_limit_shared_mem", "CTA/SM (smem)"),
                ("launch__occupancy_limit_registers", "CTA/SM (regs)")]
     names = [cls(d[col("Kernel Name")]) for d in data]

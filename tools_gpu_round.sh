@@ -11,7 +11,7 @@ tail -5 gpurun_out/pytest_$TAG.log
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
 cat gpurun_out/bench_$TAG.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$TAG.csv \
-  python bench.py --pairs 64 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launch_$TAG.log 2>&1
+  python bench.py --pairs 128 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-latency > gpurun_out/ncu_launch_$TAG.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:fft_kernel_entry|pearson' -s 4 -c 4 -f -o gpurun_out/prof_$TAG \
-  python bench.py --pairs 64 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_$TAG.log 2>&1
+  python bench.py --pairs 64 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-latency > gpurun_out/ncu_full_$TAG.log 2>&1
 ls -la gpurun_out/
