@@ -174,7 +174,7 @@ struct ColFwdKernel {
                     // HZ: first pass of a staged SAMPLE tile.  Inputs q >= R/2 are rows of the
                     // zero pad (i0 + q*S >= M1/2): zeros in registers, no shared-memory reads.
                     auto items_loop = [&](auto HZ) {
-                        constexpr bool hz = decltype(HZ)::value;
+                        [[maybe_unused]] constexpr bool hz = decltype(HZ)::value;
                         cplx t[R];
                         for (int w = tid; w < items; w += NT) {
                             const int bf = w >> 4;
@@ -761,54 +761,47 @@ struct DeviceExec {
 #endif
     }
     // CTA-wide (peak key, second peak) of the per-thread pairs, then one atomicMax on *dst
-    // and one on *dst_second.  The key the atomicMax displaces (or fails to displace) is a
-    // second-peak candidate too: over all CTAs max(min(old, mine)) is exactly the second
-    // largest CTA peak.  `scratch`: at least 33 * 8 bytes of the CTA's dynamic shared memory;
-    // it may alias data f() reads (a barrier separates the two uses).  No static shared
-    // memory, so the column kernels keep 3 CTAs per SM.
+    // and one on *dst_second.  Pairs merge associatively: the larger key leads, the smaller
+    // key's magnitude joins the two seconds.  At grid level the key the atomicMax displaces
+    // (or fails to displace) is a second-peak candidate too: over all CTAs max(min(old, mine))
+    // is exactly the second largest CTA peak.  `scratch`: at least 32 * 12 bytes of the CTA's
+    // dynamic shared memory; it may alias data f() reads (a barrier separates the two uses).
+    // No static shared memory, so the column kernels keep 3 CTAs per SM.
+#if defined(__CUDA_ARCH__)
+    static __device__ __forceinline__ void merge_pairs(unsigned long long& best, float& second,
+                                                       unsigned long long ob, float os) {
+        const unsigned long long lose = ob > best ? best : ob;
+        best = ob > best ? ob : best;
+        second = fmaxf(second, os);
+        if (lose != 0ull) second = fmaxf(second, argmax_key_mag(lose));
+    }
+#endif
     template <class F>
     ASC_HD void phase_argmax(F&& f, unsigned long long* dst, unsigned int* dst_second, void* scratch) {
 #if defined(__CUDA_ARCH__)
-        unsigned long long* s_best = reinterpret_cast<unsigned long long*>(scratch);   // [32] + [1] broadcast
-        unsigned int* s_sec = reinterpret_cast<unsigned int*>(s_best + 33);            // [32]
+        unsigned long long* s_best = reinterpret_cast<unsigned long long*>(scratch);   // [32]
+        float* s_sec = reinterpret_cast<float*>(s_best + 32);                          // [32]
         const ArgmaxPair mine = f((int)threadIdx.x);
         unsigned long long best = mine.best;
-        __syncthreads();
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-            best = other > best ? other : best;
-        }
+        float second = mine.second;
+        for (int o = 16; o > 0; o >>= 1)
+            merge_pairs(best, second, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, second, o));
         const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
         const int nw = (blockDim.x + 31) >> 5;
-        if (lane == 0) s_best[wid] = best;
+        __syncthreads();                      // every warp is done reading what `scratch` aliases
+        if (lane == 0) { s_best[wid] = best; s_sec[wid] = second; }
         __syncthreads();
         if (wid == 0) {
             best = lane < nw ? s_best[lane] : 0ull;
-            for (int o = 16; o > 0; o >>= 1) {
-                unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-                best = other > best ? other : best;
-            }
-            if (lane == 0) s_best[32] = best;
-        }
-        __syncthreads();
-        const unsigned long long cta_best = s_best[32];
-        // every thread but the winner also offers its own peak as a second-peak candidate
-        float cand = mine.second;
-        if (mine.best != cta_best && mine.best != 0ull) cand = fmaxf(cand, argmax_key_mag(mine.best));
-        unsigned int cb = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(cand, 0.0f)));
-        if (lane == 0) s_sec[wid] = cb;
-        __syncthreads();
-        if (wid == 0) {
-            cb = __reduce_max_sync(0xffffffffu, lane < nw ? s_sec[lane] : 0u);
+            second = lane < nw ? s_sec[lane] : 0.0f;
+            for (int o = 16; o > 0; o >>= 1)
+                merge_pairs(best, second, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, second, o));
             if (lane == 0) {
-                const unsigned long long old = atomicMax(dst, cta_best);
-                const unsigned long long loser = old < cta_best ? old : cta_best;
-                float sec = __uint_as_float(cb);
-                if (loser != 0ull && old != cta_best) sec = fmaxf(sec, argmax_key_mag(loser));
-                atomicMax(dst_second, float_order_bits(sec));
+                const unsigned long long old = atomicMax(dst, best);
+                if (old != best) merge_pairs(best, second, old, 0.0f);
+                atomicMax(dst_second, float_order_bits(second));
             }
         }
-        __syncthreads();
 #endif
     }
 };
