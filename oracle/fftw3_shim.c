@@ -19,12 +19,22 @@
  *     the life of the process so that plan creation stays cheap, as it is
  *     with FFTW_ESTIMATE.
  *
+ * Optional second backend, for TIMING the reference only (bench.py's CPU legs):
+ * with ORACLE_FFT_BACKEND=mkl in the environment and Intel MKL's DFTI entry
+ * points reachable (PyTorch's libtorch_cpu.so exports them; ORACLE_MKL_LIB names
+ * the library), plans of even length run on MKL -- an FFTW-class library -- one
+ * thread per transform like FFTW's default plans, so the reference's CPU number
+ * is not held back by this file's plain-C Stockham core.  The backend is
+ * self-tested against a direct DFT when it is loaded and is never used by the
+ * tests: golden vectors and parity checks stay on the independent core below.
+ *
  * Nothing under /root/reference was consulted for this file beyond the call
  * sites; nothing in the product library links it.
  */
 #define _GNU_SOURCE
 #include "fftw3.h"
 
+#include <dlfcn.h>
 #include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
@@ -305,7 +315,93 @@ struct oracle_fftw_plan_s {
     struct cfft core;
     const cpx *wn;          /* W_n^t for the split/merge step (even n)   */
     cpx *work0, *work1;
+    void *mkl;              /* committed DFTI descriptor when the MKL backend serves this plan */
 };
+
+
+/* ------------------------------------------------------- optional MKL backend */
+/* Values of mkl_dfti.h (enum DFTI_CONFIG_PARAM / DFTI_CONFIG_VALUE); checked by the self-test. */
+enum { DFTI_CONJUGATE_EVEN_STORAGE_ = 10, DFTI_PLACEMENT_ = 11, DFTI_PACKED_FORMAT_ = 21, DFTI_THREAD_LIMIT_ = 27,
+       DFTI_REAL_ = 33, DFTI_DOUBLE_ = 36, DFTI_COMPLEX_COMPLEX_ = 39, DFTI_NOT_INPLACE_ = 44, DFTI_CCE_FORMAT_ = 57 };
+typedef long (*dfti_create_t)(void **, int, long);
+typedef long (*dfti_set_t)(void *, int, ...);
+typedef long (*dfti_commit_t)(void *);
+typedef long (*dfti_compute_t)(void *, void *, ...);
+typedef long (*dfti_free_t)(void **);
+static struct {
+    int state;              /* 0 untried, 1 usable, -1 unavailable */
+    dfti_create_t create; dfti_set_t set; dfti_commit_t commit;
+    dfti_compute_t fwd, bwd; dfti_free_t release;
+} mkl;
+static pthread_mutex_t mkl_mutex = PTHREAD_MUTEX_INITIALIZER;
+
+static void *mkl_descriptor(int n)
+{
+    void *d = NULL;
+    if (mkl.create(&d, DFTI_REAL_, (long)n) != 0 || !d) return NULL;
+    if (mkl.set(d, DFTI_PLACEMENT_, DFTI_NOT_INPLACE_) != 0 ||
+        mkl.set(d, DFTI_CONJUGATE_EVEN_STORAGE_, DFTI_COMPLEX_COMPLEX_) != 0 ||
+        mkl.set(d, DFTI_PACKED_FORMAT_, DFTI_CCE_FORMAT_) != 0 ||
+        mkl.set(d, DFTI_THREAD_LIMIT_, 1L) != 0 ||
+        mkl.commit(d) != 0) {
+        mkl.release(&d);
+        return NULL;
+    }
+    return d;
+}
+
+/* r2c and c2r of a short signal against a direct DFT */
+static int mkl_selftest(void)
+{
+    enum { N = 24 };
+    double x[N], y[N];
+    cpx X[N / 2 + 1];
+    for (int j = 0; j < N; j++) x[j] = sin(0.7 * j) + 0.01 * j * j - 0.3 * (j % 5);
+    void *d = mkl_descriptor(N);
+    if (!d) return -1;
+    int ok = mkl.fwd(d, x, X) == 0;
+    for (int k = 0; ok && k <= N / 2; k++) {
+        double re = 0.0, im = 0.0;
+        for (int j = 0; j < N; j++) {
+            re += x[j] * cos(2.0 * M_PI * j * k / N);
+            im -= x[j] * sin(2.0 * M_PI * j * k / N);
+        }
+        if (fabs(re - X[k].re) > 1e-10 || fabs(im - X[k].im) > 1e-10) ok = 0;
+    }
+    ok = ok && mkl.bwd(d, X, y) == 0;
+    for (int j = 0; ok && j < N; j++)
+        if (fabs(y[j] - N * x[j]) > 1e-9) ok = 0;          /* unnormalised, like FFTW's c2r */
+    mkl.release(&d);
+    return ok ? 0 : -1;
+}
+
+static int mkl_ready(void)
+{
+    pthread_mutex_lock(&mkl_mutex);
+    if (mkl.state == 0) {
+        mkl.state = -1;
+        const char *want = getenv("ORACLE_FFT_BACKEND");
+        if (want && strcmp(want, "mkl") == 0) {
+            const char *path = getenv("ORACLE_MKL_LIB");
+            void *h = dlopen(path ? path : "libtorch_cpu.so", RTLD_NOW | RTLD_NOLOAD);
+            if (!h) h = dlopen(path ? path : "libtorch_cpu.so", RTLD_NOW | RTLD_LOCAL);
+            if (h) {
+                mkl.create = (dfti_create_t)dlsym(h, "DftiCreateDescriptor_d_1d");
+                mkl.set = (dfti_set_t)dlsym(h, "DftiSetValue");
+                mkl.commit = (dfti_commit_t)dlsym(h, "DftiCommitDescriptor");
+                mkl.fwd = (dfti_compute_t)dlsym(h, "DftiComputeForward");
+                mkl.bwd = (dfti_compute_t)dlsym(h, "DftiComputeBackward");
+                mkl.release = (dfti_free_t)dlsym(h, "DftiFreeDescriptor");
+                if (mkl.create && mkl.set && mkl.commit && mkl.fwd && mkl.bwd && mkl.release &&
+                    mkl_selftest() == 0)
+                    mkl.state = 1;
+            }
+        }
+    }
+    const int r = mkl.state == 1;
+    pthread_mutex_unlock(&mkl_mutex);
+    return r;
+}
 
 static fftw_plan plan_new(enum plan_kind kind, int n, double *r, fftw_complex *cx)
 {
@@ -313,6 +409,10 @@ static fftw_plan plan_new(enum plan_kind kind, int n, double *r, fftw_complex *c
     fftw_plan p = calloc(1, sizeof(*p));
     if (!p) return NULL;
     p->kind = kind; p->n = n; p->rbuf = r; p->cbuf = cx;
+    if (n % 2 == 0 && n >= 4 && mkl_ready()) {
+        p->mkl = mkl_descriptor(n);
+        if (p->mkl) return p;
+    }
     p->h = (n % 2 == 0) ? n / 2 : n;
     if (cfft_init(&p->core, p->h) != 0) { free(p); return NULL; }
     p->wn = (n % 2 == 0) ? twiddles_for(n) : NULL;
@@ -397,12 +497,18 @@ static void exec_c2r(const fftw_plan p)
 void fftw_execute(const fftw_plan p)
 {
     if (!p) return;
+    if (p->mkl) {
+        if (p->kind == PLAN_R2C) mkl.fwd(p->mkl, p->rbuf, p->cbuf);
+        else mkl.bwd(p->mkl, p->cbuf, p->rbuf);
+        return;
+    }
     if (p->kind == PLAN_R2C) exec_r2c(p); else exec_c2r(p);
 }
 
 void fftw_destroy_plan(fftw_plan p)
 {
     if (!p) return;
+    if (p->mkl) mkl.release(&p->mkl);
     free(p->work0); free(p->work1); free(p);
 }
 
@@ -417,4 +523,7 @@ double *fftw_alloc_real(size_t n) { return fftw_malloc(n * sizeof(double)); }
 fftw_complex *fftw_alloc_complex(size_t n) { return fftw_malloc(n * sizeof(fftw_complex)); }
 void fftw_free(void *p) { free(p); }
 
-const char *oracle_fft_backend(void) { return "shim-stockham-f64"; }
+const char *oracle_fft_backend(void)
+{
+    return mkl_ready() ? "mkl-dfti-f64 (one thread per transform)" : "shim-stockham-f64";
+}
