@@ -213,7 +213,7 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     # the reference runs two FFT threads per call: nproc/2 concurrent callers use every core
     callers = max(1, cores // 2)
-    per_step = max(2 * callers, 8)
+    per_step = max(4 * callers, 8)
     for _ in range(args.warmup):
         cpu_reference_run(L, callers, callers, SEED)
     times = []

@@ -335,9 +335,47 @@ static struct {
 } mkl;
 static pthread_mutex_t mkl_mutex = PTHREAD_MUTEX_INITIALIZER;
 
-static void *mkl_descriptor(int n)
+/* Committed descriptors are pooled per length: the reference creates and destroys its plans
+ * on every call (FFTW_ESTIMATE plans are cheap, a DFTI commit for 2.88M points is not), so a
+ * destroyed plan parks its descriptor here and the next plan of that length takes it over --
+ * the counterpart of the twiddle cache of the built-in core. */
+struct mkl_idle { int n; void *d; struct mkl_idle *next; };
+static struct mkl_idle *mkl_pool = NULL;
+static pthread_mutex_t mkl_pool_mutex = PTHREAD_MUTEX_INITIALIZER;
+
+static void *mkl_pool_take(int n)
 {
     void *d = NULL;
+    pthread_mutex_lock(&mkl_pool_mutex);
+    for (struct mkl_idle **pp = &mkl_pool; *pp; pp = &(*pp)->next) {
+        if ((*pp)->n == n) {
+            struct mkl_idle *e = *pp;
+            *pp = e->next;
+            d = e->d;
+            free(e);
+            break;
+        }
+    }
+    pthread_mutex_unlock(&mkl_pool_mutex);
+    return d;
+}
+
+static int mkl_pool_park(int n, void *d)
+{
+    struct mkl_idle *e = malloc(sizeof(*e));
+    if (!e) return -1;
+    e->n = n; e->d = d;
+    pthread_mutex_lock(&mkl_pool_mutex);
+    e->next = mkl_pool;
+    mkl_pool = e;
+    pthread_mutex_unlock(&mkl_pool_mutex);
+    return 0;
+}
+
+static void *mkl_descriptor(int n)
+{
+    void *d = mkl_pool_take(n);
+    if (d) return d;
     if (mkl.create(&d, DFTI_REAL_, (long)n) != 0 || !d) return NULL;
     if (mkl.set(d, DFTI_PLACEMENT_, DFTI_NOT_INPLACE_) != 0 ||
         mkl.set(d, DFTI_CONJUGATE_EVEN_STORAGE_, DFTI_COMPLEX_COMPLEX_) != 0 ||
@@ -508,7 +546,7 @@ void fftw_execute(const fftw_plan p)
 void fftw_destroy_plan(fftw_plan p)
 {
     if (!p) return;
-    if (p->mkl) mkl.release(&p->mkl);
+    if (p->mkl && mkl_pool_park(p->n, p->mkl) != 0) mkl.release(&p->mkl);
     free(p->work0); free(p->work1); free(p);
 }
 
