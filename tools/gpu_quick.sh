@@ -1,6 +1,6 @@
 #!/bin/bash
 # Quick GPU visit: selected tests + device-resident sweep with the wave pipeline on and off.
-# usage: tools_gpu_quick.sh TAG [pytest -k expression]
+# usage: tools/gpu_quick.sh TAG [pytest -k expression]
 TAG=${1:-q}; KEXPR=${2:-pipeline}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q -k "$KEXPR" > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$TAG.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit: parity tests, bench, ncu launch list, ncu full capture of the path kernels.
-# usage: tools_gpu_round.sh TAG
+# usage: tools/gpu_round.sh TAG
 TAG=${1:-vX}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi_$TAG.txt 2>&1
