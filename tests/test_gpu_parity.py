@@ -251,6 +251,28 @@ def test_interval_schedule_vs_golden(ac, capi, pid):
             assert lag == c["lag"]
 
 
+@pytest.mark.parametrize("L,where", [(10, "source"), (1000, "sample"), (6000, "source"), (144000, "sample"),
+                                     (144000, "source")])
+def test_nan_input_behaves_like_the_reference(ac, capi, L, where):
+    """A NaN anywhere in the inputs makes every r[i] NaN.  Reference :52-67: the seed r[0] = NaN
+    is never beaten (`fabs(x) > NaN` is false), so idx = 0, lag = 0; the Pearson sums are NaN and
+    the NaN gate (:276) returns -1 with both outputs written.  All three GPU paths must agree."""
+    src, smp = capi.synth_pair(SEED + 21, 0, L)
+    src = src.copy(); smp = smp.copy()
+    (src if where == "source" else smp)[L // 3] = np.nan
+    o = capi.cross_correlation(src, smp)
+    assert (o["ret"], o["lag"]) == (-1, 0) and o["coef"] != o["coef"]
+    ret, lag, coef = ac.cross_correlation(src, smp)
+    assert (ret, lag) == (-1, 0) and coef != coef
+    with ac.Context([0]) as c:
+        for npdt, dt in ((np.float32, ac.F32), (np.float64, ac.F64)):
+            s1 = np.ascontiguousarray(src, npdt); p1 = np.ascontiguousarray(smp, npdt)
+            rec = c.xcorr_batch_records(s1.ctypes.data, p1.ctypes.data, 1, L, dt, ac.HOST)
+            assert int(rec["ret"][0]) == -1 and int(rec["lag"][0]) == 0 and int(rec["raw_index"][0]) == 0
+            assert rec["coef"][0] != rec["coef"][0] and int(rec["success"][0]) == 0
+            assert float(rec["second"][0]) == 0.0                     # NaNs never count (oracle: second = 0)
+
+
 # ------------------------------------------------------------------ interval-schedule residency
 
 def _schedule_case(capi, pid):
