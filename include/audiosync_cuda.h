@@ -156,6 +156,38 @@ int audiosync_cuda_xcorr_batch_device(audiosync_cuda_ctx *ctx, int device,
                                       size_t n_pairs, size_t sample_len, int dtype,
                                       audiosync_cuda_result *d_results, void *stream);
 
+/* ------------------------------------------------------------------------
+ * Session pool: many concurrent audiosync sessions on one device.
+ * Each slot owns device-resident source / sample buffers that grow as audio arrives
+ * (the reference's reader threads append f64le frames, src/ffmpeg_pipe.c:70-81); when
+ * the sessions of a slot range have reached an interval of the schedule
+ * (src/audiosync.c:50-70), ONE batched call evaluates that interval for all of them.
+ * Only new frames ever cross PCIe, and the transform runs at batch throughput.
+ *   dtype F64: slots keep the doubles as sent (results identical to cross_correlation()).
+ *   dtype F32: frames are converted on the device as they arrive (half the memory, the
+ *              fast fp32 staging path; the coefficient then sees fp32-rounded inputs).
+ * ------------------------------------------------------------------------ */
+typedef struct audiosync_cuda_pool audiosync_cuda_pool;
+
+int  audiosync_cuda_pool_create(audiosync_cuda_ctx *ctx, int device, size_t n_slots,
+                                size_t max_sample_len, int dtype, audiosync_cuda_pool **pool);
+void audiosync_cuda_pool_destroy(audiosync_cuda_pool *pool);
+/* Forget a slot's frames (a new session starts in it). */
+int  audiosync_cuda_pool_reset(audiosync_cuda_pool *pool, size_t slot);
+/* Append host doubles to a slot; either count may be 0.  The data is on the device when the
+ * call returns.  -1 if the slot would exceed 2 * max_sample_len / max_sample_len frames. */
+int  audiosync_cuda_pool_append(audiosync_cuda_pool *pool, size_t slot,
+                                const double *source_frames, size_t n_source,
+                                const double *sample_frames, size_t n_sample);
+/* Frames a slot holds so far. */
+int  audiosync_cuda_pool_fill(const audiosync_cuda_pool *pool, size_t slot,
+                              size_t *source_frames, size_t *sample_frames);
+/* cross_correlation(source[0, 2L), sample[0, L)) for slots first_slot .. first_slot+n_slots-1
+ * as one batch; every one of them must hold at least 2L / L frames.  results: host array of
+ * n_slots records.  Returns 0 / -1. */
+int  audiosync_cuda_pool_run(audiosync_cuda_pool *pool, size_t first_slot, size_t n_slots,
+                             size_t sample_len, audiosync_cuda_result *results);
+
 /* Seeded all-integer synthetic pairs written straight into device memory
  * (same generator as oracle/xcorr_oracle.c: bit-identical values).  Pair ids
  * first_pair .. first_pair+n_pairs-1; stream-ordered like the call above. */

@@ -24,7 +24,7 @@ __all__ = [
     "interval_loop", "Context", "RESULT_DTYPE", "MIN_CONFIDENCE", "SAMPLE_RATE",
     "INTERV_SAMPLE", "frames_to_ms", "F32", "F64", "HOST", "DEVICE",
     "PATH_AUTO", "PATH_FFT", "PATH_DIRECT", "EXPORTED_SYMBOLS", "shard_pairs", "gather_results",
-    "cross_correlation_ptr", "RealBuffer", "set_residency", "dropin_stats",
+    "cross_correlation_ptr", "RealBuffer", "set_residency", "dropin_stats", "SessionPool",
 ]
 
 F32, F64 = 0, 1
@@ -49,6 +49,8 @@ EXPORTED_SYMBOLS = [
     "audiosync_cuda_synth_pairs", "audiosync_cuda_synchronize",
     "audiosync_cuda_set_path", "audiosync_cuda_set_wave_pairs", "audiosync_cuda_set_debug",
     "audiosync_cuda_set_pipeline", "audiosync_cuda_set_residency", "audiosync_cuda_dropin_stats",
+    "audiosync_cuda_pool_create", "audiosync_cuda_pool_destroy", "audiosync_cuda_pool_reset",
+    "audiosync_cuda_pool_append", "audiosync_cuda_pool_fill", "audiosync_cuda_pool_run",
     "audiosync_cuda_describe_plan", "audiosync_cuda_launch_count",
     "audiosync_cuda_profile_enable", "audiosync_cuda_profile_reset",
     "audiosync_cuda_profile_read", "audiosync_cuda_last_error", "audiosync_cuda_version",
@@ -115,6 +117,18 @@ def lib() -> C.CDLL:
     L.audiosync_cuda_set_residency.argtypes = [i32]
     L.audiosync_cuda_dropin_stats.restype = None
     L.audiosync_cuda_dropin_stats.argtypes = [C.POINTER(C.c_uint64)] * 3
+    L.audiosync_cuda_pool_create.restype = i32
+    L.audiosync_cuda_pool_create.argtypes = [vp, i32, sz, sz, i32, C.POINTER(vp)]
+    L.audiosync_cuda_pool_destroy.restype = None
+    L.audiosync_cuda_pool_destroy.argtypes = [vp]
+    L.audiosync_cuda_pool_reset.restype = i32
+    L.audiosync_cuda_pool_reset.argtypes = [vp, sz]
+    L.audiosync_cuda_pool_append.restype = i32
+    L.audiosync_cuda_pool_append.argtypes = [vp, sz, vp, sz, vp, sz]
+    L.audiosync_cuda_pool_fill.restype = i32
+    L.audiosync_cuda_pool_fill.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz)]
+    L.audiosync_cuda_pool_run.restype = i32
+    L.audiosync_cuda_pool_run.argtypes = [vp, sz, sz, sz, vp]
     L.audiosync_cuda_set_pipeline.restype = i32
     L.audiosync_cuda_set_pipeline.argtypes = [vp, i32]
     L.audiosync_cuda_set_debug.restype = None
@@ -504,3 +518,63 @@ class Context:
             lib().audiosync_cuda_profile_read(self._h, i, name, 64, C.byref(n), C.byref(ms))
             out[name.value.decode()] = (int(n.value), float(ms.value))
         return out
+
+
+class SessionPool:
+    """``audiosync_cuda_pool``: many concurrent sessions with device-resident, growing buffers.
+
+    Frames are appended as they arrive (host doubles, the reference's f64le wire format); when a
+    range of slots has reached an interval of the schedule, ``run`` evaluates that interval for all
+    of them as one batch and returns the ``RESULT_DTYPE`` records.
+    """
+
+    def __init__(self, ctx: "Context", device: int, n_slots: int, max_sample_len: int, dtype: int = F64):
+        self._ctx = ctx                       # keeps the context alive
+        self._h = C.c_void_p()
+        self.n_slots, self.max_sample_len, self.dtype = n_slots, max_sample_len, dtype
+        rc = lib().audiosync_cuda_pool_create(ctx._h, device, n_slots, max_sample_len, dtype, C.byref(self._h))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise AudiosyncCudaError("pool_create failed: " + last_error())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().audiosync_cuda_pool_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self, slot: int):
+        if lib().audiosync_cuda_pool_reset(self._h, slot) != 0:
+            raise AudiosyncCudaError("pool_reset failed: " + last_error())
+
+    def append(self, slot: int, source_frames=None, sample_frames=None):
+        s = np.ascontiguousarray(source_frames if source_frames is not None else [], np.float64)
+        m = np.ascontiguousarray(sample_frames if sample_frames is not None else [], np.float64)
+        rc = lib().audiosync_cuda_pool_append(self._h, slot, s.ctypes.data if s.size else None, s.size,
+                                              m.ctypes.data if m.size else None, m.size)
+        if rc != 0:
+            raise AudiosyncCudaError("pool_append failed: " + last_error())
+
+    def fill(self, slot: int):
+        a, b = C.c_size_t(), C.c_size_t()
+        if lib().audiosync_cuda_pool_fill(self._h, slot, C.byref(a), C.byref(b)) != 0:
+            raise AudiosyncCudaError("pool_fill: bad slot")
+        return int(a.value), int(b.value)
+
+    def run(self, first_slot: int, n_slots: int, sample_len: int) -> np.ndarray:
+        res = np.zeros(n_slots, RESULT_DTYPE)
+        rc = lib().audiosync_cuda_pool_run(self._h, first_slot, n_slots, sample_len, res.ctypes.data)
+        if rc != 0:
+            raise AudiosyncCudaError("pool_run failed: " + last_error())
+        return res

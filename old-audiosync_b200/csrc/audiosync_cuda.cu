@@ -95,8 +95,9 @@ struct FftPlan {
     std::function<int(audiosync_cuda_ctx*, DeviceState&, const void*, const void*, int, size_t,
                       audiosync_cuda_result*, int, cudaStream_t)> run_pipelined;
     // enqueues the transform kernels for `pairs` pairs (planes/r in ws)
-    std::function<int(audiosync_cuda_ctx*, DeviceState&, const void*, const void*, int, void*,
-                      PairPeak*, int, cudaStream_t)> run_wave;
+    // (src, smp, dtype, src_pitch, smp_pitch [elements between pairs], workspace, peaks, pairs, stream)
+    std::function<int(audiosync_cuda_ctx*, DeviceState&, const void*, const void*, int, long long, long long,
+                      void*, PairPeak*, int, cudaStream_t)> run_wave;
     ~FftPlan() {
         col_tw.release(); col_tc.release(); row_tw.release(); row_rev.release(); m_lo.release(); m_hi.release();
         wm.release(); wn.release(); sched.release();
@@ -140,8 +141,8 @@ static int prepare_kernel(size_t smem) {
 
 template <class P>
 static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d,
-                           const void* src, const void* smp, int dtype, void* ws,
-                           PairPeak* peaks, int pairs, cudaStream_t st) {
+                           const void* src, const void* smp, int dtype, long long src_pitch,
+                           long long smp_pitch, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
     using Col = typename P::Col;
     using Row = typename P::Row;
     constexpr int M1 = Col::n, M2 = Row::n;
@@ -155,7 +156,7 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
     const dim3 grid_a(M2 / COL_T, 2, pairs);
     auto col_fwd = [&](auto KK, const auto* s_in, const auto* m_in) -> int {
         using K = decltype(KK);
-        typename K::Params p{s_in, m_in, planes, peaks, col_tw, col_tc, m_lo, m_hi, P::L};
+        typename K::Params p{s_in, m_in, planes, peaks, col_tw, col_tc, m_lo, m_hi, P::L, src_pitch, smp_pitch};
         return launch(ctx, d, KC_COL_FWD, st, [&] {
             fft_kernel_entry<K><<<grid_a, K::THREADS, K::SMEM, st>>>(p);
         });
@@ -164,7 +165,8 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
         // cp.async staging needs 16-byte aligned rows: every pair / row offset is a multiple
         // of 16 bytes, so only the base pointers decide.
         static const bool no_async = getenv("AUDIOSYNC_CUDA_NOASYNC") != nullptr;   // experiment knob
-        const bool aligned = !no_async && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(smp)) & 15u) == 0;
+        const bool aligned = !no_async && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(smp)) & 15u) == 0 &&
+                             src_pitch % 4 == 0 && smp_pitch % 4 == 0;
         const float* s_in = static_cast<const float*>(src);
         const float* m_in = static_cast<const float*>(smp);
         const int rc = aligned ? col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, float, true>{}, s_in, m_in)
@@ -311,8 +313,9 @@ static int build_static_plan(FftPlan* plan) {
         prepare_kernel<ColInvKernel<Col, Row::n, P::NT_COL>>(ColInvKernel<Col, Row::n, P::NT_COL>::SMEM) != 0)
         return -1;
     plan->run_wave = [plan](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
-                            int dtype, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
-        return run_static_wave<P>(plan, ctx, d, src, smp, dtype, ws, peaks, pairs, st);
+                            int dtype, long long sp, long long mp, void* ws, PairPeak* peaks, int pairs,
+                            cudaStream_t st) {
+        return run_static_wave<P>(plan, ctx, d, src, smp, dtype, sp, mp, ws, peaks, pairs, st);
     };
     if constexpr (P::NT_COL == P::NT_ROW && P::PIPELINE) {
         plan->shape = pipe_shape(Col::n, Row::n, P::L, P::NT_COL);
@@ -335,11 +338,12 @@ static int build_static_plan(FftPlan* plan) {
 
 template <typename InT>
 static int run_small_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d, const void* src,
-                          const void* smp, PairPeak* peaks, int pairs, cudaStream_t st) {
+                          const void* smp, long long sp, long long mp, PairPeak* peaks, int pairs,
+                          cudaStream_t st) {
     using K = SmallXcorrKernel<InT>;
     typename K::Params p{static_cast<const InT*>(src), static_cast<const InT*>(smp), peaks,
                          static_cast<const cplx*>(plan->wm.p), static_cast<const cplx*>(plan->wn.p),
-                         plan->small};
+                         plan->small, sp, mp};
     const size_t smem = K::smem_bytes(plan->small.M);
     const dim3 grid(1, 1, pairs);
     return launch(ctx, d, KC_SMALL_FFT, st, [&] {
@@ -367,22 +371,24 @@ static int build_small_plan(FftPlan* plan, long long L) {
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     }
     plan->run_wave = [plan](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
-                            int dtype, void*, PairPeak* peaks, int pairs, cudaStream_t st) {
-        return dtype == AUDIOSYNC_CUDA_F32 ? run_small_wave<float>(plan, ctx, d, src, smp, peaks, pairs, st)
-                                           : run_small_wave<double>(plan, ctx, d, src, smp, peaks, pairs, st);
+                            int dtype, long long sp, long long mp, void*, PairPeak* peaks, int pairs,
+                            cudaStream_t st) {
+        return dtype == AUDIOSYNC_CUDA_F32 ? run_small_wave<float>(plan, ctx, d, src, smp, sp, mp, peaks, pairs, st)
+                                           : run_small_wave<double>(plan, ctx, d, src, smp, sp, mp, peaks, pairs, st);
     };
     return 0;
 }
 
 template <typename InT>
 static int run_direct_wave(long long L, audiosync_cuda_ctx* ctx, DeviceState& d, const void* src,
-                           const void* smp, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
+                           const void* smp, long long sp, long long mp, void* ws, PairPeak* peaks, int pairs,
+                           cudaStream_t st) {
     const long long N = 2 * L;
     double* r = static_cast<double*>(ws);
     const dim3 grid((unsigned)((N + DIRECT_TILE - 1) / DIRECT_TILE), pairs);
     if (launch(ctx, d, KC_DIRECT, st, [&] {
             direct_corr_kernel<InT><<<grid, DIRECT_TILE, 0, st>>>(static_cast<const InT*>(src),
-                                                                  static_cast<const InT*>(smp), r, L);
+                                                                  static_cast<const InT*>(smp), r, L, sp, mp);
         }) != 0) return -1;
     return launch(ctx, d, KC_ARGMAX_F64, st, [&] {
         argmax_f64_kernel<<<pairs, 1024, 0, st>>>(r, N, peaks);
@@ -395,9 +401,10 @@ static int build_direct_plan(FftPlan* plan, long long L) {
     plan->ws_bytes_per_pair = (size_t)2 * L * sizeof(double);
     plan->desc = "direct L=" + std::to_string(L) + " time-domain O(L^2) fp64";
     plan->run_wave = [L](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
-                         int dtype, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
-        return dtype == AUDIOSYNC_CUDA_F32 ? run_direct_wave<float>(L, ctx, d, src, smp, ws, peaks, pairs, st)
-                                           : run_direct_wave<double>(L, ctx, d, src, smp, ws, peaks, pairs, st);
+                         int dtype, long long sp, long long mp, void* ws, PairPeak* peaks, int pairs,
+                         cudaStream_t st) {
+        return dtype == AUDIOSYNC_CUDA_F32 ? run_direct_wave<float>(L, ctx, d, src, smp, sp, mp, ws, peaks, pairs, st)
+                                           : run_direct_wave<double>(L, ctx, d, src, smp, sp, mp, ws, peaks, pairs, st);
     };
     return 0;
 }
@@ -453,10 +460,14 @@ static int ensure_tickets(DeviceState& d, size_t n) {
 }
 
 // Enqueue the whole path for device-resident pairs on `st` (no sync).
+// src_pitch / smp_pitch: elements between consecutive pairs (0 = packed [pair][2L] / [pair][L]).
 static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
                          size_t n_pairs, long long L, int dtype, audiosync_cuda_result* d_results,
-                         cudaStream_t st) {
+                         cudaStream_t st, long long src_pitch = 0, long long smp_pitch = 0) {
     if (n_pairs == 0) return 0;
+    if (src_pitch == 0) src_pitch = 2 * L;
+    if (smp_pitch == 0) smp_pitch = L;
+    const bool packed = src_pitch == 2 * L && smp_pitch == L;
     if (L <= 0 || L > (1LL << 30)) { set_last_error("unsupported sample_len %lld", L); return -1; }
     ASC_CUDA_OK(cudaSetDevice(d.device));
     FftPlan* plan = get_plan(ctx, d, L);
@@ -467,7 +478,7 @@ static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, const void* sr
     wave = std::min(wave, 65535);
     // More than one wave of a static plan: the wave pipeline kernel (cp.async staging of fp32
     // tiles needs 16-byte aligned inputs; anything else takes the launch-per-stage path below).
-    if (ctx->pipeline && plan->run_pipelined && n_pairs > (size_t)wave &&
+    if (ctx->pipeline && packed && plan->run_pipelined && n_pairs > (size_t)wave &&
         (dtype == AUDIOSYNC_CUDA_F64 ||
          ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(smp)) & 15u) == 0))
         return plan->run_pipelined(ctx, d, src, smp, dtype, n_pairs, d_results, wave, st);
@@ -481,21 +492,21 @@ static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, const void* sr
     unsigned int* tickets = static_cast<unsigned int*>(d.tickets.p);
     for (size_t p0 = 0; p0 < n_pairs; p0 += (size_t)wave) {
         const int pairs = (int)std::min<size_t>((size_t)wave, n_pairs - p0);
-        const char* s = static_cast<const char*>(src) + p0 * (size_t)(2 * L) * esz;
-        const char* m = static_cast<const char*>(smp) + p0 * (size_t)L * esz;
-        if (plan->run_wave(ctx, d, s, m, dtype, d.ws.p, peaks, pairs, st) != 0) return -1;
+        const char* s = static_cast<const char*>(src) + p0 * (size_t)src_pitch * esz;
+        const char* m = static_cast<const char*>(smp) + p0 * (size_t)smp_pitch * esz;
+        if (plan->run_wave(ctx, d, s, m, dtype, src_pitch, smp_pitch, d.ws.p, peaks, pairs, st) != 0) return -1;
         const dim3 grid(n_chunks, pairs);
         int rc;
         if (dtype == AUDIOSYNC_CUDA_F32) {
             rc = launch(ctx, d, KC_PEARSON, st, [&] {
                 pearson_kernel<float><<<grid, PEARSON_THREADS, 0, st>>>(
-                    reinterpret_cast<const float*>(s), reinterpret_cast<const float*>(m), 2 * L, L, L,
+                    reinterpret_cast<const float*>(s), reinterpret_cast<const float*>(m), src_pitch, smp_pitch, L,
                     peaks, 0, partials, tickets, n_chunks, d_results + p0);
             });
         } else {
             rc = launch(ctx, d, KC_PEARSON, st, [&] {
                 pearson_kernel<double><<<grid, PEARSON_THREADS, 0, st>>>(
-                    reinterpret_cast<const double*>(s), reinterpret_cast<const double*>(m), 2 * L, L, L,
+                    reinterpret_cast<const double*>(s), reinterpret_cast<const double*>(m), src_pitch, smp_pitch, L,
                     peaks, 0, partials, tickets, n_chunks, d_results + p0);
             });
         }
@@ -894,6 +905,152 @@ int audiosync_cuda_xcorr_batch(audiosync_cuda_ctx* ctx, const void* sources, con
         if (rets) rets[i] = res[i].ret;
         if (peaks) peaks[i] = res[i].peak;
     }
+    return 0;
+}
+
+
+// ------------------------------------------------------------------ session pool
+}  // extern "C"
+#pragma GCC visibility pop
+
+struct audiosync_cuda_pool {
+    audiosync_cuda_ctx* ctx = nullptr;
+    asc::DeviceState* dev = nullptr;
+    size_t n_slots = 0, max_len = 0;
+    long long src_pitch = 0, smp_pitch = 0;      // elements; multiples of 4 (16-byte rows for cp.async)
+    int dtype = AUDIOSYNC_CUDA_F64;
+    asc::DevBuf src, smp, stage;
+    std::vector<size_t> have_src, have_smp;
+};
+
+namespace asc {
+static int pool_upload(audiosync_cuda_pool* pool, DevBuf& slab, size_t elem_off, const double* host, size_t n) {
+    DeviceState& d = *pool->dev;
+    if (n == 0) return 0;
+    if (pool->dtype == AUDIOSYNC_CUDA_F64) {
+        ASC_CUDA_OK(cudaMemcpyAsync(static_cast<double*>(slab.p) + elem_off, host, sizeof(double) * n,
+                                    cudaMemcpyHostToDevice, d.copy_stream));
+        return 0;
+    }
+    // fp32 slots: stage the doubles, convert on the device, in pieces
+    const size_t piece = 1u << 20;
+    if (pool->stage.ensure(sizeof(double) * std::min(piece, n)) != 0) return -1;
+    for (size_t o = 0; o < n; o += piece) {
+        const size_t m = std::min(piece, n - o);
+        ASC_CUDA_OK(cudaMemcpyAsync(pool->stage.p, host + o, sizeof(double) * m, cudaMemcpyHostToDevice, d.copy_stream));
+        const unsigned blocks = (unsigned)std::min<size_t>((m + 255) / 256, 2048);
+        if (launch(pool->ctx, d, KC_SYNTH, d.copy_stream, [&] {
+                convert_f64_to_f32_kernel<<<blocks, 256, 0, d.copy_stream>>>(
+                    static_cast<const double*>(pool->stage.p), static_cast<float*>(slab.p) + elem_off + o, (long long)m);
+            }) != 0) return -1;
+    }
+    return 0;
+}
+}  // namespace asc
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int audiosync_cuda_pool_create(audiosync_cuda_ctx* ctx, int device, size_t n_slots, size_t max_sample_len,
+                               int dtype, audiosync_cuda_pool** out) {
+    if (!ctx || !out || n_slots == 0 || max_sample_len == 0) { set_last_error("pool_create: invalid argument"); return -1; }
+    if (dtype != AUDIOSYNC_CUDA_F32 && dtype != AUDIOSYNC_CUDA_F64) { set_last_error("bad dtype"); return -1; }
+    *out = nullptr;
+    DeviceState* d = ctx->find(device);
+    if (!d) { set_last_error("device %d is not part of this context", device); return -1; }
+    ASC_CUDA_OK(cudaSetDevice(d->device));
+    auto* pool = new audiosync_cuda_pool();
+    pool->ctx = ctx; pool->dev = d; pool->n_slots = n_slots; pool->max_len = max_sample_len; pool->dtype = dtype;
+    pool->smp_pitch = (long long)((max_sample_len + 3) / 4 * 4);
+    pool->src_pitch = 2 * pool->smp_pitch;
+    const size_t esz = dtype == AUDIOSYNC_CUDA_F32 ? 4 : 8;
+    if (pool->src.ensure(esz * (size_t)pool->src_pitch * n_slots) != 0 ||
+        pool->smp.ensure(esz * (size_t)pool->smp_pitch * n_slots) != 0) {
+        audiosync_cuda_pool_destroy(pool);
+        return -1;
+    }
+    pool->have_src.assign(n_slots, 0);
+    pool->have_smp.assign(n_slots, 0);
+    *out = pool;
+    return 0;
+}
+
+void audiosync_cuda_pool_destroy(audiosync_cuda_pool* pool) {
+    if (!pool) return;
+    if (pool->dev && pool->dev->device >= 0) { cudaSetDevice(pool->dev->device); cudaDeviceSynchronize(); }
+    pool->src.release(); pool->smp.release(); pool->stage.release();
+    delete pool;
+}
+
+int audiosync_cuda_pool_reset(audiosync_cuda_pool* pool, size_t slot) {
+    if (!pool || slot >= pool->n_slots) { set_last_error("pool_reset: bad slot"); return -1; }
+    std::lock_guard<std::mutex> lk(pool->ctx->mu);
+    pool->have_src[slot] = 0;
+    pool->have_smp[slot] = 0;
+    return 0;
+}
+
+int audiosync_cuda_pool_fill(const audiosync_cuda_pool* pool, size_t slot, size_t* source_frames, size_t* sample_frames) {
+    if (!pool || slot >= pool->n_slots) return -1;
+    if (source_frames) *source_frames = pool->have_src[slot];
+    if (sample_frames) *sample_frames = pool->have_smp[slot];
+    return 0;
+}
+
+int audiosync_cuda_pool_append(audiosync_cuda_pool* pool, size_t slot, const double* source_frames, size_t n_source,
+                               const double* sample_frames, size_t n_sample) {
+    if (!pool || slot >= pool->n_slots || (n_source && !source_frames) || (n_sample && !sample_frames)) {
+        set_last_error("pool_append: invalid argument");
+        return -1;
+    }
+    std::lock_guard<std::mutex> lk(pool->ctx->mu);
+    if (pool->have_src[slot] + n_source > 2 * pool->max_len || pool->have_smp[slot] + n_sample > pool->max_len) {
+        set_last_error("pool_append: slot %zu would exceed its capacity (%zu source / %zu sample frames)", slot,
+                       2 * pool->max_len, pool->max_len);
+        return -1;
+    }
+    DeviceState& d = *pool->dev;
+    ASC_CUDA_OK(cudaSetDevice(d.device));
+    if (pool_upload(pool, pool->src, slot * (size_t)pool->src_pitch + pool->have_src[slot], source_frames, n_source) != 0 ||
+        pool_upload(pool, pool->smp, slot * (size_t)pool->smp_pitch + pool->have_smp[slot], sample_frames, n_sample) != 0)
+        return -1;
+    ASC_CUDA_OK(cudaStreamSynchronize(d.copy_stream));      // the frames are resident when this returns
+    pool->have_src[slot] += n_source;
+    pool->have_smp[slot] += n_sample;
+    return 0;
+}
+
+int audiosync_cuda_pool_run(audiosync_cuda_pool* pool, size_t first_slot, size_t n_slots, size_t sample_len,
+                            audiosync_cuda_result* results) {
+    if (!pool || !results || sample_len == 0 || n_slots == 0 || first_slot + n_slots > pool->n_slots ||
+        sample_len > pool->max_len) {
+        set_last_error("pool_run: invalid argument");
+        return -1;
+    }
+    std::lock_guard<std::mutex> lk(pool->ctx->mu);
+    for (size_t s = first_slot; s < first_slot + n_slots; s++) {
+        if (pool->have_src[s] < 2 * sample_len || pool->have_smp[s] < sample_len) {
+            set_last_error("pool_run: slot %zu holds %zu / %zu frames, interval %zu needs %zu / %zu", s,
+                           pool->have_src[s], pool->have_smp[s], sample_len, 2 * sample_len, sample_len);
+            return -1;
+        }
+    }
+    DeviceState& d = *pool->dev;
+    ASC_CUDA_OK(cudaSetDevice(d.device));
+    if (d.results.ensure(sizeof(audiosync_cuda_result) * n_slots) != 0 ||
+        d.h_results.ensure(sizeof(audiosync_cuda_result) * n_slots) != 0)
+        return -1;
+    const size_t esz = pool->dtype == AUDIOSYNC_CUDA_F32 ? 4 : 8;
+    const char* s0 = static_cast<const char*>(pool->src.p) + first_slot * (size_t)pool->src_pitch * esz;
+    const char* m0 = static_cast<const char*>(pool->smp.p) + first_slot * (size_t)pool->smp_pitch * esz;
+    auto* d_res = static_cast<audiosync_cuda_result*>(d.results.p);
+    if (enqueue_batch(pool->ctx, d, s0, m0, n_slots, (long long)sample_len, pool->dtype, d_res, d.stream,
+                      pool->src_pitch, pool->smp_pitch) != 0)
+        return -1;
+    ASC_CUDA_OK(cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result) * n_slots,
+                                cudaMemcpyDeviceToHost, d.stream));
+    ASC_CUDA_OK(cudaStreamSynchronize(d.stream));
+    memcpy(results, d.h_results.p, sizeof(audiosync_cuda_result) * n_slots);
     return 0;
 }
 

@@ -121,6 +121,8 @@ struct ColFwdKernel {
         const cplx* m_lo;        // W_M two-level tables
         const cplx* m_hi;
         long long L;             // sample_len == M = M1 * M2
+        long long src_pitch;     // elements between consecutive pairs' sources / samples;
+        long long smp_pitch;     // 0 = packed ([pair][2L] and [pair][L])
     };
 
     // grid = (M2 / 16, 2, pairs)
@@ -130,7 +132,8 @@ struct ColFwdKernel {
         const int sig = ex.by();
         const long long pair = ex.bz();
         const long long M = p.L;
-        const InT* __restrict__ x = sig == 0 ? p.sources + pair * 2 * M : p.samples + pair * M;
+        const InT* __restrict__ x = sig == 0 ? p.sources + pair * (p.src_pitch ? p.src_pitch : 2 * M)
+                                             : p.samples + pair * (p.smp_pitch ? p.smp_pitch : M);
         // number of valid packed points: source M, sample M/2 (upper half is the zero pad)
         const long long nvalid = sig == 0 ? M : M / 2;
         cplx* __restrict__ out = p.planes + (pair * 2 + sig) * M;

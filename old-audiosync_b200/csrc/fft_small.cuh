@@ -46,6 +46,8 @@ struct SmallXcorrKernel {
         const cplx* wm;       // exp(-2*pi*i*t/M),  t < M
         const cplx* wn;       // exp(-2*pi*i*t/2M), t < M
         SmallPlan plan;
+        long long src_pitch;  // elements between consecutive pairs; 0 = packed (2M / M)
+        long long smp_pitch;
     };
     // two rows of M points + 512 bytes of reduction scratch (phase_argmax needs 392)
     static size_t smem_bytes(int M) { return (size_t)2 * M * sizeof(cplx) + 512; }
@@ -74,8 +76,8 @@ struct SmallXcorrKernel {
                     static_for<0, R>([&](auto Q) {
                         constexpr int q = decltype(Q)::value;
                         const long long n = i0 + q * S;
-                        if (rr == 0) v[q] = load_packed<InT>(p.sources + pair * 2 * M, n);
-                        else v[q] = n < M / 2 ? load_packed<InT>(p.samples + pair * M, n)
+                        if (rr == 0) v[q] = load_packed<InT>(p.sources + pair * (p.src_pitch ? p.src_pitch : 2 * M), n);
+                        else v[q] = n < M / 2 ? load_packed<InT>(p.samples + pair * (p.smp_pitch ? p.smp_pitch : M), n)
                                               : cmake(0.f, 0.f);
                     });
                 } else {

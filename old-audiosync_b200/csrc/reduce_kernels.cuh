@@ -40,6 +40,15 @@ synth_kernel(T* __restrict__ sources, T* __restrict__ samples, uint64_t seed,
     }
 }
 
+// f64le frames -> fp32 slot of a session pool (the wire-format conversion, on arrival).
+__global__ void __launch_bounds__(256)
+convert_f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = (float)in[i];
+}
+
 // ---------------------------------------------------------------------------
 // Direct path: r[j] = N * sum_{n<L} source[(n + j) mod N] * sample[n], the
 // quantity c2r(r2c(source) * conj(r2c(pad(sample)))) equals (reference
@@ -51,13 +60,13 @@ constexpr int DIRECT_TILE = 256;
 template <typename T>
 __global__ void __launch_bounds__(DIRECT_TILE)
 direct_corr_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
-                   double* __restrict__ r_out, long long L)
+                   double* __restrict__ r_out, long long L, long long src_pitch, long long smp_pitch)
 {
     __shared__ double s_smp[DIRECT_TILE];
     __shared__ double s_src[2 * DIRECT_TILE];
     const long long N = 2 * L;
-    const T* src = sources + (size_t)blockIdx.y * (size_t)N;
-    const T* smp = samples + (size_t)blockIdx.y * (size_t)L;
+    const T* src = sources + (size_t)blockIdx.y * (size_t)src_pitch;
+    const T* smp = samples + (size_t)blockIdx.y * (size_t)smp_pitch;
     const long long j0 = (long long)blockIdx.x * DIRECT_TILE;
     const int t = threadIdx.x;
     double acc = 0.0;

@@ -404,6 +404,56 @@ def test_torch_zero_copy_batch(ac, ctx, capi):
         ctx.xcorr_batch_torch(src.half(), smp.half())
 
 
+# ------------------------------------------------------------------ session pool
+
+def test_session_pool_matches_dropin_over_the_schedule(ac, capi):
+    """SURVEY 8f rank 1, second half: five concurrent sessions whose audio arrives in pieces;
+    at every interval of the schedule (src/audiosync.c:50-70) ONE batched call evaluates all of
+    them from their device-resident buffers.  F64 slots must return exactly what
+    cross_correlation() returns on the same prefixes; each frame crosses PCIe once."""
+    Ls = ac.INTERV_SAMPLE[:4]                      # 144,000 .. 720,000: all four kernel plans
+    n, Lmax = 5, Ls[-1]
+    data = [capi.synth_pair(SEED + 31, pid, Lmax) for pid in range(n)]
+    with ac.Context([0]) as c, ac.SessionPool(c, 0, n + 1, Lmax, ac.F64) as pool:
+        prev = 0
+        for L in Ls:
+            for slot, (src, smp) in enumerate(data):
+                # ragged arrival: the source in two pieces, the sample in one
+                mid = 2 * prev + (2 * L - 2 * prev) // 3
+                pool.append(slot + 1, src[2 * prev:mid], None)
+                pool.append(slot + 1, src[mid:2 * L], smp[prev:L])
+                assert pool.fill(slot + 1) == (2 * L, L)
+            rec = pool.run(1, n, L)
+            for slot, (src, smp) in enumerate(data):
+                ret, lag, coef = ac.cross_correlation(src[:2 * L], smp[:L])
+                assert (int(rec["ret"][slot]), int(rec["lag"][slot])) == (ret, lag)
+                assert float(rec["coef"][slot]) == coef                  # same kernels, same doubles
+                o = capi.cross_correlation(src[:2 * L], smp[:L])
+                assert lag == o["lag"] and close(coef, o["coef"]) and close(float(rec["peak"][slot]), o["peak"])
+            prev = L
+        # an interval the slots have not reached yet, an empty slot, an overflow
+        with pytest.raises(ac.AudiosyncCudaError):
+            pool.run(0, 2, Ls[0])                                         # slot 0 is empty
+        with pytest.raises(ac.AudiosyncCudaError):
+            pool.append(1, np.zeros(8), None)                             # slot 1 is full
+        pool.reset(1)
+        assert pool.fill(1) == (0, 0)
+
+
+def test_session_pool_fp32_slots(ac, capi):
+    """F32 slots convert the f64le frames on arrival: same lag, coefficient within tolerance."""
+    L, n = 144000, 3
+    data = [capi.synth_pair(SEED + 32, pid, L) for pid in range(n)]
+    with ac.Context([0]) as c, ac.SessionPool(c, 0, n, L, ac.F32) as pool:
+        for slot, (src, smp) in enumerate(data):
+            pool.append(slot, src, smp)
+        rec = pool.run(0, n, L)
+    for slot, (src, smp) in enumerate(data):
+        o = capi.cross_correlation(src, smp)
+        assert int(rec["lag"][slot]) == o["lag"] == capi.synth_true_lag(SEED + 32, slot, L)
+        assert int(rec["ret"][slot]) == o["ret"] and close(float(rec["coef"][slot]), o["coef"])
+
+
 # ------------------------------------------------------------------ host batch API
 
 @pytest.mark.parametrize("npdt", [np.float32, np.float64])
