@@ -40,6 +40,14 @@ namespace asc {
 constexpr int SPLIT_UNROLL = ASC_SPLIT_UNROLL;
 
 constexpr int COL_T = 16;          // columns per tile: 16 * 8 B = one 128-byte line
+
+// Resident CTAs per SM a transform kernel is built for (its register budget follows from it):
+// as many as its tile allows in the SM's 228 KB of shared memory (1 KB per CTA is reserved),
+// at most 3 -- 960 threads of 64 registers.
+constexpr int ctas_per_sm(size_t smem) {
+    const int by_smem = (int)((228u * 1024u) / (smem + 1024u));
+    return by_smem >= 3 ? 3 : (by_smem >= 1 ? by_smem : 1);
+}
 constexpr unsigned TW2_BITS = 10;  // two-level twiddle tables: a = hi * 1024 + lo
 constexpr unsigned TW2_MASK = (1u << TW2_BITS) - 1u;
 
@@ -100,12 +108,12 @@ struct ArgmaxAcc {
 // unaligned pointers) the first pass loads, converts and packs through registers.
 template <class RL, int M2_, int NT, typename InT, bool ASYNC>
 struct ColFwdKernel {
-    static constexpr int MIN_CTAS = 3;
     static constexpr int M1 = RL::n;
     static constexpr int M2 = M2_;                  // row length (compile time: index products fold)
     static constexpr int P = RL::count;
     static constexpr int THREADS = NT;
     static constexpr size_t SMEM = (size_t)M1 * COL_T * sizeof(cplx);
+    static constexpr int MIN_CTAS = ctas_per_sm(SMEM);
     static_assert(NT % COL_T == 0, "a thread must keep its column across items");
     static_assert(P >= 2, "column plans need at least two passes");
     static_assert(!ASYNC || sizeof(InT) == 4, "async staging copies packed fp32 pairs verbatim");
@@ -220,10 +228,15 @@ struct ColFwdKernel {
                     // per-thread constant, the first is tc[f0][c] * W_M^(c0*f0).
                     constexpr int Wt = RL::weight(ps);
                     const unsigned n2 = (unsigned)(c0 + c);
+                    // Wide last radix (R > 8): only the power-of-two multiples are held; the
+                    // others are formed as products where they are used (as in pass_twiddles),
+                    // so the per-thread constants do not crowd out the butterfly's registers.
+                    constexpr bool lean_g = R > 8;
                     cplx g[R];
                     static_for<1, R>([&](auto K) {
                         constexpr int k = decltype(K)::value;
-                        g[k] = tw2(p.m_lo, p.m_hi, n2 * (unsigned)(Wt * k));
+                        if constexpr (!lean_g || (k & (k - 1)) == 0)
+                            g[k] = tw2(p.m_lo, p.m_hi, n2 * (unsigned)(Wt * k));
                     });
                     // The twiddle loads of a chunk of items are issued together ahead of the
                     // butterflies (three dependent table reads per item would otherwise be exposed
@@ -256,7 +269,23 @@ struct ColFwdKernel {
                                 o[0] = cmul(v[0], t0);
                                 static_for<1, R>([&](auto K) {
                                     constexpr int k = decltype(K)::value;
-                                    o[(size_t)k * Wt * M2] = cmul(v[k], cmul(t0, g[k]));
+                                    cplx gk;
+                                    if constexpr (!lean_g || (k & (k - 1)) == 0) {
+                                        gk = g[k];
+                                    } else {
+                                        constexpr int hb = (k >= 16) ? 16 : (k >= 8) ? 8 : (k >= 4) ? 4 : 2;
+                                        constexpr int rest = k - hb;
+                                        if constexpr ((rest & (rest - 1)) == 0) {
+                                            gk = cmul(g[hb], g[rest]);
+                                        } else {
+                                            constexpr int hb2 = (rest >= 8) ? 8 : (rest >= 4) ? 4 : 2;
+                                            constexpr int rest2 = rest - hb2;
+                                            static_assert(R <= 24, "k < 24: at most four one-bits, and then the last two are 2 + 1");
+                                            if constexpr ((rest2 & (rest2 - 1)) == 0) gk = cmul(g[hb], cmul(g[hb2], g[rest2]));
+                                            else gk = cmul(cmul(g[hb], g[hb2]), cmul(g[rest2 & ~1], g[1]));
+                                        }
+                                    }
+                                    o[(size_t)k * Wt * M2] = cmul(v[k], cmul(t0, gk));
                                 });
                             }
                         });
@@ -270,12 +299,12 @@ struct ColFwdKernel {
 // --------------------------------------------------------------------- K_C
 template <class RL, int M2_, int NT>
 struct ColInvKernel {
-    static constexpr int MIN_CTAS = 3;
     static constexpr int M1 = RL::n;
     static constexpr int M2 = M2_;
     static constexpr int P = RL::count;
     static constexpr int THREADS = NT;
     static constexpr size_t SMEM = (size_t)M1 * COL_T * sizeof(cplx);
+    static constexpr int MIN_CTAS = ctas_per_sm(SMEM);
     static_assert(NT % COL_T == 0, "a thread must keep its column across items");
     static_assert(NT % 32 == 0, "the argmax epilogue votes per warp");
     static_assert(P >= 2, "column plans need at least two passes");
@@ -476,13 +505,13 @@ ASC_HD void split_mul_merge_w2(cplx a, cplx b, cplx c, cplx d, cplx w2, cplx& qk
 
 template <class RL, int M1_, int NT>
 struct RowFusedKernel {
-    static constexpr int MIN_CTAS = 3;
     static constexpr int M2 = RL::n;
     static constexpr int M1 = M1_;
     static constexpr int P = RL::count;
     static constexpr int THREADS = NT;
     static constexpr int RP = M2;   // row pitch in shared memory
     static constexpr size_t SMEM = (size_t)4 * RP * sizeof(cplx);
+    static constexpr int MIN_CTAS = ctas_per_sm(SMEM);
     static constexpr int R0 = RL::r(0);
     static constexpr int S0 = RL::stride(0);
     static_assert(M2 % 2 == 0, "row length must be even (16-byte chunks, bulk store size)");
