@@ -435,10 +435,12 @@ static FftPlan* get_plan(audiosync_cuda_ctx* ctx, DeviceState& d, long long L) {
 static int default_wave_pairs(const FftPlan* plan, size_t n_pairs) {
     long long w;
     if (plan->kind == PATH_STATIC_FFT) {
-        // Enough pairs per launch that the partial last wave of CTAs is a few percent of the
-        // launch (64 pairs at L = 1.44M: ~43 waves of the 3-CTA/SM kernels); the workspace
-        // stays at ~1.5 GB whatever the length.
-        w = (64LL * 1440000) / plan->L;
+        // Enough pairs per launch that the partial last wave of CTAs and the serialised
+        // start/drain of each launch are ~1 % of it (256 pairs at L = 1.44M: ~170 waves of the
+        // 3-CTA/SM kernels; measured in the 4,096-pair run: 64 -> 39.0k, 128 -> 39.5k,
+        // 256 -> 39.9k pairs/s); the workspace stays at <= 5.9 GB whatever the length and
+        // is only as large as the batch needs.
+        w = (256LL * 1440000) / plan->L;
         w = std::max(16LL, std::min(1024LL, w));
     } else if (plan->kind == PATH_SMALL_FFT) {
         w = 16384;

@@ -183,6 +183,62 @@ ASC_HD void bulk_store_commit_and_drain() {
 #endif
 }
 
+// Global -> shared bulk copies of the TMA unit, completion counted in bytes on an mbarrier
+// (8 bytes of shared memory).  One thread: init, expect the byte total, issue the copies,
+// wait, invalidate; the CTA barrier that follows publishes the data to the other threads.
+// The copies do not pass through the LSU pipe (LDGSTS costs 4 issue + 4 shared-memory
+// cycles per 512 bytes there).  Host versions (CPU emulator): plain copies.
+ASC_HD void mbar_init(void* mbar, unsigned count) {
+#if defined(__CUDA_ARCH__)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the async proxy sees the init
+#else
+    (void)mbar; (void)count;
+#endif
+}
+ASC_HD void mbar_expect_tx(void* mbar, unsigned bytes) {
+#if defined(__CUDA_ARCH__)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+#else
+    (void)mbar; (void)bytes;
+#endif
+}
+// bytes % 16 == 0, both addresses 16-byte aligned
+ASC_HD void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, void* mbar) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(a) : "memory");
+#else
+    (void)mbar;
+    memcpy(smem_dst, gmem_src, bytes);
+#endif
+}
+ASC_HD void mbar_wait(void* mbar, unsigned parity) {
+#if defined(__CUDA_ARCH__)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+#else
+    (void)mbar; (void)parity;
+#endif
+}
+// required before the 8 bytes are used as ordinary shared memory again
+ASC_HD void mbar_inval(void* mbar) {
+#if defined(__CUDA_ARCH__)
+    const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+#else
+    (void)mbar;
+#endif
+}
+
 // --------------------------------------------------------------- static_for
 template <int I>
 using IC = std::integral_constant<int, I>;

@@ -34,6 +34,9 @@
 
 namespace asc {
 
+#ifndef ASC_ROW_TMA
+#define ASC_ROW_TMA 1        // K_B stages its rows with TMA bulk copies (0: cp.async / LDGSTS)
+#endif
 #ifndef ASC_SPLIT_UNROLL
 #define ASC_SPLIT_UNROLL 2   // items of the split/multiply/merge loop in flight per thread
 #endif
@@ -43,10 +46,12 @@ constexpr int COL_T = 16;          // columns per tile: 16 * 8 B = one 128-byte 
 
 // Resident CTAs per SM a transform kernel is built for (its register budget follows from it):
 // as many as its tile allows in the SM's 228 KB of shared memory (1 KB per CTA is reserved),
-// at most 3 -- 960 threads of 64 registers.
-constexpr int ctas_per_sm(size_t smem) {
+// and as 1024 threads allow, at most 3 -- 960 threads of 64 registers.
+constexpr int ctas_per_sm(size_t smem, int threads) {
     const int by_smem = (int)((228u * 1024u) / (smem + 1024u));
-    return by_smem >= 3 ? 3 : (by_smem >= 1 ? by_smem : 1);
+    const int by_threads = 1024 / threads;
+    const int n = by_smem < by_threads ? by_smem : by_threads;
+    return n >= 3 ? 3 : (n >= 1 ? n : 1);
 }
 constexpr unsigned TW2_BITS = 10;  // two-level twiddle tables: a = hi * 1024 + lo
 constexpr unsigned TW2_MASK = (1u << TW2_BITS) - 1u;
@@ -113,7 +118,7 @@ struct ColFwdKernel {
     static constexpr int P = RL::count;
     static constexpr int THREADS = NT;
     static constexpr size_t SMEM = (size_t)M1 * COL_T * sizeof(cplx);
-    static constexpr int MIN_CTAS = ctas_per_sm(SMEM);
+    static constexpr int MIN_CTAS = ctas_per_sm(SMEM, NT);
     static_assert(NT % COL_T == 0, "a thread must keep its column across items");
     static_assert(P >= 2, "column plans need at least two passes");
     static_assert(!ASYNC || sizeof(InT) == 4, "async staging copies packed fp32 pairs verbatim");
@@ -304,7 +309,7 @@ struct ColInvKernel {
     static constexpr int P = RL::count;
     static constexpr int THREADS = NT;
     static constexpr size_t SMEM = (size_t)M1 * COL_T * sizeof(cplx);
-    static constexpr int MIN_CTAS = ctas_per_sm(SMEM);
+    static constexpr int MIN_CTAS = ctas_per_sm(SMEM, NT);
     static_assert(NT % COL_T == 0, "a thread must keep its column across items");
     static_assert(NT % 32 == 0, "the argmax epilogue votes per warp");
     static_assert(P >= 2, "column plans need at least two passes");
@@ -511,12 +516,14 @@ struct RowFusedKernel {
     static constexpr int THREADS = NT;
     static constexpr int RP = M2;   // row pitch in shared memory
     static constexpr size_t SMEM = (size_t)4 * RP * sizeof(cplx);
-    static constexpr int MIN_CTAS = ctas_per_sm(SMEM);
+    static constexpr int MIN_CTAS = ctas_per_sm(SMEM, NT);
     static constexpr int R0 = RL::r(0);
     static constexpr int S0 = RL::stride(0);
     static_assert(M2 % 2 == 0, "row length must be even (16-byte chunks, bulk store size)");
     static_assert(P >= 2, "row plans need at least two passes");
     static_assert(2 * (S0 + R0) <= 2 * RP, "final-pass twiddle tables must fit the dead sample rows");
+    static constexpr bool ROW_TMA = ASC_ROW_TMA != 0;
+    static_assert(!ROW_TMA || (S0 * R0 == M2 && S0 >= 2), "pass 0 must own the last two points of a row");
 
     // A pass whose sub-stride S is below 16 (but not 1) would have half-warps
     // straddle blocks and collide in the banks; give each block 16 thread slots
@@ -548,6 +555,30 @@ struct RowFusedKernel {
         cplx* __restrict__ tab_g = buf + 2 * RP + 2 * S0;     // [2][R0]: W_M^(k*S0*k1)
 
         // ---- stage the 2*nrows rows.  smem slots: 0,1 source rows; 2,3 sample rows.
+        // ROW_TMA: four bulk copies of the TMA unit, issued by one thread, awaited by all.
+        // The CTA's shared memory is exactly the four rows, so the 8-byte mbarrier sits on the
+        // last point of slot 3; the last two points of that row are not staged -- forward pass 0
+        // reads them from global memory instead -- and the thread whose butterfly writes them
+        // first invalidates the barrier.
+        if constexpr (ROW_TMA) {
+            void* mbar = buf + 4 * RP - 1;
+            ex.phase([&](int tid) {
+                if (tid == 0) mbar_init(mbar, 1);
+            });
+            ex.phase([&](int tid) {
+                if (tid == 0) {
+                    constexpr unsigned full = (unsigned)(M2 * sizeof(cplx));
+                    mbar_expect_tx(mbar, two ? 4u * full - 16u : 2u * full);
+                    bulk_load(buf, plane_s + (long long)k1a * M2, full, mbar);
+                    bulk_load(buf + 2 * RP, plane_p + (long long)k1a * M2, full, mbar);
+                    if (two) {
+                        bulk_load(buf + RP, plane_s + (long long)k1b * M2, full, mbar);
+                        bulk_load(buf + 3 * RP, plane_p + (long long)k1b * M2, full - 16u, mbar);
+                    }
+                }
+                mbar_wait(mbar, 0);
+            });
+        } else
         ex.phase([&](int tid) {
             constexpr int cpr = M2 / 2;                       // 16-byte chunks per row
             static_for<0, 4>([&](auto B) {
@@ -587,7 +618,17 @@ struct RowFusedKernel {
                     cplx v[R];
                     static_for<0, R>([&](auto Q) {
                         constexpr int q = decltype(Q)::value;
-                        v[q] = row[i0 + q * S];
+                        if constexpr (ROW_TMA && ps == 0 && q == R - 1) {
+                            // the two points of slot 3 the staging left out (see above)
+                            if (is_smp && rr && i0 >= S - 2) {
+                                v[q] = ldg(plane_p + (long long)k1b * M2 + (i0 + q * S));
+                                if (i0 == S - 1) mbar_inval(buf + 4 * RP - 1);   // this thread overwrites it below
+                            } else {
+                                v[q] = row[i0 + q * S];
+                            }
+                        } else {
+                            v[q] = row[i0 + q * S];
+                        }
                     });
                     dft_reg<R, -1>(v);
                     row[i0] = v[0];
