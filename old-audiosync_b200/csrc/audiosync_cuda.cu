@@ -131,6 +131,48 @@ static int launch(audiosync_cuda_ctx* ctx, DeviceState& d, int cls, cudaStream_t
     return 0;
 }
 
+// ------------------------------------------------------------ tensor maps
+// Column tiles are staged by the TMA unit from 3-D views [slice][row][2*M2 floats] of the
+// caller's arrays and of the workspace planes.  The descriptors are encoded on the host per
+// launch (cuTensorMapEncodeTiled, reached through the runtime: the library does not link
+// libcuda) and travel as grid-constant kernel parameters.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static const EncodeTiledFn fn = [] {
+        if (getenv("AUDIOSYNC_CUDA_NO_TMA_TILES")) return (EncodeTiledFn) nullptr;   // experiment knob: cp.async staging
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            f = nullptr;
+        }
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+// [slices][rows][2*M2 floats], `slice_pitch_bytes` between slices; box = 32 floats x box_rows x 1.
+static int make_tile_map(CUtensorMap* tm, const void* base, int M2, int rows, size_t slice_pitch_bytes,
+                         size_t slices, int box_rows) {
+    EncodeTiledFn enc = tensor_map_encoder();
+    if (!enc) return -1;
+    const cuuint64_t gdim[3] = {(cuuint64_t)2 * M2, (cuuint64_t)rows, (cuuint64_t)std::max<size_t>(slices, 1)};
+    const cuuint64_t gstride[2] = {(cuuint64_t)M2 * sizeof(cplx), (cuuint64_t)slice_pitch_bytes};
+    const cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u};
+    const cuuint32_t estride[3] = {1u, 1u, 1u};
+    static const int promo = getenv("AUDIOSYNC_CUDA_TMA_L2PROMO") ? atoi(getenv("AUDIOSYNC_CUDA_TMA_L2PROMO")) : 0;   // experiment knob
+    const CUtensorMapL2promotion l2 = promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                      : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                      : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estride,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
+    return 0;
+}
+
 template <class K>
 static int prepare_kernel(size_t smem) {
     if (smem > 48 * 1024)
@@ -169,11 +211,26 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
                              src_pitch % 4 == 0 && smp_pitch % 4 == 0;
         const float* s_in = static_cast<const float*>(src);
         const float* m_in = static_cast<const float*>(smp);
-        const int rc = aligned ? col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, float, true>{}, s_in, m_in)
-                               : col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, float, false>{}, s_in, m_in);
+        int rc;
+        static const bool fwd_tma = getenv("AUDIOSYNC_CUDA_COLFWD_TMA") ? atoi(getenv("AUDIOSYNC_CUDA_COLFWD_TMA")) != 0 : true;   // experiment knob
+        if (aligned && fwd_tma && tensor_map_encoder()) {
+            using K = ColFwdKernel<Col, Row::n, P::NT_COL, float, 2>;
+            typename K::Params p{s_in, m_in, planes, peaks, col_tw, col_tc, m_lo, m_hi, P::L, src_pitch, smp_pitch};
+            if (make_tile_map(&p.tm_src, s_in, M2, M1, (size_t)src_pitch * sizeof(float), (size_t)pairs,
+                              tile_box_rows(K::SRC_ROWS)) != 0 ||
+                make_tile_map(&p.tm_smp, m_in, M2, M1 / 2, (size_t)smp_pitch * sizeof(float), (size_t)pairs,
+                              tile_box_rows(K::SMP_ROWS)) != 0)
+                return -1;
+            rc = launch(ctx, d, KC_COL_FWD, st, [&] {
+                fft_kernel_entry<K><<<grid_a, K::THREADS, K::SMEM, st>>>(p);
+            });
+        } else {
+            rc = aligned ? col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, float, 1>{}, s_in, m_in)
+                         : col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, float, 0>{}, s_in, m_in);
+        }
         if (rc != 0) return -1;
     } else {
-        if (col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, double, false>{}, static_cast<const double*>(src),
+        if (col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, double, 0>{}, static_cast<const double*>(src),
                     static_cast<const double*>(smp)) != 0) return -1;
     }
     {
@@ -184,7 +241,17 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
                 fft_kernel_entry<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
             }) != 0) return -1;
     }
-    {
+    if (tensor_map_encoder()) {
+        using K = ColInvKernel<Col, Row::n, P::NT_COL, true>;
+        typename K::Params p{planes, peaks, col_tw, P::L};
+        if (make_tile_map(&p.tm, planes, M2, M1, (size_t)P::L * sizeof(cplx), (size_t)2 * pairs,
+                          tile_box_rows(K::TMA_ROWS)) != 0)
+            return -1;
+        const dim3 grid(pairs, M2 / COL_T, 1);
+        if (launch(ctx, d, KC_COL_INV, st, [&] {
+                fft_kernel_entry<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
+            }) != 0) return -1;
+    } else {
         using K = ColInvKernel<Col, Row::n, P::NT_COL>;
         typename K::Params p{planes, peaks, col_tw, P::L};
         const dim3 grid(pairs, M2 / COL_T, 1);
@@ -207,7 +274,7 @@ static int run_static_pipelined(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceSt
     using Col = typename P::Col;
     using Row = typename P::Row;
     constexpr int NT = P::NT_COL;
-    using KA = ColFwdKernel<Col, Row::n, NT, InT, sizeof(InT) == 4>;
+    using KA = ColFwdKernel<Col, Row::n, NT, InT, sizeof(InT) == 4 ? 1 : 0>;
     using KB = RowFusedKernel<Row, Col::n, NT>;
     using KC = ColInvKernel<Col, Row::n, NT>;
     constexpr size_t SMEM = std::max(std::max(KA::SMEM, KB::SMEM), std::max(KC::SMEM, sizeof(PearsonShared<NT>)));
@@ -272,7 +339,7 @@ static int prepare_pipeline() {
     using Col = typename P::Col;
     using Row = typename P::Row;
     constexpr int NT = P::NT_COL;
-    using KA = ColFwdKernel<Col, Row::n, NT, InT, sizeof(InT) == 4>;
+    using KA = ColFwdKernel<Col, Row::n, NT, InT, sizeof(InT) == 4 ? 1 : 0>;
     using KB = RowFusedKernel<Row, Col::n, NT>;
     using KC = ColInvKernel<Col, Row::n, NT>;
     constexpr size_t SMEM = std::max(std::max(KA::SMEM, KB::SMEM), std::max(KC::SMEM, sizeof(PearsonShared<NT>)));
@@ -306,10 +373,12 @@ static int build_static_plan(FftPlan* plan) {
         upload(plan->row_rev, build_row_rev<Row>()) != 0 ||
         upload(plan->m_lo, m_lo) != 0 || upload(plan->m_hi, m_hi) != 0)
         return -1;
-    if (prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, true>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, true>::SMEM) != 0 ||
-        prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, false>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, false>::SMEM) != 0 ||
-        prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, double, false>>(ColFwdKernel<Col, Row::n, P::NT_COL, double, false>::SMEM) != 0 ||
+    if (prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, 2>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, 2>::SMEM) != 0 ||
+        prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, 1>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, 1>::SMEM) != 0 ||
+        prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, 0>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, 0>::SMEM) != 0 ||
+        prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, double, 0>>(ColFwdKernel<Col, Row::n, P::NT_COL, double, 0>::SMEM) != 0 ||
         prepare_kernel<RowFusedKernel<Row, Col::n, P::NT_ROW>>(RowFusedKernel<Row, Col::n, P::NT_ROW>::SMEM) != 0 ||
+        prepare_kernel<ColInvKernel<Col, Row::n, P::NT_COL, true>>(ColInvKernel<Col, Row::n, P::NT_COL, true>::SMEM) != 0 ||
         prepare_kernel<ColInvKernel<Col, Row::n, P::NT_COL>>(ColInvKernel<Col, Row::n, P::NT_COL>::SMEM) != 0)
         return -1;
     plan->run_wave = [plan](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,

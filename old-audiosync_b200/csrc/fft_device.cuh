@@ -8,6 +8,7 @@
 // oracle before any GPU time is spent.
 #pragma once
 
+#include <cuda.h>            // CUtensorMap (the descriptor type only; no driver call is made from here)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -227,6 +228,25 @@ ASC_HD void mbar_wait(void* mbar, unsigned parity) {
     } while (!ok);
 #else
     (void)mbar; (void)parity;
+#endif
+}
+// One box of a 3-D tiled tensor map (inner extent 128 bytes = one tile row, `rows` rows, one
+// slice) into shared memory: [rows][128 bytes], the layout of the column tiles.  Coordinates
+// are (float index in the row, row, slice).  Host version: the same rows copied from `raw`
+// (pointer to the first row's 128 bytes) with `row_pitch_bytes` between rows.
+ASC_HD void tma_load_rows(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, void* mbar,
+                          const void* raw, size_t row_pitch_bytes, int rows) {
+#if defined(__CUDA_ARCH__)
+    (void)raw; (void)row_pitch_bytes; (void)rows;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+                 "[%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(d), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(a) : "memory");
+#else
+    (void)tm; (void)c0; (void)c1; (void)c2; (void)mbar;
+    for (int i = 0; i < rows; i++)
+        memcpy(static_cast<char*>(smem_dst) + (size_t)i * 128, static_cast<const char*>(raw) + (size_t)i * row_pitch_bytes, 128);
 #endif
 }
 // required before the 8 bytes are used as ordinary shared memory again

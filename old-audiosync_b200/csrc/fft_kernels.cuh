@@ -62,6 +62,15 @@ ASC_HD cplx tw2(const cplx* __restrict__ lo, const cplx* __restrict__ hi, unsign
     return cmul(ldg(lo + (a & TW2_MASK)), ldg(hi + (a >> TW2_BITS)));
 }
 
+// Column tiles staged by the TMA unit: `rows` tile rows are covered by tile_boxes(rows) boxes
+// of tile_box_rows(rows) rows (a tensor-map box holds at most 256), the last one shifted up so
+// that it ends on the last row (overlapping rows are simply loaded twice).
+constexpr int tile_boxes(int rows) { return (rows + 255) / 256; }
+constexpr int tile_box_rows(int rows) { return (rows + tile_boxes(rows) - 1) / tile_boxes(rows); }
+constexpr int tile_box_start(int rows, int i) {
+    return i * tile_box_rows(rows) + tile_box_rows(rows) <= rows ? i * tile_box_rows(rows) : rows - tile_box_rows(rows);
+}
+
 template <typename InT>
 ASC_HD cplx load_packed(const InT* __restrict__ x, long long n);
 
@@ -108,11 +117,19 @@ struct ArgmaxAcc {
 };
 
 // --------------------------------------------------------------------- K_A
-// ASYNC (fp32 input, 16-byte aligned): the tile is staged with cp.async and the
-// zero half of the padded sample is written as zeros; otherwise (fp64 input or
-// unaligned pointers) the first pass loads, converts and packs through registers.
-template <class RL, int M2_, int NT, typename InT, bool ASYNC>
+// STAGE 1 / 2 (fp32 input, 16-byte aligned): the tile is staged in shared memory before pass 0
+// -- 1: cp.async (LDGSTS), 2: boxes of a tensor map through the TMA unit, completion on an
+// mbarrier -- and the zero half of the padded sample is never touched; STAGE 0 (fp64 input or
+// unaligned pointers): the first pass loads, converts and packs through registers.
+//
+// TMA staging of the SOURCE tile: the CTA's shared memory is exactly the tile, so the 8-byte
+// mbarrier sits at its very end and the last tile row (128 bytes) is not staged; pass 0 reads
+// that row from global memory, and the thread whose butterfly writes the barrier's bytes
+// invalidates it first.  (The sample tile has its unstaged upper half to spare.)
+template <class RL, int M2_, int NT, typename InT, int STAGE>
 struct ColFwdKernel {
+    static constexpr bool ASYNC = STAGE != 0;
+    static constexpr bool TMA = STAGE == 2;
     static constexpr int M1 = RL::n;
     static constexpr int M2 = M2_;                  // row length (compile time: index products fold)
     static constexpr int P = RL::count;
@@ -136,7 +153,11 @@ struct ColFwdKernel {
         long long L;             // sample_len == M = M1 * M2
         long long src_pitch;     // elements between consecutive pairs' sources / samples;
         long long smp_pitch;     // 0 = packed ([pair][2L] and [pair][L])
+        // STAGE 2: [pair][M1 or M1/2 rows][2*M2 floats] views of sources / samples, boxes of
+        // 32 floats x tile_box_rows(M1 - 1) resp. tile_box_rows(M1 / 2) rows
+        CUtensorMap tm_src, tm_smp;
     };
+    static constexpr int SRC_ROWS = M1 - 1, SMP_ROWS = M1 / 2;   // rows the TMA unit stages
 
     // grid = (M2 / 16, 2, pairs)
     template <class Ex>
@@ -152,7 +173,38 @@ struct ColFwdKernel {
         cplx* __restrict__ out = p.planes + (pair * 2 + sig) * M;
         const bool clears_peak = ex.bx() == 0 && sig == 0;
 
-        if constexpr (ASYNC) {
+        [[maybe_unused]] void* mbar = reinterpret_cast<char*>(buf) + SMEM - 8;
+        if constexpr (TMA) {
+            static_assert(!TMA || M1 >= 4, "tile too small for a box");
+            ex.phase([&](int tid) {
+                if (tid == 0) {
+                    if (clears_peak) p.peaks[pair] = cleared_peak();
+                    mbar_init(mbar, 1);
+                }
+            });
+            ex.phase([&](int tid) {
+                if (tid == 0) {
+                    const char* __restrict__ raw = reinterpret_cast<const char*>(x) + (size_t)c0 * sizeof(cplx);
+                    constexpr size_t pitch = (size_t)M2 * sizeof(cplx);
+                    if (sig == 0) {
+                        constexpr int NB = tile_boxes(SRC_ROWS), BR = tile_box_rows(SRC_ROWS);
+                        mbar_expect_tx(mbar, (unsigned)(NB * BR * 128));
+                        static_for<0, NB>([&](auto I) {
+                            constexpr int r0 = tile_box_start(SRC_ROWS, decltype(I)::value);
+                            tma_load_rows(buf + r0 * COL_T, &p.tm_src, 2 * c0, r0, (int)pair, mbar, raw + r0 * pitch, pitch, BR);
+                        });
+                    } else {
+                        constexpr int NB = tile_boxes(SMP_ROWS), BR = tile_box_rows(SMP_ROWS);
+                        mbar_expect_tx(mbar, (unsigned)(NB * BR * 128));
+                        static_for<0, NB>([&](auto I) {
+                            constexpr int r0 = tile_box_start(SMP_ROWS, decltype(I)::value);
+                            tma_load_rows(buf + r0 * COL_T, &p.tm_smp, 2 * c0, r0, (int)pair, mbar, raw + r0 * pitch, pitch, BR);
+                        });
+                    }
+                }
+                mbar_wait(mbar, 0);
+            });
+        } else if constexpr (ASYNC) {
             // tile row n1 = 16 packed points = 128 bytes = 8 chunks; shared tile has the same pitch
             ex.phase([&](int tid) {
                 if (clears_peak && tid == 0) p.peaks[pair] = cleared_peak();
@@ -207,9 +259,19 @@ struct ColFwdKernel {
                             } else {
                                 static_for<0, R>([&](auto Q) {
                                     constexpr int q = decltype(Q)::value;
-                                    if constexpr (hz && 2 * q >= R) v[q] = cmake(0.f, 0.f);
-                                    else v[q] = buf[(i0 + q * S) * COL_T + c];
+                                    if constexpr (hz && 2 * q >= R) {
+                                        v[q] = cmake(0.f, 0.f);
+                                    } else if constexpr (TMA && first && !hz && q == R - 1) {
+                                        // tile row M1 - 1 is not staged (the mbarrier sits there)
+                                        if (i0 == S - 1) v[q] = load_packed<InT>(x, (long long)(M1 - 1) * M2 + c0 + c);
+                                        else v[q] = buf[(i0 + q * S) * COL_T + c];
+                                    } else {
+                                        v[q] = buf[(i0 + q * S) * COL_T + c];
+                                    }
                                 });
+                                if constexpr (TMA && first) {
+                                    if (i0 == S - 1 && c == COL_T - 1) mbar_inval(mbar);   // overwritten below
+                                }
                             }
                             dft_reg<R, -1>(v);
                             pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
@@ -302,7 +364,9 @@ struct ColFwdKernel {
 };
 
 // --------------------------------------------------------------------- K_C
-template <class RL, int M2_, int NT>
+// TMA: the tile is staged with boxes of a tensor map over plane 0 (rows 0 .. M1-2; the last row
+// and the mbarrier as in ColFwdKernel); otherwise with cp.async.
+template <class RL, int M2_, int NT, bool TMA = false>
 struct ColInvKernel {
     static constexpr int M1 = RL::n;
     static constexpr int M2 = M2_;
@@ -319,7 +383,9 @@ struct ColInvKernel {
         PairPeak* peaks;         // [pair]
         const cplx* tw;          // RL pass tables (forward sign; conjugated here)
         long long L;
+        CUtensorMap tm;          // TMA: [2 * pair][M1 rows][2*M2 floats] view of the planes
     };
+    static constexpr int TMA_ROWS = M1 - 1;
 
     // grid = (pairs, M2 / 16): the pair index runs fastest, so the tiles of one pair are
     // spread over the launch and later tiles see the running maximum of earlier ones.
@@ -331,6 +397,25 @@ struct ColInvKernel {
         const cplx* __restrict__ in = p.planes + pair * 2 * M;
 
         // stage the tile: row n1 = 128 bytes = 8 chunks of 16 bytes
+        [[maybe_unused]] void* mbar = reinterpret_cast<char*>(buf) + SMEM - 8;
+        if constexpr (TMA) {
+            ex.phase([&](int tid) {
+                if (tid == 0) mbar_init(mbar, 1);
+            });
+            ex.phase([&](int tid) {
+                if (tid == 0) {
+                    constexpr int NB = tile_boxes(TMA_ROWS), BR = tile_box_rows(TMA_ROWS);
+                    constexpr size_t pitch = (size_t)M2 * sizeof(cplx);
+                    const char* __restrict__ raw = reinterpret_cast<const char*>(in + c0);
+                    mbar_expect_tx(mbar, (unsigned)(NB * BR * 128));
+                    static_for<0, NB>([&](auto I) {
+                        constexpr int r0 = tile_box_start(TMA_ROWS, decltype(I)::value);
+                        tma_load_rows(buf + r0 * COL_T, &p.tm, 2 * c0, r0, (int)(2 * pair), mbar, raw + r0 * pitch, pitch, BR);
+                    });
+                }
+                mbar_wait(mbar, 0);
+            });
+        } else
         ex.phase([&](int tid) {
             static_assert(NT % 8 == 0, "a thread keeps its 16-byte part across rows");
             constexpr int RSTEP = NT / 8;
@@ -360,8 +445,17 @@ struct ColInvKernel {
                     cplx v[R];
                     static_for<0, R>([&](auto Q) {
                         constexpr int q = decltype(Q)::value;
-                        v[q] = buf[(i0 + q * S) * COL_T + c];
+                        if constexpr (TMA && ps == 0 && q == R - 1) {
+                            // tile row M1 - 1 is not staged (the mbarrier sits there)
+                            if (i0 == S - 1) v[q] = ldg(in + ((long long)(M1 - 1) * M2 + c0 + c));
+                            else v[q] = buf[(i0 + q * S) * COL_T + c];
+                        } else {
+                            v[q] = buf[(i0 + q * S) * COL_T + c];
+                        }
                     });
+                    if constexpr (TMA && ps == 0) {
+                        if (i0 == S - 1 && c == COL_T - 1) mbar_inval(mbar);   // overwritten below
+                    }
                     dft_reg<R, +1>(v);
                     pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
                     buf[i0 * COL_T + c] = v[0];
@@ -888,8 +982,9 @@ template <class K>
 struct min_ctas_of<K, std::void_t<decltype(K::MIN_CTAS)>> { static constexpr int value = K::MIN_CTAS; };
 
 template <class K>
-__global__ void __launch_bounds__(K::THREADS, min_ctas_of<K>::value) fft_kernel_entry(const typename K::Params p) {
-    extern __shared__ __align__(16) unsigned char asc_smem[];
+__global__ void __launch_bounds__(K::THREADS, min_ctas_of<K>::value)
+fft_kernel_entry(const __grid_constant__ typename K::Params p) {   // grid constant: tensor maps are used in place
+    extern __shared__ __align__(128) unsigned char asc_smem[];   // TMA tile boxes land on 128-byte rows
     DeviceExec ex;
     ex.x_ = (int)blockIdx.x; ex.y_ = (int)blockIdx.y; ex.z_ = (int)blockIdx.z;
     K::run(ex, p, reinterpret_cast<cplx*>(asc_smem));

@@ -67,7 +67,9 @@ static int run_static(const InT* source, const InT* sample, PairPeak* peak, cplx
     peak->key = 12345ull; peak->second_bits = 777u;   // garbage: K_A must clear both
 
     {
-        using K = ColFwdKernel<Col, Row::n, P::NT_COL, InT, sizeof(InT) == 4>;
+        // fp32: the TMA-staged variant (the product's default; host emulation copies the same boxes
+        // and leaves the last tile row unstaged), fp64: through registers
+        using K = ColFwdKernel<Col, Row::n, P::NT_COL, InT, sizeof(InT) == 4 ? 2 : 0>;
         typename K::Params p{source, sample, planes.data(), peak, col_tw.data(), col_tc.data(), m_lo.data(), m_hi.data(), M};
         std::vector<cplx> smem(K::SMEM / sizeof(cplx));
         for (int sig = 0; sig < 2; sig++)
@@ -87,7 +89,7 @@ static int run_static(const InT* source, const InT* sample, PairPeak* peak, cplx
     }
     if (planes_out) memcpy(planes_out, planes.data(), sizeof(cplx) * M);
     {
-        using K = ColInvKernel<Col, Row::n, P::NT_COL>;
+        using K = ColInvKernel<Col, Row::n, P::NT_COL, true>;
         typename K::Params p{planes.data(), peak, col_tw.data(), M};
         std::vector<cplx> smem(K::SMEM / sizeof(cplx));
         for (int tile = 0; tile < M2 / COL_T; tile++) {
