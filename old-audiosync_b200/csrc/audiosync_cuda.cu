@@ -173,6 +173,22 @@ static int make_tile_map(CUtensorMap* tm, const void* base, int M2, int rows, si
     return 0;
 }
 
+// Stage launches of the static path: programmatic dependent launch (see pdl_prologue).
+static bool pdl_enabled() {
+    static const bool on = getenv("AUDIOSYNC_CUDA_NO_PDL") == nullptr;   // experiment knob
+    return on;
+}
+template <class... KArgs, class... Args>
+static void launch_stage(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // errors surface through cudaGetLastError in launch()
+}
+
 template <class K>
 static int prepare_kernel(size_t smem) {
     if (smem > 48 * 1024)
@@ -200,7 +216,7 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
         using K = decltype(KK);
         typename K::Params p{s_in, m_in, planes, peaks, col_tw, col_tc, m_lo, m_hi, P::L, src_pitch, smp_pitch};
         return launch(ctx, d, KC_COL_FWD, st, [&] {
-            fft_kernel_entry<K><<<grid_a, K::THREADS, K::SMEM, st>>>(p);
+            launch_stage(fft_kernel_entry<K>, grid_a, dim3(K::THREADS), K::SMEM, st, p);
         });
     };
     if (dtype == AUDIOSYNC_CUDA_F32) {
@@ -222,7 +238,7 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
                               tile_box_rows(K::SMP_ROWS)) != 0)
                 return -1;
             rc = launch(ctx, d, KC_COL_FWD, st, [&] {
-                fft_kernel_entry<K><<<grid_a, K::THREADS, K::SMEM, st>>>(p);
+                launch_stage(fft_kernel_entry<K>, grid_a, dim3(K::THREADS), K::SMEM, st, p);
             });
         } else {
             rc = aligned ? col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, float, 1>{}, s_in, m_in)
@@ -238,7 +254,7 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
         typename K::Params p{planes, row_tw, row_rev, m_lo, m_hi, P::L};
         const dim3 grid(M1 / 2 + 1, 1, pairs);
         if (launch(ctx, d, KC_ROW_FUSED, st, [&] {
-                fft_kernel_entry<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
+                launch_stage(fft_kernel_entry<K>, grid, dim3(K::THREADS), K::SMEM, st, p);
             }) != 0) return -1;
     }
     if (tensor_map_encoder()) {
@@ -249,14 +265,14 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
             return -1;
         const dim3 grid(pairs, M2 / COL_T, 1);
         if (launch(ctx, d, KC_COL_INV, st, [&] {
-                fft_kernel_entry<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
+                launch_stage(fft_kernel_entry<K>, grid, dim3(K::THREADS), K::SMEM, st, p);
             }) != 0) return -1;
     } else {
         using K = ColInvKernel<Col, Row::n, P::NT_COL>;
         typename K::Params p{planes, peaks, col_tw, P::L};
         const dim3 grid(pairs, M2 / COL_T, 1);
         if (launch(ctx, d, KC_COL_INV, st, [&] {
-                fft_kernel_entry<K><<<grid, K::THREADS, K::SMEM, st>>>(p);
+                launch_stage(fft_kernel_entry<K>, grid, dim3(K::THREADS), K::SMEM, st, p);
             }) != 0) return -1;
     }
     return 0;
@@ -570,15 +586,15 @@ static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, const void* sr
         int rc;
         if (dtype == AUDIOSYNC_CUDA_F32) {
             rc = launch(ctx, d, KC_PEARSON, st, [&] {
-                pearson_kernel<float><<<grid, PEARSON_THREADS, 0, st>>>(
+                launch_stage(pearson_kernel<float>, grid, dim3(PEARSON_THREADS), 0, st,
                     reinterpret_cast<const float*>(s), reinterpret_cast<const float*>(m), src_pitch, smp_pitch, L,
-                    peaks, 0, partials, tickets, n_chunks, d_results + p0);
+                    (const PairPeak*)peaks, 0LL, partials, tickets, n_chunks, d_results + p0);
             });
         } else {
             rc = launch(ctx, d, KC_PEARSON, st, [&] {
-                pearson_kernel<double><<<grid, PEARSON_THREADS, 0, st>>>(
+                launch_stage(pearson_kernel<double>, grid, dim3(PEARSON_THREADS), 0, st,
                     reinterpret_cast<const double*>(s), reinterpret_cast<const double*>(m), src_pitch, smp_pitch, L,
-                    peaks, 0, partials, tickets, n_chunks, d_results + p0);
+                    (const PairPeak*)peaks, 0LL, partials, tickets, n_chunks, d_results + p0);
             });
         }
         if (rc != 0) return -1;

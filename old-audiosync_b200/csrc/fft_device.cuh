@@ -259,6 +259,17 @@ ASC_HD void mbar_inval(void* mbar) {
 #endif
 }
 
+// Programmatic dependent launch: the stages of a wave are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next stage's CTAs are scheduled
+// (and parked here) while the last CTAs of this one still run; `wait` returns when the
+// preceding grid has completed and its memory is visible.  Without the attribute both are no-ops.
+ASC_HD void pdl_prologue() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
 // --------------------------------------------------------------- static_for
 template <int I>
 using IC = std::integral_constant<int, I>;

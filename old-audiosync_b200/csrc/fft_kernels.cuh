@@ -985,6 +985,7 @@ template <class K>
 __global__ void __launch_bounds__(K::THREADS, min_ctas_of<K>::value)
 fft_kernel_entry(const __grid_constant__ typename K::Params p) {   // grid constant: tensor maps are used in place
     extern __shared__ __align__(128) unsigned char asc_smem[];   // TMA tile boxes land on 128-byte rows
+    pdl_prologue();
     DeviceExec ex;
     ex.x_ = (int)blockIdx.x; ex.y_ = (int)blockIdx.y; ex.z_ = (int)blockIdx.z;
     K::run(ex, p, reinterpret_cast<cplx*>(asc_smem));

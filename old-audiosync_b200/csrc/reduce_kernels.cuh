@@ -370,6 +370,7 @@ pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
                int n_chunks, audiosync_cuda_result* __restrict__ results)
 {
     __shared__ PearsonShared<PEARSON_THREADS> sh;
+    pdl_prologue();
     pearson_block<T, PEARSON_THREADS>(sources, samples, src_pitch, smp_pitch, L, peaks, explicit_n, partials,
                                       tickets, n_chunks, results, (int)blockIdx.y, (int)blockIdx.x,
                                       (int)threadIdx.x, sh);
