@@ -72,6 +72,28 @@ KERNEL_U = {"col_fwd": 7, "row_fused": 6, "col_inv_argmax": 2, "pearson": 2, "xc
 PATH_U = 21
 
 
+# stdout carries exactly ONE line, the JSON result: everything libraries print to fd 1 (NCCL's
+# version banner, for one) is sent to stderr, and the result is written to the saved descriptor.
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -238,7 +260,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------ single-pair latency
@@ -339,6 +361,7 @@ def measure_latency(ctx, ac, torch, dev, local, stream, d_src, d_smp, d_res, n, 
 
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -356,6 +379,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # One process per GPU: run on the CPUs (and allocate pinned host memory on the NUMA node)
+    # next to this rank's GPU, as a deployment would; the e2e leg is a PCIe / host-memory number.
+    numa = "unbound"
+    all_cpus = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        numa = "nvml cpu affinity (%d cpus)" % len(os.sched_getaffinity(0))
+    except Exception:
+        pass
 
     def barrier():
         if world > 1:
@@ -448,7 +482,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * ne * reps / float(tt[0]), "unit": UNIT,
                "h2d_bytes_per_step": ne * 3 * L * 4, "d2h_bytes_per_step": ne * ac.RESULT_DTYPE.itemsize,
-               "pairs_per_step": ne, "host_dtype": "f32", "host_memory": "pinned",
+               "pairs_per_step": ne, "host_dtype": "f32", "host_memory": "pinned", "host_binding": numa,
                "h2d_gbs_per_gpu": ne * 3 * L * 4 * reps / float(tt[0]) / 1e9, "bound": "pcie (host->device copy of 17.28 MB per pair)",
                "api": "audiosync_cuda_xcorr_batch(memspace=HOST)"}
         del h_src, h_smp
@@ -502,8 +536,9 @@ def main():
         if latency is not None:
             line["latency"] = latency
         if world == 1 and not args.no_cpu_baseline:
+            os.sched_setaffinity(0, all_cpus)      # the CPU leg gets every host core back
             line["cpu_baseline"] = cpu_baseline_sample(L, SEED)
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
