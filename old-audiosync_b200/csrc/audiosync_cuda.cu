@@ -141,7 +141,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn tensor_map_encoder() {
     static const EncodeTiledFn fn = [] {
-        if (getenv("AUDIOSYNC_CUDA_NO_TMA_TILES")) return (EncodeTiledFn) nullptr;   // experiment knob: cp.async staging
+        if (getenv("AUDIOSYNC_CUDA_NO_TMA_TILES")) return (EncodeTiledFn) nullptr;   // diagnostic knob: cp.async staging of the column tiles
         void* f = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
@@ -162,12 +162,9 @@ static int make_tile_map(CUtensorMap* tm, const void* base, int M2, int rows, si
     const cuuint64_t gstride[2] = {(cuuint64_t)M2 * sizeof(cplx), (cuuint64_t)slice_pitch_bytes};
     const cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u};
     const cuuint32_t estride[3] = {1u, 1u, 1u};
-    static const int promo = getenv("AUDIOSYNC_CUDA_TMA_L2PROMO") ? atoi(getenv("AUDIOSYNC_CUDA_TMA_L2PROMO")) : 0;   // experiment knob
-    const CUtensorMapL2promotion l2 = promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                      : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
-                                      : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    // L2 promotion measured (64 / 128 / 256 B): no gain, 256 B costs K_C 0.25 us/pair
     const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estride,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, l2,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
     return 0;
@@ -175,7 +172,7 @@ static int make_tile_map(CUtensorMap* tm, const void* base, int M2, int rows, si
 
 // Stage launches of the static path: programmatic dependent launch (see pdl_prologue).
 static bool pdl_enabled() {
-    static const bool on = getenv("AUDIOSYNC_CUDA_NO_PDL") == nullptr;   // experiment knob
+    static const bool on = getenv("AUDIOSYNC_CUDA_NO_PDL") == nullptr;   // diagnostic knob: plain stream-ordered launches
     return on;
 }
 template <class... KArgs, class... Args>
@@ -228,8 +225,7 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
         const float* s_in = static_cast<const float*>(src);
         const float* m_in = static_cast<const float*>(smp);
         int rc;
-        static const bool fwd_tma = getenv("AUDIOSYNC_CUDA_COLFWD_TMA") ? atoi(getenv("AUDIOSYNC_CUDA_COLFWD_TMA")) != 0 : true;   // experiment knob
-        if (aligned && fwd_tma && tensor_map_encoder()) {
+        if (aligned && tensor_map_encoder()) {
             using K = ColFwdKernel<Col, Row::n, P::NT_COL, float, 2>;
             typename K::Params p{s_in, m_in, planes, peaks, col_tw, col_tc, m_lo, m_hi, P::L, src_pitch, smp_pitch};
             if (make_tile_map(&p.tm_src, s_in, M2, M1, (size_t)src_pitch * sizeof(float), (size_t)pairs,

@@ -67,23 +67,18 @@ struct Plan960k {
 #endif
 struct Plan1440k {
     static constexpr long long L = 1440000;
-#if ASC_1440K_VARIANT == 0
+#if ASC_1440K_VARIANT == 0           // the product's plan
     using Col = RadixList<10, 10, 6>;    // M1 = 600
     using Row = RadixList<10, 16, 15>;   // M2 = 2400
     static constexpr int NT_COL = ASC_NT_COL_1440K, NT_ROW = ASC_NT_ROW_1440K;
     static constexpr bool PIPELINE = true;
-#elif ASC_1440K_VARIANT == 1
+#elif ASC_1440K_VARIANT == 1         // measured alternative (slower), kept buildable for A/B runs
     using Col = RadixList<20, 20>;       // M1 = 400: two passes per column tile
     using Row = RadixList<15, 16, 15>;   // M2 = 3600: 115.2 KB of rows, 2 CTAs per SM
 #ifndef ASC_V1_NT_ROW
 #define ASC_V1_NT_ROW 480
 #endif
     static constexpr int NT_COL = 320, NT_ROW = ASC_V1_NT_ROW;
-    static constexpr bool PIPELINE = false;
-#elif ASC_1440K_VARIANT == 2
-    using Col = RadixList<24, 20>;       // M1 = 480
-    using Row = RadixList<10, 20, 15>;   // M2 = 3000
-    static constexpr int NT_COL = 320, NT_ROW = 400;
     static constexpr bool PIPELINE = false;
 #endif
 };

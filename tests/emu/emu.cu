@@ -169,4 +169,9 @@ unsigned emu_key_index(unsigned long long k) { return argmax_key_index(k); }
 float emu_key_value(unsigned long long k) { return argmax_key_value(k); }
 
 int emu_path_for(long long L, int forced) { return (int)choose_path(L, forced); }
+
+// box geometry of the TMA-staged column tiles (fft_kernels.cuh)
+int emu_tile_boxes(int rows) { return tile_boxes(rows); }
+int emu_tile_box_rows(int rows) { return tile_box_rows(rows); }
+int emu_tile_box_start(int rows, int i) { return tile_box_start(rows, i); }
 }

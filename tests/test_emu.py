@@ -142,3 +142,18 @@ def test_argmax_key_semantics(emu):
         k = ka(v, i)
         assert ki(k) == i and kv(k) == np.float32(v)
     assert ki(ks(-4.0)) == 0 and kv(ks(-4.0)) == -4.0
+
+
+def test_tma_tile_boxes_cover_the_staged_rows(emu):
+    # Column tiles are staged as tile_boxes(rows) tensor-map boxes of tile_box_rows(rows) rows
+    # (a box holds at most 256), the last one shifted up to end on the last row: every staged row
+    # is covered, nothing outside [0, rows) is touched.  rows = M1 - 1 (source, K_C) or M1 / 2.
+    for rows in list(range(3, 1300)) + [149, 150, 199, 200, 299, 300, 399, 599]:
+        nb, br = emu.emu_tile_boxes(rows), emu.emu_tile_box_rows(rows)
+        assert 1 <= br <= 256 and nb * br >= rows and (nb - 1) * br < rows
+        covered = set()
+        for i in range(nb):
+            r0 = emu.emu_tile_box_start(rows, i)
+            assert 0 <= r0 and r0 + br <= rows
+            covered.update(range(r0, r0 + br))
+        assert covered == set(range(rows))
