@@ -37,6 +37,9 @@ namespace asc {
 #ifndef ASC_ROW_TMA
 #define ASC_ROW_TMA 1        // K_B stages its rows with TMA bulk copies (0: cp.async / LDGSTS)
 #endif
+#ifndef ASC_ROW_GROUPS
+#define ASC_ROW_GROUPS 0     // K_B: source / sample rows (forward) and the two product rows (inverse) as two thread groups
+#endif
 #ifndef ASC_SPLIT_UNROLL
 #define ASC_SPLIT_UNROLL 2   // items of the split/multiply/merge loop in flight per thread
 #endif
@@ -617,6 +620,8 @@ struct RowFusedKernel {
     static_assert(P >= 2, "row plans need at least two passes");
     static_assert(2 * (S0 + R0) <= 2 * RP, "final-pass twiddle tables must fit the dead sample rows");
     static constexpr bool ROW_TMA = ASC_ROW_TMA != 0;
+    static constexpr bool ROW_GROUPS = ASC_ROW_GROUPS != 0;
+    static_assert(!ROW_GROUPS || (NT % 64 == 0), "two thread groups of whole warps");
     static_assert(!ROW_TMA || (S0 * R0 == M2 && S0 >= 2), "pass 0 must own the last two points of a row");
 
     // A pass whose sub-stride S is below 16 (but not 1) would have half-warps
@@ -690,18 +695,20 @@ struct RowFusedKernel {
             cp_async_wait_all();
         });
 
-        // ---- forward DIF on 2*nrows rows.
-        static_for<0, P>([&](auto PP) {
+        // ---- forward DIF on 2*nrows rows.  One pass over rows b0 .. b0+nb-1 (b < nrows: source
+        // rows, then the sample rows) by threads t = 0 .. nt-1.
+        auto fwd_pass = [&](auto PP, int t, int nt, int b0, int nb) {
             constexpr int ps = decltype(PP)::value;
             constexpr int R = RL::r(ps);
             constexpr int S = RL::stride(ps);
             constexpr int SL = slots(S);
             constexpr int per_row = (M2 / (S * R)) * SL;
-            const int items = per_row * 2 * nrows;
-            ex.phase([&](int tid) {
-                for (int w = tid; w < items; w += NT) {
-                    const int b = w / per_row;
-                    const int bf = w - b * per_row;
+            const int items = per_row * nb;
+            {
+                for (int w = t; w < items; w += nt) {
+                    const int bw = w / per_row;
+                    const int b = b0 + bw;
+                    const int bf = w - bw * per_row;
                     const int blk = bf / SL;
                     const int j = bf - blk * SL;
                     if (SL != S && j >= S) continue;
@@ -740,8 +747,19 @@ struct RowFusedKernel {
                         });
                     }
                 }
+            }
+        };
+        if constexpr (ROW_GROUPS) {
+            // the source rows and the sample rows are independent until the split: two thread
+            // groups, each with its own barrier between the passes (more independent phases per SM)
+            ex.template grouped_passes<2, P>([&](int grp, int lt, int gsz, auto PP) {
+                fwd_pass(PP, lt, gsz, grp * nrows, nrows);
             });
-        });
+        } else {
+            static_for<0, P>([&](auto PP) {
+                ex.phase([&](int tid) { fwd_pass(PP, tid, NT, 0, 2 * nrows); });
+            });
+        }
 
         // ---- split + conj-multiply + merge, in place into the source rows.
         {
@@ -788,8 +806,9 @@ struct RowFusedKernel {
             });
         }
 
-        // ---- inverse DIT on nrows rows (slots 0,1), passes P-1 .. 0.
-        static_for<0, P>([&](auto PP) {
+        // ---- inverse DIT on nrows rows (slots 0,1), passes P-1 .. 0.  One pass over rows
+        // r0 .. r0+nr-1 by threads t = 0 .. nt-1.
+        auto inv_pass = [&](auto PP, int t, int nt, int r0, int nr) {
             constexpr int ps = P - 1 - decltype(PP)::value;
             constexpr int R = RL::r(ps);
             constexpr int S = RL::stride(ps);
@@ -797,22 +816,23 @@ struct RowFusedKernel {
             constexpr bool last = ps == 0;
             constexpr bool setup = ps == P - 1;
             constexpr int per_row = (M2 / (S * R)) * SL;
-            const int items = per_row * nrows;
-            ex.phase([&](int tid) {
+            const int items = per_row * nr;
+            {
                 if constexpr (setup) {
                     // the sample rows are dead now: build the final-pass twiddle tables there
-                    for (int e = tid; e < nrows * (S0 + R0); e += NT) {
-                        const int rr = e / (S0 + R0);
-                        const int i = e - rr * (S0 + R0);
+                    for (int e = t; e < nr * (S0 + R0); e += nt) {
+                        const int rr = r0 + e / (S0 + R0);
+                        const int i = e - (rr - r0) * (S0 + R0);
                         const unsigned k1 = (unsigned)(rr ? k1b : k1a);
                         // the factor 1/2 of the merge step rides on this table (exact)
                         if (i < S0) tab_ab[rr * S0 + i] = cscale(tw2(p.m_lo, p.m_hi, (unsigned)i * k1), 0.5f);
                         else tab_g[rr * R0 + (i - S0)] = tw2(p.m_lo, p.m_hi, (unsigned)((i - S0) * S0) * k1);
                     }
                 }
-                for (int w = tid; w < items; w += NT) {
-                    const int rr = w / per_row;
-                    const int bf = w - rr * per_row;
+                for (int w = t; w < items; w += nt) {
+                    const int rw = w / per_row;
+                    const int rr = r0 + rw;
+                    const int bf = w - rw * per_row;
                     const int blk = bf / SL;
                     const int j = bf - blk * SL;
                     if (SL != S && j >= S) continue;
@@ -850,8 +870,17 @@ struct RowFusedKernel {
                     }
                 }
                 if constexpr (last) fence_async_proxy();   // rows are read by the bulk store below
+            }
+        };
+        if constexpr (ROW_GROUPS) {
+            ex.template grouped_passes<2, P>([&](int grp, int lt, int gsz, auto PP) {
+                inv_pass(PP, lt, gsz, grp, grp < nrows ? 1 : 0);
             });
-        });
+        } else {
+            static_for<0, P>([&](auto PP) {
+                ex.phase([&](int tid) { inv_pass(PP, tid, NT, 0, nrows); });
+            });
+        }
 
         // ---- the product rows leave through the TMA unit, back in place (row k1 of plane 0).
         ex.single([&]() {
@@ -877,6 +906,23 @@ struct DeviceExec {
     ASC_HD void phase(F&& f) {
 #if defined(__CUDA_ARCH__)
         f((int)threadIdx.x);
+        __syncthreads();
+#endif
+    }
+    // NPASS passes on NG independent thread groups (blockDim / NG threads each, whole warps):
+    // f(group, local thread, group size, IC<pass>).  The passes of a group are separated by a
+    // barrier among that group's threads only (named barrier 1 + group); a CTA barrier follows.
+    template <int NG, int NPASS, class F>
+    ASC_HD void grouped_passes(F&& f) {
+#if defined(__CUDA_ARCH__)
+        const int gsz = (int)blockDim.x / NG;
+        const int grp = (int)threadIdx.x / gsz;
+        const int lt = (int)threadIdx.x - grp * gsz;
+        static_for<0, NPASS>([&](auto PS) {
+            f(grp, lt, gsz, PS);
+            if constexpr (decltype(PS)::value + 1 < NPASS)
+                asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(gsz) : "memory");
+        });
         __syncthreads();
 #endif
     }
