@@ -18,11 +18,13 @@
 //
 // All passes are in-place radix passes in shared memory (decimation in
 // frequency forward, decimation in time for the inverse rows).  Tiles and rows
-// are staged global -> shared with cp.async (LDGSTS, 16 bytes per thread, no
-// registers, every request of the CTA in flight at once) so that the load of
-// one CTA overlaps the butterflies of the other CTAs on the SM; K_B's product
-// rows leave through the TMA unit (cp.async.bulk shared -> global).  The last
-// pass is fused with the global store / epilogue.
+// are staged global -> shared by the TMA unit -- boxes of a 3-D tensor map for the
+// column tiles (cp.async.bulk.tensor), plain bulk copies for the contiguous rows,
+// completion on an mbarrier -- so that no thread spends instructions on the load
+// and the load of one CTA overlaps the butterflies of the other CTAs on the SM;
+// K_B's product rows leave the same way (cp.async.bulk shared -> global).  A
+// cp.async (LDGSTS) variant of each staging step remains selectable at compile
+// time.  The last pass is fused with the global store / epilogue.
 //
 // Kernel bodies are written against an executor (DeviceExec on the GPU,
 // tests/emu's HostExec on the CPU) that runs one "phase" for every thread and
