@@ -643,3 +643,41 @@ def test_profile_and_launch_accounting(ac, capi):
         assert c.launch_count() > before
     for k in ("col_fwd", "row_fused", "col_inv_argmax", "pearson"):
         assert prof[k][0] >= 1 and prof[k][1] > 0.0, (k, prof)
+
+
+# ------------------------------------------------------------------ staging / launch variants
+_VARIANT_SNIPPET = r"""
+import sys, json
+sys.path.insert(0, {root!r}); sys.path.insert(0, {pkg!r})
+import numpy as np, torch
+import audiosync_cuda as ac
+L, n = {L}, 5
+with ac.Context([0]) as c:
+    d_src = torch.empty(n * 2 * L, dtype=torch.float32, device="cuda:0")
+    d_smp = torch.empty(n * L, dtype=torch.float32, device="cuda:0")
+    d_res = torch.zeros(n * ac.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda:0")
+    c.synth_pairs(0, {seed}, 0, n, L, ac.F32, d_src.data_ptr(), d_smp.data_ptr())
+    c.xcorr_batch_device(0, d_src.data_ptr(), d_smp.data_ptr(), n, L, ac.F32, d_res.data_ptr())
+    c.synchronize(0)
+    r = d_res.cpu().numpy().view(ac.RESULT_DTYPE)
+print(json.dumps({{k: [float(x).hex() for x in r[k]] for k in ("raw_index", "lag", "peak", "coef", "second", "ret")}}))
+"""
+
+
+@pytest.mark.parametrize("L", [144000, 1440000])
+def test_staging_and_launch_variants_are_bit_identical(L):
+    """The TMA-staged tiles / programmatic dependent launch (default) and the diagnostic
+    fallbacks (cp.async staging of the column tiles, plain stream-ordered launches) run the
+    same arithmetic: every field of the result records must agree bit for bit."""
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    code = _VARIANT_SNIPPET.format(root=root, pkg=os.path.join(root, "old-audiosync_b200"), L=L, seed=SEED)
+    outs = []
+    for extra in ({}, {"AUDIOSYNC_CUDA_NO_TMA_TILES": "1"}, {"AUDIOSYNC_CUDA_NO_PDL": "1"}):
+        env = dict(os.environ, **extra)
+        p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        outs.append(json.loads(p.stdout.strip().splitlines()[-1]))
+    assert outs[0] == outs[1] == outs[2]
+    assert all(float.fromhex(x) == 0.0 for x in outs[0]["ret"])
