@@ -166,8 +166,7 @@ static int make_tile_map(CUtensorMap* tm, const void* base, int M2, int rows, si
     const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estride,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return -1; }
-    return 0;
+    return r == CUDA_SUCCESS ? 0 : -1;   // the caller falls back to cp.async staging
 }
 
 // Stage launches of the static path: programmatic dependent launch (see pdl_prologue).
@@ -225,16 +224,15 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
         const float* s_in = static_cast<const float*>(src);
         const float* m_in = static_cast<const float*>(smp);
         int rc;
-        if (aligned && tensor_map_encoder()) {
-            using K = ColFwdKernel<Col, Row::n, P::NT_COL, float, 2>;
-            typename K::Params p{s_in, m_in, planes, peaks, col_tw, col_tc, m_lo, m_hi, P::L, src_pitch, smp_pitch};
-            if (make_tile_map(&p.tm_src, s_in, M2, M1, (size_t)src_pitch * sizeof(float), (size_t)pairs,
-                              tile_box_rows(K::SRC_ROWS)) != 0 ||
-                make_tile_map(&p.tm_smp, m_in, M2, M1 / 2, (size_t)smp_pitch * sizeof(float), (size_t)pairs,
-                              tile_box_rows(K::SMP_ROWS)) != 0)
-                return -1;
+        using KT = ColFwdKernel<Col, Row::n, P::NT_COL, float, 2>;
+        typename KT::Params pt{s_in, m_in, planes, peaks, col_tw, col_tc, m_lo, m_hi, P::L, src_pitch, smp_pitch};
+        if (aligned && tensor_map_encoder() &&
+            make_tile_map(&pt.tm_src, s_in, M2, M1, (size_t)src_pitch * sizeof(float), (size_t)pairs,
+                          tile_box_rows(KT::SRC_ROWS)) == 0 &&
+            make_tile_map(&pt.tm_smp, m_in, M2, M1 / 2, (size_t)smp_pitch * sizeof(float), (size_t)pairs,
+                          tile_box_rows(KT::SMP_ROWS)) == 0) {
             rc = launch(ctx, d, KC_COL_FWD, st, [&] {
-                launch_stage(fft_kernel_entry<K>, grid_a, dim3(K::THREADS), K::SMEM, st, p);
+                launch_stage(fft_kernel_entry<KT>, grid_a, dim3(KT::THREADS), KT::SMEM, st, pt);
             });
         } else {
             rc = aligned ? col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, float, 1>{}, s_in, m_in)
@@ -253,15 +251,14 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
                 launch_stage(fft_kernel_entry<K>, grid, dim3(K::THREADS), K::SMEM, st, p);
             }) != 0) return -1;
     }
-    if (tensor_map_encoder()) {
-        using K = ColInvKernel<Col, Row::n, P::NT_COL, true>;
-        typename K::Params p{planes, peaks, col_tw, P::L};
-        if (make_tile_map(&p.tm, planes, M2, M1, (size_t)P::L * sizeof(cplx), (size_t)2 * pairs,
-                          tile_box_rows(K::TMA_ROWS)) != 0)
-            return -1;
+    using KCT = ColInvKernel<Col, Row::n, P::NT_COL, true>;
+    typename KCT::Params pct{planes, peaks, col_tw, P::L};
+    if (tensor_map_encoder() &&
+        make_tile_map(&pct.tm, planes, M2, M1, (size_t)P::L * sizeof(cplx), (size_t)2 * pairs,
+                      tile_box_rows(KCT::TMA_ROWS)) == 0) {
         const dim3 grid(pairs, M2 / COL_T, 1);
         if (launch(ctx, d, KC_COL_INV, st, [&] {
-                launch_stage(fft_kernel_entry<K>, grid, dim3(K::THREADS), K::SMEM, st, p);
+                launch_stage(fft_kernel_entry<KCT>, grid, dim3(KCT::THREADS), KCT::SMEM, st, pct);
             }) != 0) return -1;
     } else {
         using K = ColInvKernel<Col, Row::n, P::NT_COL>;

@@ -39,6 +39,9 @@ namespace asc {
 #ifndef ASC_ROW_TMA
 #define ASC_ROW_TMA 1        // K_B stages its rows with TMA bulk copies (0: cp.async / LDGSTS)
 #endif
+#ifndef ASC_COLFWD_STEP
+#define ASC_COLFWD_STEP 1    // K_A last pass: W_M^(n2*f0) stepped from item to item (see ColFwdKernel)
+#endif
 #ifndef ASC_ROW_GROUPS
 #define ASC_ROW_GROUPS 0     // K_B: source / sample rows (forward) and the two product rows (inverse) as two thread groups
 #endif
@@ -251,7 +254,7 @@ struct ColFwdKernel {
                         cplx t[R];
                         for (int w = tid; w < items; w += NT) {
                             const int bf = w >> 4;
-                            const int blk = bf / S;
+                            const int blk = (S * R == M1) ? 0 : bf / S;    // pass 0: one block
                             const int j = bf - blk * S;
                             const int i0 = blk * (S * R) + j;
                             cplx v[R];
@@ -315,15 +318,37 @@ struct ColFwdKernel {
                     // once per item: the tables do not stay in the small L1 left beside the tiles).
                     constexpr int ITER = (items + NT - 1) / NT;
                     constexpr int CH = ITER <= 6 ? ITER : 4;
+                    // STEP: consecutive items of a thread are NT/16 blocks apart; when that is a
+                    // whole number MSTEP of units of the leading digit (M1/r0 positions), the bin
+                    // f0 advances by MSTEP per item and W_M^(n2*f0) by the per-thread constant
+                    // W_M^(n2*MSTEP): one product per item instead of the digit reversal, three
+                    // table reads (L2 latency) and two products.
+                    constexpr int DB = NT / COL_T, UNIT = RL::stride(0) / R;
+                    constexpr bool STEP = ASC_COLFWD_STEP != 0 && ITER > 1 && DB % UNIT == 0;
+                    constexpr int MSTEP = STEP ? DB / UNIT : 0;
+                    [[maybe_unused]] int f0_run = 0;
+                    [[maybe_unused]] cplx t0_run = cmake(1.f, 0.f), gstep = cmake(1.f, 0.f);
+                    if constexpr (STEP) {
+                        f0_run = RL::freq_of_pos(((tid < items ? tid : 0) >> 4) * R);
+                        t0_run = cmul(ldg(p.tc + f0_run * COL_T + c), tw2(p.m_lo, p.m_hi, (unsigned)c0 * (unsigned)f0_run));
+                        gstep = tw2(p.m_lo, p.m_hi, n2 * (unsigned)MSTEP);
+                    }
                     for (int it0 = 0; it0 < ITER; it0 += CH) {
                         int f0s[CH];
                         cplx t0s[CH];
                         static_for<0, CH>([&](auto I) {
                             constexpr int i = decltype(I)::value;
-                            const int w = tid + (it0 + i) * NT;
-                            f0s[i] = RL::freq_of_pos(((w < items ? w : 0) >> 4) * R);
-                            t0s[i] = cmul(ldg(p.tc + f0s[i] * COL_T + c),
-                                          tw2(p.m_lo, p.m_hi, (unsigned)c0 * (unsigned)f0s[i]));
+                            if constexpr (STEP) {
+                                f0s[i] = f0_run;
+                                t0s[i] = t0_run;
+                                f0_run += MSTEP;
+                                t0_run = cmul(t0_run, gstep);
+                            } else {
+                                const int w = tid + (it0 + i) * NT;
+                                f0s[i] = RL::freq_of_pos(((w < items ? w : 0) >> 4) * R);
+                                t0s[i] = cmul(ldg(p.tc + f0s[i] * COL_T + c),
+                                              tw2(p.m_lo, p.m_hi, (unsigned)c0 * (unsigned)f0s[i]));
+                            }
                         });
                         static_for<0, CH>([&](auto I) {
                             constexpr int i = decltype(I)::value;
@@ -444,7 +469,7 @@ struct ColInvKernel {
                 cplx t[R];
                 for (int w = tid; w < items; w += NT) {
                     const int bf = w >> 4;
-                    const int blk = bf / S;
+                    const int blk = (S * R == M1) ? 0 : bf / S;    // pass 0: one block
                     const int j = bf - blk * S;
                     const int i0 = blk * (S * R) + j;
                     cplx v[R];
@@ -624,7 +649,7 @@ struct RowFusedKernel {
     static constexpr bool ROW_TMA = ASC_ROW_TMA != 0;
     static constexpr bool ROW_GROUPS = ASC_ROW_GROUPS != 0;
     static_assert(!ROW_GROUPS || (NT % 64 == 0), "two thread groups of whole warps");
-    static_assert(!ROW_TMA || (S0 * R0 == M2 && S0 >= 2), "pass 0 must own the last two points of a row");
+    static_assert(!ROW_TMA || (S0 * R0 == M2 && S0 >= 16), "pass 0 must own the last two points of a row as its last two items");
 
     // A pass whose sub-stride S is below 16 (but not 1) would have half-warps
     // straddle blocks and collide in the banks; give each block 16 thread slots
@@ -706,12 +731,15 @@ struct RowFusedKernel {
             constexpr int SL = slots(S);
             constexpr int per_row = (M2 / (S * R)) * SL;
             const int items = per_row * nb;
+            // ROW_TMA, pass 0: items (slot 3, i0 = S-2) and (slot 3, i0 = S-1) are the last two of
+            // the sample rows' share; b0 + nb == 4 exactly when this call covers slot 3
+            [[maybe_unused]] const int tail_w = (two && b0 + nb == 4) ? items - 2 : 0x7fffffff;
             {
                 for (int w = t; w < items; w += nt) {
                     const int bw = w / per_row;
                     const int b = b0 + bw;
                     const int bf = w - bw * per_row;
-                    const int blk = bf / SL;
+                    const int blk = (per_row == SL) ? 0 : bf / SL;   // pass 0: one block per row
                     const int j = bf - blk * SL;
                     if (SL != S && j >= S) continue;
                     const int is_smp = b >= nrows ? 1 : 0;
@@ -721,18 +749,17 @@ struct RowFusedKernel {
                     cplx v[R];
                     static_for<0, R>([&](auto Q) {
                         constexpr int q = decltype(Q)::value;
-                        if constexpr (ROW_TMA && ps == 0 && q == R - 1) {
-                            // the two points of slot 3 the staging left out (see above)
-                            if (is_smp && rr && i0 >= S - 2) {
-                                v[q] = ldg(plane_p + (long long)k1b * M2 + (i0 + q * S));
-                                if (i0 == S - 1) mbar_inval(buf + 4 * RP - 1);   // this thread overwrites it below
-                            } else {
-                                v[q] = row[i0 + q * S];
-                            }
-                        } else {
-                            v[q] = row[i0 + q * S];
-                        }
+                        v[q] = row[i0 + q * S];
                     });
+                    if constexpr (ROW_TMA && ps == 0) {
+                        // the two points of slot 3 the staging left out (see above): the last two
+                        // items of the pass; what the shared-memory read returned for them was the
+                        // barrier's bytes
+                        if (w >= tail_w) {
+                            v[R - 1] = ldg(plane_p + (long long)k1b * M2 + (i0 + (R - 1) * S));
+                            if (w == tail_w + 1) mbar_inval(buf + 4 * RP - 1);   // this thread overwrites it below
+                        }
+                    }
                     dft_reg<R, -1>(v);
                     row[i0] = v[0];
                     if constexpr (S > 1) {
@@ -835,7 +862,7 @@ struct RowFusedKernel {
                     const int rw = w / per_row;
                     const int rr = r0 + rw;
                     const int bf = w - rw * per_row;
-                    const int blk = bf / SL;
+                    const int blk = (per_row == SL) ? 0 : bf / SL;   // pass 0: one block per row
                     const int j = bf - blk * SL;
                     if (SL != S && j >= S) continue;
                     cplx* __restrict__ row = buf + rr * RP;
