@@ -46,7 +46,7 @@ namespace asc {
 #define ASC_ROW_GROUPS 0     // K_B: source / sample rows (forward) and the two product rows (inverse) as two thread groups
 #endif
 #ifndef ASC_SPLIT_UNROLL
-#define ASC_SPLIT_UNROLL 2   // items of the split/multiply/merge loop in flight per thread
+#define ASC_SPLIT_UNROLL 4   // items of the split/multiply/merge loop in flight per thread (2: +0.09, 8: +0.2 us/pair)
 #endif
 constexpr int SPLIT_UNROLL = ASC_SPLIT_UNROLL;
 
