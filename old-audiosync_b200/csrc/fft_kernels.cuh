@@ -722,9 +722,9 @@ struct RowFusedKernel {
             cp_async_wait_all();
         });
 
-        // ---- forward DIF on 2*nrows rows.  One pass over rows b0 .. b0+nb-1 (b < nrows: source
-        // rows, then the sample rows) by threads t = 0 .. nt-1.
-        auto fwd_pass = [&](auto PP, int t, int nt, int b0, int nb) {
+        // ---- forward DIF on 2*nrows rows.  One pass over the nb rows in shared-memory slots
+        // slot0, slot0 + sstep, ... by threads t = 0 .. nt-1.
+        auto fwd_pass = [&](auto PP, int t, int nt, int slot0, int sstep, int nb) {
             constexpr int ps = decltype(PP)::value;
             constexpr int R = RL::r(ps);
             constexpr int S = RL::stride(ps);
@@ -732,19 +732,16 @@ struct RowFusedKernel {
             constexpr int per_row = (M2 / (S * R)) * SL;
             const int items = per_row * nb;
             // ROW_TMA, pass 0: items (slot 3, i0 = S-2) and (slot 3, i0 = S-1) are the last two of
-            // the sample rows' share; b0 + nb == 4 exactly when this call covers slot 3
-            [[maybe_unused]] const int tail_w = (two && b0 + nb == 4) ? items - 2 : 0x7fffffff;
+            // a call whose last row is slot 3
+            [[maybe_unused]] const int tail_w = (slot0 + (nb - 1) * sstep == 3) ? items - 2 : 0x7fffffff;
             {
                 for (int w = t; w < items; w += nt) {
                     const int bw = w / per_row;
-                    const int b = b0 + bw;
                     const int bf = w - bw * per_row;
                     const int blk = (per_row == SL) ? 0 : bf / SL;   // pass 0: one block per row
                     const int j = bf - blk * SL;
                     if (SL != S && j >= S) continue;
-                    const int is_smp = b >= nrows ? 1 : 0;
-                    const int rr = b - is_smp * nrows;          // 0 or 1: which row of the pair
-                    cplx* __restrict__ row = buf + (is_smp * 2 + rr) * RP;
+                    cplx* __restrict__ row = buf + (slot0 + bw * sstep) * RP;
                     const int i0 = blk * (S * R) + j;
                     cplx v[R];
                     static_for<0, R>([&](auto Q) {
@@ -782,11 +779,11 @@ struct RowFusedKernel {
             // the source rows and the sample rows are independent until the split: two thread
             // groups, each with its own barrier between the passes (more independent phases per SM)
             ex.template grouped_passes<2, P>([&](int grp, int lt, int gsz, auto PP) {
-                fwd_pass(PP, lt, gsz, grp * nrows, nrows);
+                fwd_pass(PP, lt, gsz, 2 * grp, 1, nrows);
             });
         } else {
             static_for<0, P>([&](auto PP) {
-                ex.phase([&](int tid) { fwd_pass(PP, tid, NT, 0, 2 * nrows); });
+                ex.phase([&](int tid) { fwd_pass(PP, tid, NT, 0, two ? 1 : 2, 2 * nrows); });   // slots 0,1,2,3 or 0,2
             });
         }
 
