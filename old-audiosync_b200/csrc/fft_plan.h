@@ -81,6 +81,7 @@ struct Plan1440k {
     static constexpr int NT_COL = 320, NT_ROW = ASC_V1_NT_ROW;
     static constexpr bool PIPELINE = false;
 #endif
+    // column radix orders 6.10.10 and 10.6.10 (last pass radix 10) measured: K_A +0.2 us/pair, K_C -0.03
 };
 
 using StaticPlans = std::tuple<Plan144k, Plan288k, Plan480k, Plan720k, Plan960k, Plan1440k>;
