@@ -681,3 +681,40 @@ def test_staging_and_launch_variants_are_bit_identical(L):
         outs.append(json.loads(p.stdout.strip().splitlines()[-1]))
     assert outs[0] == outs[1] == outs[2]
     assert all(float.fromhex(x) == 0.0 for x in outs[0]["ret"])
+
+
+def test_full_size_peak_and_coefficient_from_first_principles(ac, ctx):
+    """L = 1,440,000, independent of the oracle: at the lag the kernels report, the peak must be
+    the circular correlation sum itself (reference src/cross_correlation.c:232-239: c2r of the
+    product is N * sum_n source[(n + idx) mod N] * sample_pad[n]) and the coefficient the
+    Pearson coefficient of the reference's windows (:256-271, :74-116), both evaluated here in
+    fp64 with torch on the device from the same inputs."""
+    import torch
+    L, n, first = 1440000, 12, 40
+    res, d_src, d_smp = _batch_on_device(ac, ctx, SEED, first, n, L)
+    signs = set()
+    for i in range(n):
+        src = d_src[i * 2 * L:(i + 1) * 2 * L].double()
+        smp = d_smp[i * L:(i + 1) * L].double()
+        idx, lag = int(res["raw_index"][i]), int(res["lag"][i])
+        assert lag == (idx if idx < L else idx - 2 * L)
+        signs.add(lag >= 0)
+        # peak: N * sum_n source[(n + idx) mod N] * sample[n], n < L
+        rolled = torch.roll(src, -idx)[:L]
+        peak = 2.0 * L * float(torch.dot(rolled, smp))
+        assert abs(float(res["peak"][i]) - peak) <= RTOL * abs(peak)
+        # coefficient over the reference's windows
+        if lag >= 0:
+            x, y = src[lag:lag + L], smp
+        else:
+            x, y = src[:L + lag], smp[-lag:]
+        dx, dy = x - x.mean(), y - y.mean()
+        coef = float(torch.dot(dx, dy) / torch.sqrt(torch.dot(dx, dx) * torch.dot(dy, dy)))
+        assert abs(float(res["coef"][i]) - coef) <= 1e-6 * abs(coef)
+        # nothing else in r reaches the peak: spot-check a few hundred other lags
+        g = torch.Generator(device="cpu").manual_seed(i)
+        for j in torch.randint(0, 2 * L, (8,), generator=g).tolist():
+            if j != idx:
+                other = 2.0 * L * float(torch.dot(torch.roll(src, -j)[:L], smp))
+                assert abs(other) <= float(res["second"][i]) * (1 + 1e-3) + 1e-6 * abs(peak)
+    assert signs == {True, False}      # both lag signs were exercised
