@@ -86,7 +86,7 @@ struct FftPlan {
     int M1 = 0, M2 = 0;
     std::string desc;
     size_t ws_bytes_per_pair = 0;
-    DevBuf col_tw, col_tc, row_tw, row_rev, m_lo, m_hi;   // static four-step
+    DevBuf col_tw, col_tc, row_tw, row_rev, row_tab, m_lo, m_hi;   // static four-step
     DevBuf wm, wn;                                   // short-length kernel
     SmallPlan small;
     DevBuf sched;                                    // wave pipeline: role schedule of one pair
@@ -99,7 +99,7 @@ struct FftPlan {
     std::function<int(audiosync_cuda_ctx*, DeviceState&, const void*, const void*, int, long long, long long,
                       void*, PairPeak*, int, cudaStream_t)> run_wave;
     ~FftPlan() {
-        col_tw.release(); col_tc.release(); row_tw.release(); row_rev.release(); m_lo.release(); m_hi.release();
+        col_tw.release(); col_tc.release(); row_tw.release(); row_rev.release(); row_tab.release(); m_lo.release(); m_hi.release();
         wm.release(); wn.release(); sched.release();
     }
 };
@@ -205,6 +205,7 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
     const cplx* row_tw = static_cast<const cplx*>(plan->row_tw.p);
     const cplx* col_tc = static_cast<const cplx*>(plan->col_tc.p);
     const cplx* row_rev = static_cast<const cplx*>(plan->row_rev.p);
+    const cplx* row_tab = static_cast<const cplx*>(plan->row_tab.p);
     const cplx* m_lo = static_cast<const cplx*>(plan->m_lo.p);
     const cplx* m_hi = static_cast<const cplx*>(plan->m_hi.p);
     const dim3 grid_a(M2 / COL_T, 2, pairs);
@@ -245,7 +246,7 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
     }
     {
         using K = RowFusedKernel<Row, Col::n, P::NT_ROW>;
-        typename K::Params p{planes, row_tw, row_rev, m_lo, m_hi, P::L};
+        typename K::Params p{planes, row_tw, row_rev, m_lo, m_hi, P::L, row_tab};
         const dim3 grid(M1 / 2 + 1, 1, pairs);
         if (launch(ctx, d, KC_ROW_FUSED, st, [&] {
                 launch_stage(fft_kernel_entry<K>, grid, dim3(K::THREADS), K::SMEM, st, p);
@@ -308,6 +309,7 @@ static int run_static_pipelined(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceSt
     const cplx* row_tw = static_cast<const cplx*>(plan->row_tw.p);
     const cplx* col_tc = static_cast<const cplx*>(plan->col_tc.p);
     const cplx* row_rev = static_cast<const cplx*>(plan->row_rev.p);
+    const cplx* row_tab = static_cast<const cplx*>(plan->row_tab.p);
     const cplx* m_lo = static_cast<const cplx*>(plan->m_lo.p);
     const cplx* m_hi = static_cast<const cplx*>(plan->m_hi.p);
     const long long n_waves = (long long)((n_pairs + (size_t)wave - 1) / (size_t)wave);
@@ -326,7 +328,7 @@ static int run_static_pipelined(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceSt
         q.a = typename KA::Params{src + (size_t)wa * wave * (size_t)(2 * L), smp + (size_t)wa * wave * (size_t)L,
                                   ws + (size_t)(wa % 3) * plane_elems, peaks + (size_t)(wa % 4) * wave,
                                   col_tw, col_tc, m_lo, m_hi, L};
-        q.b = typename KB::Params{ws + (size_t)(wb % 3) * plane_elems, row_tw, row_rev, m_lo, m_hi, L};
+        q.b = typename KB::Params{ws + (size_t)(wb % 3) * plane_elems, row_tw, row_rev, m_lo, m_hi, L, row_tab};
         q.c = typename KC::Params{ws + (size_t)(wc % 3) * plane_elems, peaks + (size_t)(wc % 4) * wave, col_tw, L};
         q.p = PearsonArgs<InT>{src + (size_t)wp * wave * (size_t)(2 * L), smp + (size_t)wp * wave * (size_t)L, L,
                                peaks + (size_t)(wp % 4) * wave, static_cast<PearsonPartial*>(d.partials.p),
@@ -380,6 +382,7 @@ static int build_static_plan(FftPlan* plan) {
         upload(plan->row_tw, build_pass_tables(radix_vector<Row>())) != 0 ||
         upload(plan->col_tc, build_col_tc(P::L, Col::weight(Col::count - 1))) != 0 ||
         upload(plan->row_rev, build_row_rev<Row>()) != 0 ||
+        upload(plan->row_tab, build_row_tab<Row>(P::L, Col::n)) != 0 ||
         upload(plan->m_lo, m_lo) != 0 || upload(plan->m_hi, m_hi) != 0)
         return -1;
     if (prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, 2>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, 2>::SMEM) != 0 ||

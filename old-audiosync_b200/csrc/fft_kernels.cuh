@@ -645,7 +645,6 @@ struct RowFusedKernel {
     static constexpr int S0 = RL::stride(0);
     static_assert(M2 % 2 == 0, "row length must be even (16-byte chunks, bulk store size)");
     static_assert(P >= 2, "row plans need at least two passes");
-    static_assert(2 * (S0 + R0) <= 2 * RP, "final-pass twiddle tables must fit the dead sample rows");
     static constexpr bool ROW_TMA = ASC_ROW_TMA != 0;
     static constexpr bool ROW_GROUPS = ASC_ROW_GROUPS != 0;
     static_assert(!ROW_GROUPS || (NT % 64 == 0), "two thread groups of whole warps");
@@ -663,7 +662,13 @@ struct RowFusedKernel {
         const cplx* m_lo;        // W_M tables
         const cplx* m_hi;
         long long L;
+        const cplx* rtab;        // [M1][TABP]: per row k1 the final-pass tables (fft_plan.h: build_row_tab)
     };
+    // Final-pass twiddle tables of one row k1: S0 entries 0.5 * W_M^(j*k1) (the factor 1/2 of the
+    // merge step rides here, exactly), then R0 entries W_M^(k*S0*k1); padded to an even count so
+    // that a row is a whole number of 16-byte units for the bulk copy.
+    static constexpr int TABP = (S0 + R0 + 1) & ~1;
+    static_assert(2 * TABP + 1 <= 2 * RP, "final-pass twiddle tables and their mbarrier must fit the dead sample rows");
 
     // grid = (M1/2 + 1, 1, pairs); CTA r owns rows r and M1 - r.
     template <class Ex>
@@ -676,9 +681,9 @@ struct RowFusedKernel {
         const int k1a = r, k1b = M1 - r;   // k1b unused when !two
         cplx* __restrict__ plane_s = p.planes + pair * 2 * M;
         cplx* __restrict__ plane_p = plane_s + M;
-        // final-pass twiddle tables, built in the (then dead) sample rows
-        cplx* __restrict__ tab_ab = buf + 2 * RP;             // [2][S0]: W_M^(j*k1)
-        cplx* __restrict__ tab_g = buf + 2 * RP + 2 * S0;     // [2][R0]: W_M^(k*S0*k1)
+        // final-pass twiddle tables of the two rows, copied into the (then dead) sample rows
+        cplx* __restrict__ tab = buf + 2 * RP;                // [2][TABP]
+        void* tabbar = buf + 2 * RP + 2 * TABP;               // mbarrier of that copy
 
         // ---- stage the 2*nrows rows.  smem slots: 0,1 source rows; 2,3 sample rows.
         // ROW_TMA: four bulk copies of the TMA unit, issued by one thread, awaited by all.
@@ -832,6 +837,16 @@ struct RowFusedKernel {
             });
         }
 
+        // ---- the sample rows are dead now: the TMA unit fetches the final-pass twiddle tables of
+        // the two rows into them while the first inverse passes run (waited for in the last one).
+        ex.single([&]() {
+            constexpr unsigned bytes = (unsigned)(TABP * sizeof(cplx));
+            mbar_init(tabbar, 1);
+            mbar_expect_tx(tabbar, (unsigned)nrows * bytes);
+            bulk_load(tab, p.rtab + (long long)k1a * TABP, bytes, tabbar);
+            if (two) bulk_load(tab + TABP, p.rtab + (long long)k1b * TABP, bytes, tabbar);
+        });
+
         // ---- inverse DIT on nrows rows (slots 0,1), passes P-1 .. 0.  One pass over rows
         // r0 .. r0+nr-1 by threads t = 0 .. nt-1.
         auto inv_pass = [&](auto PP, int t, int nt, int r0, int nr) {
@@ -840,21 +855,10 @@ struct RowFusedKernel {
             constexpr int S = RL::stride(ps);
             constexpr int SL = slots(S);
             constexpr bool last = ps == 0;
-            constexpr bool setup = ps == P - 1;
             constexpr int per_row = (M2 / (S * R)) * SL;
             const int items = per_row * nr;
             {
-                if constexpr (setup) {
-                    // the sample rows are dead now: build the final-pass twiddle tables there
-                    for (int e = t; e < nr * (S0 + R0); e += nt) {
-                        const int rr = r0 + e / (S0 + R0);
-                        const int i = e - (rr - r0) * (S0 + R0);
-                        const unsigned k1 = (unsigned)(rr ? k1b : k1a);
-                        // the factor 1/2 of the merge step rides on this table (exact)
-                        if (i < S0) tab_ab[rr * S0 + i] = cscale(tw2(p.m_lo, p.m_hi, (unsigned)i * k1), 0.5f);
-                        else tab_g[rr * R0 + (i - S0)] = tw2(p.m_lo, p.m_hi, (unsigned)((i - S0) * S0) * k1);
-                    }
-                }
+                if constexpr (last) mbar_wait(tabbar, 0);      // the tables requested after the split have landed
                 for (int w = t; w < items; w += nt) {
                     const int rw = w / per_row;
                     const int rr = r0 + rw;
@@ -887,11 +891,11 @@ struct RowFusedKernel {
                         });
                     } else {
                         // natural order n2 = j + k*S0; conj W_M^(n2*k1) = conj(ab[j] * g[k]); in place
-                        const cplx t0 = tab_ab[rr * S0 + j];
+                        const cplx t0 = tab[rr * TABP + j];
                         row[j] = cmulc(v[0], t0);
                         static_for<1, R>([&](auto K) {
                             constexpr int k = decltype(K)::value;
-                            row[j + k * S] = cmulc(v[k], cmul(t0, tab_g[rr * R0 + k]));
+                            row[j + k * S] = cmulc(v[k], cmul(t0, tab[rr * TABP + S0 + k]));
                         });
                     }
                 }

@@ -175,6 +175,23 @@ inline std::vector<cplx> build_row_rev() {
     return t;
 }
 
+// K_B final-pass tables, one row per k1 (layout: RowFusedKernel::TABP): S0 entries
+// 0.5 * exp(-2*pi*i*j*k1/M), then R0 entries exp(-2*pi*i*k*S0*k1/M), zero padded to an even count.
+template <class RL>
+inline std::vector<cplx> build_row_tab(long long M, int M1) {
+    constexpr int S0 = RL::stride(0), R0 = RL::r(0), TABP = (S0 + R0 + 1) & ~1;
+    std::vector<cplx> t((size_t)M1 * TABP, cmake(0.f, 0.f));
+    for (int k1 = 0; k1 < M1; k1++) {
+        cplx* row = t.data() + (size_t)k1 * TABP;
+        for (int j = 0; j < S0; j++) {
+            const cplx u = unit_root((long long)j * k1, M);
+            row[j] = cmake(0.5f * u.x, 0.5f * u.y);
+        }
+        for (int k = 0; k < R0; k++) row[S0 + k] = unit_root((long long)k * S0 * k1, M);
+    }
+    return t;
+}
+
 // Two-level tables for exp(-2*pi*i*a/base), a in [0, max_index].
 inline void build_two_level(long long base, long long max_index, std::vector<cplx>& lo,
                             std::vector<cplx>& hi) {

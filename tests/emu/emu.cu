@@ -71,6 +71,7 @@ static int run_static(const InT* source, const InT* sample, PairPeak* peak, cplx
     std::vector<cplx> row_tw = build_pass_tables(radix_vector<Row>());
     std::vector<cplx> col_tc = build_col_tc(M, Col::weight(Col::count - 1));
     std::vector<cplx> row_rev = build_row_rev<Row>();
+    std::vector<cplx> row_tab = build_row_tab<Row>(M, M1);
     std::vector<cplx> m_lo, m_hi;
     build_two_level(M, M - 1, m_lo, m_hi);
     peak->key = 12345ull; peak->second_bits = 777u;   // garbage: K_A must clear both
@@ -89,7 +90,7 @@ static int run_static(const InT* source, const InT* sample, PairPeak* peak, cplx
     }
     {
         using K = RowFusedKernel<Row, Col::n, P::NT_ROW>;
-        typename K::Params p{planes.data(), row_tw.data(), row_rev.data(), m_lo.data(), m_hi.data(), M};
+        typename K::Params p{planes.data(), row_tw.data(), row_rev.data(), m_lo.data(), m_hi.data(), M, row_tab.data()};
         std::vector<cplx> smem(K::SMEM / sizeof(cplx));
         for (int r = 0; r <= M1 / 2; r++) {
             HostExec ex{r, 0, 0, K::THREADS};
