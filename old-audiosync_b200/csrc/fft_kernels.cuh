@@ -668,6 +668,11 @@ struct RowFusedKernel {
     // merge step rides here, exactly), then R0 entries W_M^(k*S0*k1); padded to an even count so
     // that a row is a whole number of 16-byte units for the bulk copy.
     static constexpr int TABP = (S0 + R0 + 1) & ~1;
+    // split phase: thread (a, b) = (tid / 64, tid % 64) of an A x 64 grid over (d0, e1)
+    static_assert(NT % 64 == 0, "the split phase maps threads to an (NT/64) x 64 grid");
+    static constexpr int SPLIT_A = NT / 64;
+    static constexpr int SPLIT_XN = (R0 + SPLIT_A - 1) / SPLIT_A;
+    static constexpr int SPLIT_MN = (S0 + 63) / 64;
     static_assert(2 * TABP + 1 <= 2 * RP, "final-pass twiddle tables and their mbarrier must fit the dead sample rows");
 
     // grid = (M1/2 + 1, 1, pairs); CTA r owns rows r and M1 - r.
@@ -805,15 +810,37 @@ struct RowFusedKernel {
                     cplx* __restrict__ zs_b = buf + RP;
                     cplx* __restrict__ zp_a = buf + 2 * RP;
                     cplx* __restrict__ zp_b = buf + 3 * RP;
-#pragma unroll SPLIT_UNROLL
-                    for (int e = tid; e < M2; e += NT) {
-                        const int pb = M2 - 1 - e;
-                        const cplx w2 = cmul(ldg(p.rev + e), wk1);
-                        cplx qk, qmk;
-                        split_mul_merge_w2(zs_a[e], zs_b[pb], zp_a[e], zp_b[pb], w2, qk, qmk);
-                        zs_a[e] = qk;
-                        zs_b[pb] = qmk;
-                    }
+                    // Position e = d0*S0 + e1 (d0 < R0, e1 < S0) holds bin d0 + freq_of_pos(e1), so
+                    // rev[e] = rev[d0*S0] * rev[e1].  Thread (a, b) = (tid / 64, tid % 64) takes
+                    // d0 = a, a + A, ... and e1 = b, b + 64, ...: its w^2 values are products of
+                    // SPLIT_XN + SPLIT_MN per-thread constants read once from the first S0 (+ R0
+                    // strided) entries of rev -- 2 KB that stay in L1 -- instead of one read of the
+                    // whole 19 KB table from L2 per item.  Lanes still walk contiguous positions.
+                    cplx ax[SPLIT_XN], cm[SPLIT_MN];
+                    const int sa = tid >> 6, sb = tid & 63;
+                    static_for<0, SPLIT_XN>([&](auto X) {
+                        const int d0 = sa + decltype(X)::value * SPLIT_A;
+                        ax[decltype(X)::value] = cmul(ldg(p.rev + (d0 < R0 ? d0 : 0) * S0), wk1);
+                    });
+                    static_for<0, SPLIT_MN>([&](auto Mm) {
+                        const int e1 = sb + decltype(Mm)::value * 64;
+                        cm[decltype(Mm)::value] = ldg(p.rev + (e1 < S0 ? e1 : 0));
+                    });
+                    static_for<0, SPLIT_MN>([&](auto Mm) {
+                        static_for<0, SPLIT_XN>([&](auto X) {
+                            const int d0 = sa + decltype(X)::value * SPLIT_A;
+                            const int e1 = sb + decltype(Mm)::value * 64;
+                            if (d0 < R0 && e1 < S0) {
+                                const int e = d0 * S0 + e1;
+                                const int pb = M2 - 1 - e;
+                                const cplx w2 = cmul(ax[decltype(X)::value], cm[decltype(Mm)::value]);
+                                cplx qk, qmk;
+                                split_mul_merge_w2(zs_a[e], zs_b[pb], zp_a[e], zp_b[pb], w2, qk, qmk);
+                                zs_a[e] = qk;
+                                zs_b[pb] = qmk;
+                            }
+                        });
+                    });
                 } else {
                     cplx* __restrict__ zs = buf;
                     cplx* __restrict__ zp = buf + 2 * RP;
