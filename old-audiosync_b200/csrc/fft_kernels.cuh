@@ -39,6 +39,9 @@ namespace asc {
 #ifndef ASC_ROW_TMA
 #define ASC_ROW_TMA 1        // K_B stages its rows with TMA bulk copies (0: cp.async / LDGSTS)
 #endif
+#ifndef ASC_COLFWD_GPOW
+#define ASC_COLFWD_GPOW 1    // K_A last pass: per-thread constants W_M^(n2*Wt*k) as powers of the k = 1 value
+#endif
 #ifndef ASC_COLFWD_STEP
 #define ASC_COLFWD_STEP 1    // K_A last pass: W_M^(n2*f0) stepped from item to item (see ColFwdKernel)
 #endif
@@ -308,11 +311,22 @@ struct ColFwdKernel {
                     // so the per-thread constants do not crowd out the butterfly's registers.
                     constexpr bool lean_g = R > 8;
                     cplx g[R];
-                    static_for<1, R>([&](auto K) {
-                        constexpr int k = decltype(K)::value;
-                        if constexpr (!lean_g || (k & (k - 1)) == 0)
-                            g[k] = tw2(p.m_lo, p.m_hi, n2 * (unsigned)(Wt * k));
-                    });
+                    if constexpr (!lean_g && ASC_COLFWD_GPOW != 0) {
+                        // g[k] = g[1]^k by products (k = 2: g1*g1, 3: g2*g1, 4: g2*g2, 5: g4*g1, ...:
+                        // at most three roundings) instead of two scattered table reads per k
+                        static_assert(R <= 8, "power chain written for k < 8");
+                        g[1] = tw2(p.m_lo, p.m_hi, n2 * (unsigned)Wt);
+                        static_for<2, R>([&](auto K) {
+                            constexpr int k = decltype(K)::value;
+                            g[k] = (k % 2 == 0) ? cmul(g[k / 2], g[k / 2]) : cmul(g[k - 1], g[1]);
+                        });
+                    } else {
+                        static_for<1, R>([&](auto K) {
+                            constexpr int k = decltype(K)::value;
+                            if constexpr (!lean_g || (k & (k - 1)) == 0)
+                                g[k] = tw2(p.m_lo, p.m_hi, n2 * (unsigned)(Wt * k));
+                        });
+                    }
                     // The twiddle loads of a chunk of items are issued together ahead of the
                     // butterflies (three dependent table reads per item would otherwise be exposed
                     // once per item: the tables do not stay in the small L1 left beside the tiles).
