@@ -65,7 +65,7 @@ if os.path.exists(rep):
     algU = {"col_fwd": 7, "row_fused": 6, "col_inv_argmax": 2, "pearson": 2}
     for n, d in zip(names, data):
         b = (tobytes(d[ir], units[ir]) + tobytes(d[iw], units[iw])) / ppl
-        traffic[n] = {"bytes_per_pair": b, "source": "profiles/%s_ncu.md" % tag}
+        traffic[n] = {"bytes_per_pair": b, "source": "profiles/r01_%s_ncu.md" % tag}
         out.append("- %s: %.2f MB / pair measured, %.2f MB algorithmic (%d U)" % (n, b / 1e6, algU.get(n, 0) * 5.76, algU.get(n, 0)))
     tot = sum(v["bytes_per_pair"] for v in traffic.values())
     out += ["- whole path: %.2f MB / pair measured; 97.92 MB moved by design (17 U); 120.96 MB in the prescribed accounting (21 U)" % (tot / 1e6), ""]
