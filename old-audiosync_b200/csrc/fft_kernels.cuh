@@ -285,7 +285,7 @@ struct ColFwdKernel {
                                 }
                             }
                             dft_reg<R, -1>(v);
-                            pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
+                            pass_twiddles_s<R, S>(p.tw + RL::tw_offset(ps), j, t);
                             buf[i0 * COL_T + c] = v[0];
                             static_for<1, R>([&](auto K) {
                                 constexpr int k = decltype(K)::value;
@@ -501,7 +501,7 @@ struct ColInvKernel {
                         if (i0 == S - 1 && c == COL_T - 1) mbar_inval(mbar);   // overwritten below
                     }
                     dft_reg<R, +1>(v);
-                    pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
+                    pass_twiddles_s<R, S>(p.tw + RL::tw_offset(ps), j, t);
                     buf[i0 * COL_T + c] = v[0];
                     static_for<1, R>([&](auto K) {
                         constexpr int k = decltype(K)::value;
@@ -785,7 +785,7 @@ struct RowFusedKernel {
                     row[i0] = v[0];
                     if constexpr (S > 1) {
                         cplx t[R];
-                        pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
+                        pass_twiddles_s<R, S>(p.tw + RL::tw_offset(ps), j, t);
                         static_for<1, R>([&](auto K) {
                             constexpr int k = decltype(K)::value;
                             row[i0 + k * S] = cmul(v[k], t[k]);
@@ -913,7 +913,7 @@ struct RowFusedKernel {
                     v[0] = row[i0];
                     if constexpr (S > 1) {
                         cplx t[R];
-                        pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
+                        pass_twiddles_s<R, S>(p.tw + RL::tw_offset(ps), j, t);
                         static_for<1, R>([&](auto Q) {
                             constexpr int q = decltype(Q)::value;
                             v[q] = cmulc(row[i0 + q * S], t[q]);

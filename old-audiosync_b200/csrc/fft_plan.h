@@ -152,6 +152,11 @@ inline std::vector<cplx> build_pass_tables(const std::vector<int>& radices) {
     for (size_t p = 0; p < radices.size(); p++) {
         prod *= radices[p];
         const long long s = n / prod, m = s * radices[p];
+        if (tw_full((int)s)) {      // short sub-stride: every multiple (see pass_twiddles_s)
+            for (int k = 1; k < radices[p]; k++)
+                for (long long j = 0; j < s; j++) t.push_back(unit_root(j * k, m));
+            continue;
+        }
         for (int k = 1; k < radices[p]; k *= 2)
             for (long long j = 0; j < s; j++) t.push_back(unit_root(j * k, m));
     }
