@@ -89,7 +89,7 @@ inline std::vector<uint16_t> build_pipe_schedule(const PipeShape& s) {
 template <class KA, class KB, class KC, typename InT, int NT>
 __global__ void __launch_bounds__(NT, 3) pipeline_entry(const PipelineParams<KA, KB, KC, InT> q) {
     static_assert(KA::THREADS == NT && KB::THREADS == NT && KC::THREADS == NT, "one block size for every role");
-    extern __shared__ __align__(16) unsigned char asc_smem[];
+    extern __shared__ __align__(128) unsigned char asc_smem[];   // one declaration of the dynamic buffer for every entry
     const unsigned b = blockIdx.x;
     const unsigned g = b / (unsigned)q.period;          // pair of the wave
     const unsigned i = b - g * (unsigned)q.period;
