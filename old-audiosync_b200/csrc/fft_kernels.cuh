@@ -48,10 +48,9 @@ namespace asc {
 #ifndef ASC_ROW_GROUPS
 #define ASC_ROW_GROUPS 0     // K_B: source / sample rows (forward) and the two product rows (inverse) as two thread groups
 #endif
-#ifndef ASC_SPLIT_UNROLL
-#define ASC_SPLIT_UNROLL 4   // items of the split/multiply/merge loop in flight per thread (2: +0.09, 8: +0.2 us/pair)
+#ifndef ASC_SPLIT_FENCE_EVERY
+#define ASC_SPLIT_FENCE_EVERY 2   // split phase: compiler fence after every n-th e1 step (0: none): four items in flight (none: +0.14, 1: +0.1 us/pair)
 #endif
-constexpr int SPLIT_UNROLL = ASC_SPLIT_UNROLL;
 
 constexpr int COL_T = 16;          // columns per tile: 16 * 8 B = one 128-byte line
 
@@ -841,6 +840,11 @@ struct RowFusedKernel {
                         cm[decltype(Mm)::value] = ldg(p.rev + (e1 < S0 ? e1 : 0));
                     });
                     static_for<0, SPLIT_MN>([&](auto Mm) {
+#if defined(__CUDA_ARCH__)
+                        if constexpr (ASC_SPLIT_FENCE_EVERY > 0 && decltype(Mm)::value > 0 &&
+                                      decltype(Mm)::value % (ASC_SPLIT_FENCE_EVERY > 0 ? ASC_SPLIT_FENCE_EVERY : 1) == 0)
+                            asm volatile("" ::: "memory");
+#endif
                         static_for<0, SPLIT_XN>([&](auto X) {
                             const int d0 = sa + decltype(X)::value * SPLIT_A;
                             const int e1 = sb + decltype(Mm)::value * 64;
