@@ -66,9 +66,7 @@ UNIT = "pairs/s"
 #   row_fused reads 4U (both planes), writes 2U (product rows, in place)           = 6 U
 #   col_inv   reads 2U                                                             = 2 U
 #   pearson   reads 2U (the two windows)                                           = 2 U
-#   xcorr_pipeline: one launch = all four stages, each on its own wave of pairs; per pair
-#             of throughput it is the whole path, accounted with SURVEY 8(d)'s 21 U          = 21 U
-KERNEL_U = {"col_fwd": 7, "row_fused": 6, "col_inv_argmax": 2, "pearson": 2, "xcorr_pipeline": 21}
+KERNEL_U = {"col_fwd": 7, "row_fused": 6, "col_inv_argmax": 2, "pearson": 2}
 PATH_U = 21
 
 
@@ -104,7 +102,6 @@ def parse():
     ap.add_argument("--sample-len", type=int, default=L_HEADLINE)
     ap.add_argument("--e2e-pairs", type=int, default=192)
     ap.add_argument("--wave", type=int, default=0, help="pairs per kernel wave (0 = library default)")
-    ap.add_argument("--no-pipeline", action="store_true", help="one launch per stage instead of the wave pipeline kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
@@ -324,7 +321,7 @@ def measure_latency(ctx, ac, torch, dev, local, stream, d_src, d_smp, d_res, n, 
             sched["resident" if resident else "full_upload"] = {
                 "p50_ms_six_calls": tot[len(tot) // 2],
                 "h2d_bytes_six_calls": (ac.dropin_stats()[1] - b0) // 12}
-        lib.audiosync_cuda_set_residency(1)
+        lib.audiosync_cuda_set_residency(0)
         out["c_abi_interval_schedule"] = sched
         # (iv) the same schedule for many concurrent sessions through the session pool: frames are
         # appended as they "arrive" (each crosses PCIe once, f64le), every interval is ONE batched call
@@ -403,8 +400,6 @@ def main():
     ctx = ac.Context([local])
     if args.wave:
         ctx.set_wave_pairs(args.wave)
-    if args.no_pipeline:
-        ctx.set_pipeline(False)
     plan = ctx.describe_plan(L)
 
     d_src = torch.empty(n * 2 * L, dtype=torch.float32, device=dev)

@@ -49,7 +49,14 @@ extern "C" {
  * failure (outputs untouched, one stderr line).  Prints the reference's
  * "%ld frames of delay with a confidence of %f" line (:278) when the
  * reference's global_debug (or audiosync_cuda_set_debug) is on.
- * Thread-safe; concurrent callers are serialised on the default context. */
+ * Thread-safe and reentrant: every caller leases its own stream, input mirrors and
+ * scratch on the default context, so concurrent callers overlap each other's upload
+ * and kernels (the reference's mutex likewise covers only FFTW planning, :33-44).
+ * Pageable buffers are staged through pinned bounce buffers, page-locked ones (e.g.
+ * from fftw_alloc_real below) are read by the copy engine in place.
+ * Environment: AUDIOSYNC_CUDA_DEVICE=k (default 0) or AUDIOSYNC_CUDA_DEVICES=all|i,j,..
+ * (callers are spread round-robin over the devices), AUDIOSYNC_CUDA_DROPIN_SLOTS=n
+ * in-flight calls per device (default 3). */
 int cross_correlation(double *source, double *input_sample,
                       const size_t sample_len, long *lag, double *coefficient);
 
@@ -72,16 +79,18 @@ double *fftw_alloc_real(size_t n);
 void   *fftw_alloc_complex(size_t n);        /* n * 2 doubles */
 void    fftw_free(void *p);
 
-/* Interval-schedule residency.  The reference's loop
- * (src/audiosync.c:226-259) calls cross_correlation() with the same two buffers and a
- * growing sample_len while its reader threads only append.  When `source` comes from the
- * allocators above, the library keeps the fp64 prefixes it has already uploaded on the device
- * and a call transfers only the frames that arrived since the previous one.  A session is
- * reused only if both pointers are unchanged, sample_len grew strictly, nothing was freed
- * through fftw_free in between, and 64 probe values of each cached prefix still match the
- * host buffers; otherwise everything is uploaded again.  Callers that rewrite a prefix in
- * place between growing calls must switch it off: audiosync_cuda_set_residency(0) or env
- * AUDIOSYNC_CUDA_RESIDENT=0.  Results do not depend on the setting. */
+/* Interval-schedule residency -- OPT-IN.  By default every call reads the
+ * host buffers afresh, exactly like the reference.  The reference's loop
+ * (src/audiosync.c:226-259) calls cross_correlation() with the same two buffers and a growing
+ * sample_len while its reader threads only append; a caller with that access pattern may
+ * switch residency on (audiosync_cuda_set_residency(1) or env AUDIOSYNC_CUDA_RESIDENT=1): when
+ * `source` comes from the allocators above, the library then keeps the fp64 prefixes it has
+ * already uploaded on the device and a call transfers only the frames that arrived since the
+ * previous one.  A session is reused only if both pointers are unchanged, sample_len grew
+ * strictly, nothing was freed through fftw_free in between, and 64 probe values of each cached
+ * prefix still match the host buffers; otherwise everything is uploaded again.  The probes are
+ * a guard against reuse of the buffers for another recording, NOT a proof: a caller that edits
+ * already-submitted frames in place between growing calls must leave residency off. */
 void audiosync_cuda_set_residency(int on);
 /* Counters of the drop-in cross_correlation() since load: calls, host->device bytes, and
  * calls that reused a resident session.  Any pointer may be NULL. */
@@ -202,14 +211,6 @@ int audiosync_cuda_synchronize(audiosync_cuda_ctx *ctx, int device);
 int  audiosync_cuda_set_path(audiosync_cuda_ctx *ctx, int path);          /* AUTO / FFT / DIRECT */
 int  audiosync_cuda_set_wave_pairs(audiosync_cuda_ctx *ctx, int pairs);   /* pairs per kernel wave, 0 = auto */
 void audiosync_cuda_set_debug(int on);                                    /* same effect as global_debug */
-/* Optional wave pipeline kernel: batches of more than one wave of the L = 1,440,000 plan run as
- * one launch per wave (forward columns of wave k, fused rows of wave k-1, inverse columns +
- * argmax of wave k-2, Pearson of wave k-3 as interleaved CTA roles) instead of one launch per
- * stage.  Same lag / raw index / peak bit for bit.  Default off: on B200 the stages' bottlenecks
- * do not complement each other and it measured 2-4 % slower; env AUDIOSYNC_CUDA_PIPELINE=1 or
- * this call turns it on. */
-int  audiosync_cuda_set_pipeline(audiosync_cuda_ctx *ctx, int on);
-
 /* Describes the plan for a length, e.g.
  * "fft L=1440000 M1=600 M2=2400 col=6x10x10 row=8x10x30 static". Returns the
  * number of characters written (excluding the NUL), -1 if buf is too small. */

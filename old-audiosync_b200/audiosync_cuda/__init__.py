@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "audiosync_cuda_xcorr_batch", "audiosync_cuda_xcorr_batch_results", "audiosync_cuda_xcorr_batch_device",
     "audiosync_cuda_synth_pairs", "audiosync_cuda_synchronize",
     "audiosync_cuda_set_path", "audiosync_cuda_set_wave_pairs", "audiosync_cuda_set_debug",
-    "audiosync_cuda_set_pipeline", "audiosync_cuda_set_residency", "audiosync_cuda_dropin_stats",
+    "audiosync_cuda_set_residency", "audiosync_cuda_dropin_stats",
     "audiosync_cuda_pool_create", "audiosync_cuda_pool_destroy", "audiosync_cuda_pool_reset",
     "audiosync_cuda_pool_append", "audiosync_cuda_pool_fill", "audiosync_cuda_pool_run",
     "audiosync_cuda_describe_plan", "audiosync_cuda_launch_count",
@@ -129,8 +129,6 @@ def lib() -> C.CDLL:
     L.audiosync_cuda_pool_fill.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz)]
     L.audiosync_cuda_pool_run.restype = i32
     L.audiosync_cuda_pool_run.argtypes = [vp, sz, sz, sz, vp]
-    L.audiosync_cuda_set_pipeline.restype = i32
-    L.audiosync_cuda_set_pipeline.argtypes = [vp, i32]
     L.audiosync_cuda_set_debug.restype = None
     L.audiosync_cuda_set_debug.argtypes = [i32]
     L.audiosync_cuda_describe_plan.restype = i32
@@ -280,7 +278,7 @@ class RealBuffer:
 
 
 def set_residency(on: bool) -> None:
-    """Interval-schedule residency of the drop-in ``cross_correlation`` (default on)."""
+    """Interval-schedule residency of the drop-in ``cross_correlation`` (opt-in, default off)."""
     lib().audiosync_cuda_set_residency(1 if on else 0)
 
 
@@ -384,10 +382,6 @@ class Context:
 
     def set_wave_pairs(self, pairs: int):
         self._check(lib().audiosync_cuda_set_wave_pairs(self._h, pairs), "set_wave_pairs")
-
-    def set_pipeline(self, on: bool):
-        """Wave pipeline kernel for multi-wave batches (default off = one launch per stage)."""
-        self._check(lib().audiosync_cuda_set_pipeline(self._h, 1 if on else 0), "set_pipeline")
 
     def describe_plan(self, sample_len: int) -> str:
         buf = C.create_string_buffer(512)

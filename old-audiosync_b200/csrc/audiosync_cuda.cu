@@ -21,7 +21,6 @@
 #include "fft_kernels.cuh"
 #include "fft_plan.h"
 #include "fft_small.cuh"
-#include "pipeline.cuh"
 #include "reduce_kernels.cuh"
 
 // The reference defines `volatile int global_debug` in src/audiosync.c:37 and its
@@ -46,12 +45,18 @@ void set_last_error(const char* fmt, ...) {
     fprintf(stderr, "audiosync: %s\n", g_last_error);
 }
 
+// A worker thread's message (its own thread-local buffer) handed to the calling thread.
+static std::string take_last_error() { return std::string(g_last_error); }
+static void adopt_last_error(const std::string& msg) {
+    snprintf(g_last_error, sizeof(g_last_error), "%s", msg.c_str());
+}
+
 static bool debug_on() { return g_debug_flag || (&global_debug != nullptr && global_debug); }
 
 const char* kernel_class_name(int k) {
     static const char* names[KC_COUNT] = {
         "synth", "direct_corr", "argmax_f64", "col_fwd", "row_fused",
-        "col_inv_argmax", "small_fft", "pearson", "xcorr_pipeline"};
+        "col_inv_argmax", "small_fft", "pearson"};
     return (k >= 0 && k < KC_COUNT) ? names[k] : "?";
 }
 
@@ -89,18 +94,13 @@ struct FftPlan {
     DevBuf col_tw, col_tc, row_tw, row_rev, row_tab, m_lo, m_hi;   // static four-step
     DevBuf wm, wn;                                   // short-length kernel
     SmallPlan small;
-    DevBuf sched;                                    // wave pipeline: role schedule of one pair
-    PipeShape shape{};
-    // whole batches through the wave pipeline kernel (static plans with one block size only)
-    std::function<int(audiosync_cuda_ctx*, DeviceState&, const void*, const void*, int, size_t,
-                      audiosync_cuda_result*, int, cudaStream_t)> run_pipelined;
     // enqueues the transform kernels for `pairs` pairs (planes/r in ws)
     // (src, smp, dtype, src_pitch, smp_pitch [elements between pairs], workspace, peaks, pairs, stream)
     std::function<int(audiosync_cuda_ctx*, DeviceState&, const void*, const void*, int, long long, long long,
                       void*, PairPeak*, int, cudaStream_t)> run_wave;
     ~FftPlan() {
         col_tw.release(); col_tc.release(); row_tw.release(); row_rev.release(); row_tab.release(); m_lo.release(); m_hi.release();
-        wm.release(); wn.release(); sched.release();
+        wm.release(); wn.release();
     }
 };
 
@@ -114,7 +114,9 @@ static int upload(DevBuf& b, const std::vector<cplx>& v) {
 template <class F>
 static int launch(audiosync_cuda_ctx* ctx, DeviceState& d, int cls, cudaStream_t st, F&& fn) {
     ProfileRecord rec{cls, nullptr, nullptr};
-    if (ctx->profile) {
+    const bool prof = ctx->profile;
+    if (prof) {
+        std::lock_guard<std::mutex> lk(d.prof_mu);
         for (cudaEvent_t* e : {&rec.e0, &rec.e1}) {
             if (!d.event_pool.empty()) { *e = d.event_pool.back(); d.event_pool.pop_back(); }
             else ASC_CUDA_OK(cudaEventCreate(e));
@@ -123,8 +125,9 @@ static int launch(audiosync_cuda_ctx* ctx, DeviceState& d, int cls, cudaStream_t
     }
     fn();
     ASC_CUDA_OK(cudaGetLastError());
-    if (ctx->profile) {
+    if (prof) {
         ASC_CUDA_OK(cudaEventRecord(rec.e1, st));
+        std::lock_guard<std::mutex> lk(d.prof_mu);
         d.prof_pending.push_back(rec);
     }
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
@@ -273,93 +276,6 @@ static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& 
 }
 
 
-// ---------------------------------------------------------- wave pipeline
-// Launch k runs K_A on wave k, K_B on wave k-1, K_C on wave k-2 and K_P on wave k-3
-// (pipeline.cuh).  Workspace rings: planes x3 (A writes, B in place, C reads), peaks x4
-// (A clears, C atomicMax, P reads).  Stream order between launches carries the dependencies.
-template <class P, typename InT>
-static int run_static_pipelined(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d, const InT* src,
-                                const InT* smp, size_t n_pairs, audiosync_cuda_result* d_results,
-                                int wave, cudaStream_t st) {
-    using Col = typename P::Col;
-    using Row = typename P::Row;
-    constexpr int NT = P::NT_COL;
-    using KA = ColFwdKernel<Col, Row::n, NT, InT, sizeof(InT) == 4 ? 1 : 0>;
-    using KB = RowFusedKernel<Row, Col::n, NT>;
-    using KC = ColInvKernel<Col, Row::n, NT>;
-    constexpr size_t SMEM = std::max(std::max(KA::SMEM, KB::SMEM), std::max(KC::SMEM, sizeof(PearsonShared<NT>)));
-    const long long L = P::L;
-    const PipeShape& shape = plan->shape;
-    const int n_chunks = shape.items[ROLE_P];
-    const size_t plane_elems = (size_t)2 * L * (size_t)wave;          // cplx per ring slot
-    if (d.ws.ensure(3 * plane_elems * sizeof(cplx) + 256) != 0) return -1;
-    if (d.peaks.ensure(sizeof(PairPeak) * 4 * (size_t)wave) != 0) return -1;
-    if (d.partials.ensure(sizeof(PearsonPartial) * (size_t)wave * n_chunks) != 0) return -1;
-    {
-        const size_t need = sizeof(unsigned int) * (size_t)wave;
-        if (need > d.tickets.bytes) {
-            ASC_CUDA_OK(cudaDeviceSynchronize());
-            if (d.tickets.ensure(need) != 0) return -1;
-            ASC_CUDA_OK(cudaMemset(d.tickets.p, 0, d.tickets.bytes));
-        }
-    }
-    cplx* ws = static_cast<cplx*>(d.ws.p);
-    PairPeak* peaks = static_cast<PairPeak*>(d.peaks.p);
-    const cplx* col_tw = static_cast<const cplx*>(plan->col_tw.p);
-    const cplx* row_tw = static_cast<const cplx*>(plan->row_tw.p);
-    const cplx* col_tc = static_cast<const cplx*>(plan->col_tc.p);
-    const cplx* row_rev = static_cast<const cplx*>(plan->row_rev.p);
-    const cplx* row_tab = static_cast<const cplx*>(plan->row_tab.p);
-    const cplx* m_lo = static_cast<const cplx*>(plan->m_lo.p);
-    const cplx* m_hi = static_cast<const cplx*>(plan->m_hi.p);
-    const long long n_waves = (long long)((n_pairs + (size_t)wave - 1) / (size_t)wave);
-    auto pairs_of = [&](long long w) -> int {
-        if (w < 0 || w >= n_waves) return 0;
-        return (int)std::min<size_t>((size_t)wave, n_pairs - (size_t)w * (size_t)wave);
-    };
-    auto clampw = [&](long long w) -> long long { return std::min(std::max(w, 0LL), n_waves - 1); };
-    for (long long k = 0; k < n_waves + 3; k++) {
-        const long long wa = clampw(k), wb = clampw(k - 1), wc = clampw(k - 2), wp = clampw(k - 3);
-        PipelineParams<KA, KB, KC, InT> q{};
-        q.pairs[ROLE_A] = pairs_of(k);
-        q.pairs[ROLE_B] = pairs_of(k - 1);
-        q.pairs[ROLE_C] = pairs_of(k - 2);
-        q.pairs[ROLE_P] = pairs_of(k - 3);
-        q.a = typename KA::Params{src + (size_t)wa * wave * (size_t)(2 * L), smp + (size_t)wa * wave * (size_t)L,
-                                  ws + (size_t)(wa % 3) * plane_elems, peaks + (size_t)(wa % 4) * wave,
-                                  col_tw, col_tc, m_lo, m_hi, L};
-        q.b = typename KB::Params{ws + (size_t)(wb % 3) * plane_elems, row_tw, row_rev, m_lo, m_hi, L, row_tab};
-        q.c = typename KC::Params{ws + (size_t)(wc % 3) * plane_elems, peaks + (size_t)(wc % 4) * wave, col_tw, L};
-        q.p = PearsonArgs<InT>{src + (size_t)wp * wave * (size_t)(2 * L), smp + (size_t)wp * wave * (size_t)L, L,
-                               peaks + (size_t)(wp % 4) * wave, static_cast<PearsonPartial*>(d.partials.p),
-                               static_cast<unsigned int*>(d.tickets.p), n_chunks,
-                               d_results + (size_t)wp * wave};
-        q.sched = static_cast<const uint16_t*>(plan->sched.p);
-        q.period = shape.period();
-        const int G = std::max(std::max(q.pairs[0], q.pairs[1]), std::max(q.pairs[2], q.pairs[3]));
-        const unsigned grid = (unsigned)G * (unsigned)q.period;
-        if (launch(ctx, d, KC_PIPELINE, st, [&] {
-                pipeline_entry<KA, KB, KC, InT, NT><<<grid, NT, SMEM, st>>>(q);
-            }) != 0) return -1;
-    }
-    return 0;
-}
-
-template <class P, typename InT>
-static int prepare_pipeline() {
-    using Col = typename P::Col;
-    using Row = typename P::Row;
-    constexpr int NT = P::NT_COL;
-    using KA = ColFwdKernel<Col, Row::n, NT, InT, sizeof(InT) == 4 ? 1 : 0>;
-    using KB = RowFusedKernel<Row, Col::n, NT>;
-    using KC = ColInvKernel<Col, Row::n, NT>;
-    constexpr size_t SMEM = std::max(std::max(KA::SMEM, KB::SMEM), std::max(KC::SMEM, sizeof(PearsonShared<NT>)));
-    if (SMEM > 48 * 1024)
-        ASC_CUDA_OK(cudaFuncSetAttribute(pipeline_entry<KA, KB, KC, InT, NT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    return 0;
-}
-
 template <class P>
 static int build_static_plan(FftPlan* plan) {
     using Col = typename P::Col;
@@ -398,22 +314,6 @@ static int build_static_plan(FftPlan* plan) {
                             cudaStream_t st) {
         return run_static_wave<P>(plan, ctx, d, src, smp, dtype, sp, mp, ws, peaks, pairs, st);
     };
-    if constexpr (P::NT_COL == P::NT_ROW && P::PIPELINE) {
-        plan->shape = pipe_shape(Col::n, Row::n, P::L, P::NT_COL);
-        const std::vector<uint16_t> sched = build_pipe_schedule(plan->shape);
-        if (plan->sched.ensure(sched.size() * sizeof(uint16_t)) != 0) return -1;
-        ASC_CUDA_OK(cudaMemcpy(plan->sched.p, sched.data(), sched.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-        if (prepare_pipeline<P, float>() != 0 || prepare_pipeline<P, double>() != 0) return -1;
-        plan->run_pipelined = [plan](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
-                                     int dtype, size_t n_pairs, audiosync_cuda_result* d_results, int wave,
-                                     cudaStream_t st) {
-            return dtype == AUDIOSYNC_CUDA_F32
-                       ? run_static_pipelined<P, float>(plan, ctx, d, static_cast<const float*>(src),
-                                                        static_cast<const float*>(smp), n_pairs, d_results, wave, st)
-                       : run_static_pipelined<P, double>(plan, ctx, d, static_cast<const double*>(src),
-                                                         static_cast<const double*>(smp), n_pairs, d_results, wave, st);
-        };
-    }
     return 0;
 }
 
@@ -492,6 +392,7 @@ static int build_direct_plan(FftPlan* plan, long long L) {
 
 // plans are cached per device and per (L, forced path)
 static FftPlan* get_plan(audiosync_cuda_ctx* ctx, DeviceState& d, long long L) {
+    std::lock_guard<std::mutex> plk(d.plan_mu);
     const size_t key = (size_t)L * 4 + (size_t)ctx->path;
     auto it = d.plans.find(key);
     if (it != d.plans.end()) return it->second.get();
@@ -533,18 +434,18 @@ static int default_wave_pairs(const FftPlan* plan, size_t n_pairs) {
 }
 
 // Ticket counters of the Pearson kernel: zeroed once, self-resetting afterwards.
-static int ensure_tickets(DeviceState& d, size_t n) {
+static int ensure_tickets(WorkSet& w, size_t n) {
     const size_t need = sizeof(unsigned int) * n;
-    if (need <= d.tickets.bytes) return 0;
+    if (need <= w.tickets.bytes) return 0;
     ASC_CUDA_OK(cudaDeviceSynchronize());
-    if (d.tickets.ensure(need) != 0) return -1;
-    ASC_CUDA_OK(cudaMemset(d.tickets.p, 0, d.tickets.bytes));
+    if (w.tickets.ensure(need) != 0) return -1;
+    ASC_CUDA_OK(cudaMemset(w.tickets.p, 0, w.tickets.bytes));
     return 0;
 }
 
 // Enqueue the whole path for device-resident pairs on `st` (no sync).
 // src_pitch / smp_pitch: elements between consecutive pairs (0 = packed [pair][2L] / [pair][L]).
-static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
+static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, WorkSet& work, const void* src, const void* smp,
                          size_t n_pairs, long long L, int dtype, audiosync_cuda_result* d_results,
                          cudaStream_t st, long long src_pitch = 0, long long smp_pitch = 0) {
     if (n_pairs == 0) return 0;
@@ -559,25 +460,23 @@ static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, const void* sr
     int wave = ctx->wave_pairs > 0 ? ctx->wave_pairs : default_wave_pairs(plan, n_pairs);
     wave = (int)std::min<size_t>((size_t)wave, n_pairs);
     wave = std::min(wave, 65535);
-    // More than one wave of a static plan: the wave pipeline kernel (cp.async staging of fp32
-    // tiles needs 16-byte aligned inputs; anything else takes the launch-per-stage path below).
-    if (ctx->pipeline && packed && plan->run_pipelined && n_pairs > (size_t)wave &&
-        (dtype == AUDIOSYNC_CUDA_F64 ||
-         ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(smp)) & 15u) == 0))
-        return plan->run_pipelined(ctx, d, src, smp, dtype, n_pairs, d_results, wave, st);
     const int n_chunks = (int)((L + PEARSON_CHUNK - 1) / PEARSON_CHUNK);
-    if (d.ws.ensure(plan->ws_bytes_per_pair * (size_t)wave + 256) != 0) return -1;
-    if (d.peaks.ensure(sizeof(PairPeak) * (size_t)wave) != 0) return -1;
-    if (d.partials.ensure(sizeof(PearsonPartial) * (size_t)wave * n_chunks) != 0) return -1;
-    PairPeak* peaks = static_cast<PairPeak*>(d.peaks.p);
-    PearsonPartial* partials = static_cast<PearsonPartial*>(d.partials.p);
-    if (ensure_tickets(d, (size_t)wave) != 0) return -1;
-    unsigned int* tickets = static_cast<unsigned int*>(d.tickets.p);
+    // The previous user of this scratch set may still be running on another stream: order this
+    // batch behind it (same stream: stream order already does).
+    if (work.used && work.last_stream != st) ASC_CUDA_OK(cudaStreamWaitEvent(st, work.done, 0));
+    if (!work.done) ASC_CUDA_OK(cudaEventCreateWithFlags(&work.done, cudaEventDisableTiming));
+    if (work.ws.ensure(plan->ws_bytes_per_pair * (size_t)wave + 256) != 0) return -1;
+    if (work.peaks.ensure(sizeof(PairPeak) * (size_t)wave) != 0) return -1;
+    if (work.partials.ensure(sizeof(PearsonPartial) * (size_t)wave * n_chunks) != 0) return -1;
+    PairPeak* peaks = static_cast<PairPeak*>(work.peaks.p);
+    PearsonPartial* partials = static_cast<PearsonPartial*>(work.partials.p);
+    if (ensure_tickets(work, (size_t)wave) != 0) return -1;
+    unsigned int* tickets = static_cast<unsigned int*>(work.tickets.p);
     for (size_t p0 = 0; p0 < n_pairs; p0 += (size_t)wave) {
         const int pairs = (int)std::min<size_t>((size_t)wave, n_pairs - p0);
         const char* s = static_cast<const char*>(src) + p0 * (size_t)src_pitch * esz;
         const char* m = static_cast<const char*>(smp) + p0 * (size_t)smp_pitch * esz;
-        if (plan->run_wave(ctx, d, s, m, dtype, src_pitch, smp_pitch, d.ws.p, peaks, pairs, st) != 0) return -1;
+        if (plan->run_wave(ctx, d, s, m, dtype, src_pitch, smp_pitch, work.ws.p, peaks, pairs, st) != 0) return -1;
         const dim3 grid(n_chunks, pairs);
         int rc;
         if (dtype == AUDIOSYNC_CUDA_F32) {
@@ -595,6 +494,9 @@ static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, const void* sr
         }
         if (rc != 0) return -1;
     }
+    ASC_CUDA_OK(cudaEventRecord(work.done, st));
+    work.last_stream = st;
+    work.used = true;
     return 0;
 }
 
@@ -619,18 +521,49 @@ static void destroy_device_state(DeviceState& d) {
     cudaSetDevice(d.device);
     cudaDeviceSynchronize();
     d.plans.clear();
-    d.ws.release(); d.peaks.release(); d.partials.release(); d.results.release(); d.tickets.release();
+    d.work.release(); d.results.release();
     for (int i = 0; i < 2; i++) {
-        d.in_src[i].release(); d.in_smp[i].release(); d.h_stage[i].release();
+        d.in_src[i].release(); d.in_smp[i].release();
         if (d.ev_up[i]) cudaEventDestroy(d.ev_up[i]);
         if (d.ev_done[i]) cudaEventDestroy(d.ev_done[i]);
     }
     d.h_results.release();
+    d.stage.release();
     for (auto& r : d.prof_pending) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     for (auto e : d.event_pool) cudaEventDestroy(e);
     if (d.stream) cudaStreamDestroy(d.stream);
     if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
     d.device = -1;
+}
+
+// Host -> device copy of `bytes` on `st` from ANY host memory.  Page-locked (cudaMallocHost /
+// cudaHostRegister'ed, e.g. this library's fftw_alloc_real) and managed sources go straight to
+// the copy engine; pageable ones are staged through the pinned ring.
+static bool host_pointer_is_pageable(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+static int upload_from_host(void* dst, const void* src, size_t bytes, cudaStream_t st, StageRing& ring,
+                            bool pageable) {
+    if (bytes == 0) return 0;
+    if (!pageable) {
+        ASC_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    }
+    for (size_t o = 0; o < bytes; o += StageRing::PIECE) {
+        const size_t m = std::min(StageRing::PIECE, bytes - o);
+        const int i = ring.next;
+        ring.next = (ring.next + 1) % StageRing::N;
+        if (ring.buf[i].ensure(StageRing::PIECE) != 0) return -1;
+        if (!ring.ev[i]) ASC_CUDA_OK(cudaEventCreateWithFlags(&ring.ev[i], cudaEventDisableTiming));
+        if (ring.pending[i]) ASC_CUDA_OK(cudaEventSynchronize(ring.ev[i]));   // its last DMA has drained
+        memcpy(ring.buf[i].p, static_cast<const char*>(src) + o, m);
+        ASC_CUDA_OK(cudaMemcpyAsync(static_cast<char*>(dst) + o, ring.buf[i].p, m, cudaMemcpyHostToDevice, st));
+        ASC_CUDA_OK(cudaEventRecord(ring.ev[i], st));
+        ring.pending[i] = true;
+    }
+    return 0;
 }
 
 // Host-memory pairs [p0, p1) on one device: chunked, double buffered.
@@ -650,6 +583,7 @@ static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* s
         if (!d.ev_done[b]) ASC_CUDA_OK(cudaEventCreateWithFlags(&d.ev_done[b], cudaEventDisableTiming));
     }
     const size_t total = p1 - p0;
+    const bool pageable = host_pointer_is_pageable(sources) || host_pointer_is_pageable(samples);
     if (d.results.ensure(sizeof(audiosync_cuda_result) * total) != 0) return -1;
     if (d.h_results.ensure(sizeof(audiosync_cuda_result) * total) != 0) return -1;
     audiosync_cuda_result* d_res = static_cast<audiosync_cuda_result*>(d.results.p);
@@ -658,13 +592,12 @@ static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* s
         const size_t n = std::min(chunk, total - c0);
         const int b = it & 1;
         if (it >= 2) ASC_CUDA_OK(cudaStreamWaitEvent(d.copy_stream, d.ev_done[b], 0));
-        ASC_CUDA_OK(cudaMemcpyAsync(d.in_src[b].p, sources + (p0 + c0) * src_bytes, src_bytes * n,
-                                    cudaMemcpyHostToDevice, d.copy_stream));
-        ASC_CUDA_OK(cudaMemcpyAsync(d.in_smp[b].p, samples + (p0 + c0) * smp_bytes, smp_bytes * n,
-                                    cudaMemcpyHostToDevice, d.copy_stream));
+        if (upload_from_host(d.in_src[b].p, sources + (p0 + c0) * src_bytes, src_bytes * n, d.copy_stream, d.stage, pageable) != 0 ||
+            upload_from_host(d.in_smp[b].p, samples + (p0 + c0) * smp_bytes, smp_bytes * n, d.copy_stream, d.stage, pageable) != 0)
+            return -1;
         ASC_CUDA_OK(cudaEventRecord(d.ev_up[b], d.copy_stream));
         ASC_CUDA_OK(cudaStreamWaitEvent(d.stream, d.ev_up[b], 0));
-        if (enqueue_batch(ctx, d, d.in_src[b].p, d.in_smp[b].p, n, L, dtype, d_res + c0, d.stream) != 0)
+        if (enqueue_batch(ctx, d, d.work, d.in_src[b].p, d.in_smp[b].p, n, L, dtype, d_res + c0, d.stream) != 0)
             return -1;
         ASC_CUDA_OK(cudaEventRecord(d.ev_done[b], d.stream));
     }
@@ -700,7 +633,7 @@ static bool residency_enabled() {
     int v = g_residency.load();
     if (v < 0) {
         const char* e = getenv("AUDIOSYNC_CUDA_RESIDENT");
-        v = (e && atoi(e) == 0) ? 0 : 1;
+        v = (e && atoi(e) != 0) ? 1 : 0;          // opt-in: the reference re-reads the host buffers on every call
         g_residency.store(v);
     }
     return v != 0;
@@ -761,7 +694,7 @@ int audiosync_cuda_create(audiosync_cuda_ctx** out, const int* devices, int n_de
     if (devices && n_devices > 0) ids.assign(devices, devices + n_devices);
     else for (int i = 0; i < count; i++) ids.push_back(i);
     auto* ctx = new audiosync_cuda_ctx();
-    ctx->devs.resize(ids.size());
+    ctx->devs = std::vector<DeviceState>(ids.size());
     for (size_t i = 0; i < ids.size(); i++) {
         DeviceState& d = ctx->devs[i];
         cudaDeviceProp prop;
@@ -792,14 +725,20 @@ int audiosync_cuda_create(audiosync_cuda_ctx** out, const int* devices, int n_de
     }
     const char* w = getenv("AUDIOSYNC_CUDA_WAVE_PAIRS");
     if (w) ctx->wave_pairs = atoi(w);
-    const char* pl = getenv("AUDIOSYNC_CUDA_PIPELINE");
-    if (pl) ctx->pipeline = atoi(pl) != 0;
     *out = ctx;
     return 0;
 }
 
 void audiosync_cuda_destroy(audiosync_cuda_ctx* ctx) {
     if (!ctx) return;
+    for (auto& sl : ctx->slots) {
+        if (sl->dev && sl->dev->device >= 0) { cudaSetDevice(sl->dev->device); cudaDeviceSynchronize(); }
+        sl->work.release(); sl->in_src.release(); sl->in_smp.release(); sl->d_res.release();
+        sl->h_res.release(); sl->stage.release();
+        if (sl->stream) cudaStreamDestroy(sl->stream);
+    }
+    ctx->slots.clear();
+    ctx->resident.d_src.release(); ctx->resident.d_smp.release();
     for (auto& d : ctx->devs) destroy_device_state(d);
     delete ctx;
 }
@@ -815,12 +754,6 @@ int audiosync_cuda_set_path(audiosync_cuda_ctx* ctx, int path) {
 int audiosync_cuda_set_wave_pairs(audiosync_cuda_ctx* ctx, int pairs) {
     if (!ctx || pairs < 0) return -1;
     ctx->wave_pairs = pairs;
-    return 0;
-}
-
-int audiosync_cuda_set_pipeline(audiosync_cuda_ctx* ctx, int on) {
-    if (!ctx) return -1;
-    ctx->pipeline = on != 0;
     return 0;
 }
 
@@ -887,6 +820,7 @@ int audiosync_cuda_synth_pairs(audiosync_cuda_ctx* ctx, int device, uint64_t see
     DeviceState* d = ctx->find(device);
     if (!d) { set_last_error("device %d is not part of this context", device); return -1; }
     if (n_pairs == 0) return 0;
+    std::lock_guard<std::mutex> lk(ctx->mu);
     ASC_CUDA_OK(cudaSetDevice(d->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
     const long long L = (long long)sample_len;
@@ -922,7 +856,7 @@ int audiosync_cuda_xcorr_batch_device(audiosync_cuda_ctx* ctx, int device, const
     if (!d) { set_last_error("device %d is not part of this context", device); return -1; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
-    return enqueue_batch(ctx, *d, d_sources, d_samples, n_pairs, (long long)sample_len, dtype, d_results, st);
+    return enqueue_batch(ctx, *d, d->work, d_sources, d_samples, n_pairs, (long long)sample_len, dtype, d_results, st);
 }
 
 int audiosync_cuda_xcorr_batch_results(audiosync_cuda_ctx* ctx, const void* sources, const void* samples,
@@ -946,7 +880,7 @@ int audiosync_cuda_xcorr_batch_results(audiosync_cuda_ctx* ctx, const void* sour
         ASC_CUDA_OK(cudaSetDevice(d->device));
         if (d->results.ensure(sizeof(audiosync_cuda_result) * n_pairs) != 0) return -1;
         auto* d_res = static_cast<audiosync_cuda_result*>(d->results.p);
-        if (enqueue_batch(ctx, *d, sources, samples, n_pairs, L, dtype, d_res, d->stream) != 0) return -1;
+        if (enqueue_batch(ctx, *d, d->work, sources, samples, n_pairs, L, dtype, d_res, d->stream) != 0) return -1;
         ASC_CUDA_OK(cudaMemcpyAsync(results, d_res, sizeof(audiosync_cuda_result) * n_pairs,
                                     cudaMemcpyDeviceToHost, d->stream));
         ASC_CUDA_OK(cudaStreamSynchronize(d->stream));
@@ -954,6 +888,7 @@ int audiosync_cuda_xcorr_batch_results(audiosync_cuda_ctx* ctx, const void* sour
         // contiguous block split over the devices, one host thread per device
         const size_t G = ctx->devs.size();
         std::vector<int> rcs(G, 0);
+        std::vector<std::string> errs(G);
         std::vector<std::thread> th;
         const size_t base = n_pairs / G, rem = n_pairs % G;
         size_t p0 = 0;
@@ -965,11 +900,16 @@ int audiosync_cuda_xcorr_batch_results(audiosync_cuda_ctx* ctx, const void* sour
             auto work = [&, g, a, b] {
                 rcs[g] = run_host_range(ctx, ctx->devs[g], static_cast<const char*>(sources),
                                         static_cast<const char*>(samples), a, b, L, dtype, results);
+                if (rcs[g] != 0) errs[g] = take_last_error();   // the worker's thread-local message
             };
             if (G == 1) work(); else th.emplace_back(work);
         }
         for (auto& t : th) t.join();
-        for (int r : rcs) rc |= r;
+        for (size_t g = 0; g < G; g++)
+            if (rcs[g] != 0) {
+                if (rc == 0) adopt_last_error(errs[g]);           // first failing device, for audiosync_cuda_last_error()
+                rc = -1;
+            }
         if (rc != 0) return -1;
     }
     return 0;
@@ -1127,7 +1067,7 @@ int audiosync_cuda_pool_run(audiosync_cuda_pool* pool, size_t first_slot, size_t
     const char* s0 = static_cast<const char*>(pool->src.p) + first_slot * (size_t)pool->src_pitch * esz;
     const char* m0 = static_cast<const char*>(pool->smp.p) + first_slot * (size_t)pool->smp_pitch * esz;
     auto* d_res = static_cast<audiosync_cuda_result*>(d.results.p);
-    if (enqueue_batch(pool->ctx, d, s0, m0, n_slots, (long long)sample_len, pool->dtype, d_res, d.stream,
+    if (enqueue_batch(pool->ctx, d, d.work, s0, m0, n_slots, (long long)sample_len, pool->dtype, d_res, d.stream,
                       pool->src_pitch, pool->smp_pitch) != 0)
         return -1;
     ASC_CUDA_OK(cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result) * n_slots,
@@ -1141,19 +1081,123 @@ int audiosync_cuda_pool_run(audiosync_cuda_pool* pool, size_t first_slot, size_t
 static audiosync_cuda_ctx* g_default_ctx = nullptr;
 static std::mutex g_default_mu;
 
+// Devices of the default context: AUDIOSYNC_CUDA_DEVICE=k (one device, default 0) or
+// AUDIOSYNC_CUDA_DEVICES=all | i,j,... (concurrent drop-in callers are spread round-robin over
+// them).  AUDIOSYNC_CUDA_DROPIN_SLOTS = in-flight calls per device (default 3).
 static audiosync_cuda_ctx* default_ctx() {
     std::lock_guard<std::mutex> lk(g_default_mu);
     if (!g_default_ctx) {
-        int dev = 0;
-        const char* e = getenv("AUDIOSYNC_CUDA_DEVICE");
-        if (e) dev = atoi(e);
+        std::vector<int> ids;
+        const char* many = getenv("AUDIOSYNC_CUDA_DEVICES");
+        if (many && strcmp(many, "all") != 0) {
+            for (const char* q = many; *q;) {
+                char* end = nullptr;
+                const long v = strtol(q, &end, 10);
+                if (end == q) break;
+                ids.push_back((int)v);
+                q = (*end == ',') ? end + 1 : end;
+            }
+        } else if (!many) {
+            const char* e = getenv("AUDIOSYNC_CUDA_DEVICE");
+            ids.push_back(e ? atoi(e) : 0);
+        }
         audiosync_cuda_ctx* c = nullptr;
-        if (audiosync_cuda_create(&c, &dev, 1) != 0) return nullptr;
+        if (audiosync_cuda_create(&c, ids.empty() ? nullptr : ids.data(), (int)ids.size()) != 0) return nullptr;
         const char* p = getenv("AUDIOSYNC_CUDA_PATH");
         if (p && !strcmp(p, "direct")) c->path = AUDIOSYNC_CUDA_PATH_DIRECT;
+        const char* ns = getenv("AUDIOSYNC_CUDA_DROPIN_SLOTS");
+        const int per_dev = std::max(1, std::min(16, ns ? atoi(ns) : 3));
+        for (int k = 0; k < per_dev; k++)
+            for (auto& d : c->devs) {
+                auto slot = std::make_unique<DropinSlot>();
+                slot->dev = &d;
+                if (cudaSetDevice(d.device) != cudaSuccess ||
+                    cudaStreamCreateWithFlags(&slot->stream, cudaStreamNonBlocking) != cudaSuccess) {
+                    set_last_error("cannot create a stream for drop-in callers on device %d", d.device);
+                    audiosync_cuda_destroy(c);
+                    return nullptr;
+                }
+                c->slots.push_back(std::move(slot));
+            }
         g_default_ctx = c;
     }
     return g_default_ctx;
+}
+
+namespace {
+// A free slot, round-robin over the slots (and with them over the devices); waits when all are busy.
+struct SlotLease {
+    audiosync_cuda_ctx* ctx;
+    DropinSlot* slot = nullptr;
+    explicit SlotLease(audiosync_cuda_ctx* c) : ctx(c) {
+        std::unique_lock<std::mutex> lk(ctx->slot_mu);
+        for (;;) {
+            const size_t n = ctx->slots.size();
+            for (size_t k = 0; k < n; k++) {
+                DropinSlot* s = ctx->slots[(ctx->slot_next + k) % n].get();
+                if (!s->busy) {
+                    s->busy = true;
+                    ctx->slot_next = (ctx->slot_next + k + 1) % n;
+                    slot = s;
+                    return;
+                }
+            }
+            ctx->slot_cv.wait(lk);
+        }
+    }
+    ~SlotLease() {
+        { std::lock_guard<std::mutex> lk(ctx->slot_mu); slot->busy = false; }
+        ctx->slot_cv.notify_one();
+    }
+};
+}  // namespace
+
+// The resident form of the call (opt-in, see audiosync_cuda_set_residency): one session, the
+// context's own stream and scratch, serialised on the context mutex.
+static int cross_correlation_resident(audiosync_cuda_ctx* ctx, size_t block, double* source, double* input_sample,
+                                      long long L, audiosync_cuda_result* out) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceState& d = ctx->devs[0];
+    ASC_CUDA_OK(cudaSetDevice(d.device));
+    if (d.results.ensure(sizeof(audiosync_cuda_result)) != 0 ||
+        d.h_results.ensure(sizeof(audiosync_cuda_result)) != 0)
+        return -1;
+    auto* d_res = static_cast<audiosync_cuda_result*>(d.results.p);
+    const size_t src_n = (size_t)(2 * L), smp_n = (size_t)L;
+    ResidentSession& s = ctx->resident;
+    bool hit = s.src == source && s.smp == input_sample && (size_t)L > s.L && s.L != 0 &&
+               s.alloc_gen == g_alloc_gen.load() && s.src_valid <= src_n && s.smp_valid <= smp_n &&
+               fingerprint_matches(source, s.fp_idx_src, s.fp_val_src) &&
+               fingerprint_matches(input_sample, s.fp_idx_smp, s.fp_val_smp);
+    // device mirrors sized for the whole host block, so they never move while a session lives
+    const size_t cap_src = std::max(block, src_n * sizeof(double));
+    const size_t cap_smp = std::max(block / 2, smp_n * sizeof(double));
+    if (cap_src > s.d_src.bytes || cap_smp > s.d_smp.bytes) hit = false;
+    if (!hit) {
+        s.invalidate();
+        if (s.d_src.ensure(cap_src) != 0 || s.d_smp.ensure(cap_smp) != 0) return -1;
+    } else {
+        g_dropin_resident_hits.fetch_add(1, std::memory_order_relaxed);
+    }
+    const size_t new_src = src_n - s.src_valid, new_smp = smp_n - s.smp_valid;
+    const bool pageable_smp = host_pointer_is_pageable(input_sample);
+    ASC_CUDA_OK(cudaMemcpyAsync(static_cast<double*>(s.d_src.p) + s.src_valid, source + s.src_valid,
+                                sizeof(double) * new_src, cudaMemcpyHostToDevice, d.stream));
+    if (upload_from_host(static_cast<double*>(s.d_smp.p) + s.smp_valid, input_sample + s.smp_valid,
+                         sizeof(double) * new_smp, d.stream, d.stage, pageable_smp) != 0) return -1;
+    g_dropin_h2d_bytes.fetch_add(sizeof(double) * (new_src + new_smp), std::memory_order_relaxed);
+    s.src = source; s.smp = input_sample; s.L = (size_t)L; s.src_valid = src_n; s.smp_valid = smp_n;
+    s.alloc_gen = g_alloc_gen.load();
+    fingerprint(source, src_n, s.fp_idx_src, s.fp_val_src);
+    fingerprint(input_sample, smp_n, s.fp_idx_smp, s.fp_val_smp);
+    if (enqueue_batch(ctx, d, d.work, s.d_src.p, s.d_smp.p, 1, L, AUDIOSYNC_CUDA_F64, d_res, d.stream) != 0) {
+        ctx->resident.invalidate();
+        return -1;
+    }
+    ASC_CUDA_OK(cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result), cudaMemcpyDeviceToHost, d.stream));
+    ASC_CUDA_OK(cudaStreamSynchronize(d.stream));
+    *out = *static_cast<audiosync_cuda_result*>(d.h_results.p);
+    return 0;
 }
 
 // ---- Part 1: drop-in for reference src/cross_correlation.c -----------------
@@ -1165,65 +1209,41 @@ int cross_correlation(double* source, double* input_sample, const size_t sample_
     }
     audiosync_cuda_ctx* ctx = default_ctx();
     if (!ctx) return -1;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    DeviceState& d = ctx->devs[0];
     const long long L = (long long)sample_len;
-    ASC_CUDA_OK(cudaSetDevice(d.device));
-    if (d.results.ensure(sizeof(audiosync_cuda_result)) != 0 ||
-        d.h_results.ensure(sizeof(audiosync_cuda_result)) != 0)
-        return -1;
-    auto* d_res = static_cast<audiosync_cuda_result*>(d.results.p);
-    g_dropin_calls.fetch_add(1, std::memory_order_relaxed);
     const size_t src_n = (size_t)(2 * L), smp_n = (size_t)L;
-    // Residency: the interval loop of src/audiosync.c:226-259 passes the same
-    // buffers with a growing sample_len; only the frames that arrived since the last call are
+    g_dropin_calls.fetch_add(1, std::memory_order_relaxed);
+    audiosync_cuda_result r;
+    // Residency (opt-in): the interval loop of src/audiosync.c:226-259 passes the
+    // same buffers with a growing sample_len; only the frames that arrived since the last call are
     // uploaded.  Taken only for a source from this library's allocator, a strictly larger
     // sample_len, an unchanged allocator generation and matching fingerprints of both prefixes.
     const size_t block = residency_enabled() ? library_block_bytes(source, src_n * sizeof(double)) : 0;
-    const void *d_src_in, *d_smp_in;
     if (block != 0) {
-        ResidentSession& s = ctx->resident;
-        bool hit = s.src == source && s.smp == input_sample && (size_t)L > s.L && s.L != 0 &&
-                   s.alloc_gen == g_alloc_gen.load() && s.src_valid <= src_n && s.smp_valid <= smp_n &&
-                   fingerprint_matches(source, s.fp_idx_src, s.fp_val_src) &&
-                   fingerprint_matches(input_sample, s.fp_idx_smp, s.fp_val_smp);
-        // device mirrors sized for the whole host block, so they never move while a session lives
-        const size_t cap_src = std::max(block, src_n * sizeof(double));
-        const size_t cap_smp = std::max(block / 2, smp_n * sizeof(double));
-        if (cap_src > s.d_src.bytes || cap_smp > s.d_smp.bytes) hit = false;
-        if (!hit) {
-            s.invalidate();
-            if (s.d_src.ensure(cap_src) != 0 || s.d_smp.ensure(cap_smp) != 0) return -1;
-        } else {
-            g_dropin_resident_hits.fetch_add(1, std::memory_order_relaxed);
-        }
-        const size_t new_src = src_n - s.src_valid, new_smp = smp_n - s.smp_valid;
-        ASC_CUDA_OK(cudaMemcpyAsync(static_cast<double*>(s.d_src.p) + s.src_valid, source + s.src_valid,
-                                    sizeof(double) * new_src, cudaMemcpyHostToDevice, d.stream));
-        ASC_CUDA_OK(cudaMemcpyAsync(static_cast<double*>(s.d_smp.p) + s.smp_valid, input_sample + s.smp_valid,
-                                    sizeof(double) * new_smp, cudaMemcpyHostToDevice, d.stream));
-        g_dropin_h2d_bytes.fetch_add(sizeof(double) * (new_src + new_smp), std::memory_order_relaxed);
-        s.src = source; s.smp = input_sample; s.L = (size_t)L; s.src_valid = src_n; s.smp_valid = smp_n;
-        s.alloc_gen = g_alloc_gen.load();
-        fingerprint(source, src_n, s.fp_idx_src, s.fp_val_src);
-        fingerprint(input_sample, smp_n, s.fp_idx_smp, s.fp_val_smp);
-        d_src_in = s.d_src.p; d_smp_in = s.d_smp.p;
+        if (cross_correlation_resident(ctx, block, source, input_sample, L, &r) != 0) return -1;
     } else {
-        if (d.in_src[0].ensure(sizeof(double) * src_n) != 0 || d.in_smp[0].ensure(sizeof(double) * smp_n) != 0)
+        // Default: like the reference, every call reads the host buffers afresh.  Each caller
+        // leases a slot (stream + mirrors + scratch), so concurrent callers overlap.
+        SlotLease lease(ctx);
+        DropinSlot& sl = *lease.slot;
+        DeviceState& d = *sl.dev;
+        ASC_CUDA_OK(cudaSetDevice(d.device));
+        if (sl.in_src.ensure(sizeof(double) * src_n) != 0 || sl.in_smp.ensure(sizeof(double) * smp_n) != 0 ||
+            sl.d_res.ensure(sizeof(audiosync_cuda_result)) != 0 || sl.h_res.ensure(sizeof(audiosync_cuda_result)) != 0)
             return -1;
         // snapshot exactly the prefixes the reference reads (src/cross_correlation.c:164, :204-213)
-        ASC_CUDA_OK(cudaMemcpyAsync(d.in_src[0].p, source, sizeof(double) * src_n, cudaMemcpyHostToDevice, d.stream));
-        ASC_CUDA_OK(cudaMemcpyAsync(d.in_smp[0].p, input_sample, sizeof(double) * smp_n, cudaMemcpyHostToDevice, d.stream));
+        if (upload_from_host(sl.in_src.p, source, sizeof(double) * src_n, sl.stream, sl.stage,
+                             host_pointer_is_pageable(source)) != 0 ||
+            upload_from_host(sl.in_smp.p, input_sample, sizeof(double) * smp_n, sl.stream, sl.stage,
+                             host_pointer_is_pageable(input_sample)) != 0)
+            return -1;
         g_dropin_h2d_bytes.fetch_add(sizeof(double) * (src_n + smp_n), std::memory_order_relaxed);
-        d_src_in = d.in_src[0].p; d_smp_in = d.in_smp[0].p;
+        auto* d_res = static_cast<audiosync_cuda_result*>(sl.d_res.p);
+        if (enqueue_batch(ctx, d, sl.work, sl.in_src.p, sl.in_smp.p, 1, L, AUDIOSYNC_CUDA_F64, d_res, sl.stream) != 0)
+            return -1;
+        ASC_CUDA_OK(cudaMemcpyAsync(sl.h_res.p, d_res, sizeof(audiosync_cuda_result), cudaMemcpyDeviceToHost, sl.stream));
+        ASC_CUDA_OK(cudaStreamSynchronize(sl.stream));
+        r = *static_cast<audiosync_cuda_result*>(sl.h_res.p);
     }
-    if (enqueue_batch(ctx, d, d_src_in, d_smp_in, 1, L, AUDIOSYNC_CUDA_F64, d_res, d.stream) != 0) {
-        ctx->resident.invalidate();
-        return -1;
-    }
-    ASC_CUDA_OK(cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result), cudaMemcpyDeviceToHost, d.stream));
-    ASC_CUDA_OK(cudaStreamSynchronize(d.stream));
-    const audiosync_cuda_result r = *static_cast<audiosync_cuda_result*>(d.h_results.p);
     *lag = (long)r.lag;                 // written before the NaN gate, like :259/:272
     *coefficient = r.coef;
     if (r.ret != 0) return -1;          // :276
@@ -1251,23 +1271,23 @@ double pearson_coefficient(double* source_start, const double* source_end, doubl
     if (cudaSetDevice(d.device) != cudaSuccess) return fail();
     const int n_chunks = (int)((n + PEARSON_CHUNK - 1) / PEARSON_CHUNK);
     if (d.in_src[0].ensure(sizeof(double) * n) != 0 || d.in_smp[0].ensure(sizeof(double) * n) != 0 ||
-        d.partials.ensure(sizeof(PearsonPartial) * n_chunks) != 0 ||
+        d.work.partials.ensure(sizeof(PearsonPartial) * n_chunks) != 0 ||
         d.results.ensure(sizeof(audiosync_cuda_result)) != 0 ||
         d.h_results.ensure(sizeof(audiosync_cuda_result)) != 0)
         return fail();
     cudaStream_t st = d.stream;
     auto* d_res = static_cast<audiosync_cuda_result*>(d.results.p);
-    auto* partials = static_cast<PearsonPartial*>(d.partials.p);
+    auto* partials = static_cast<PearsonPartial*>(d.work.partials.p);
     if (cudaMemcpyAsync(d.in_src[0].p, source_start, sizeof(double) * n, cudaMemcpyHostToDevice, st) != cudaSuccess ||
         cudaMemcpyAsync(d.in_smp[0].p, sample_start, sizeof(double) * n, cudaMemcpyHostToDevice, st) != cudaSuccess) {
         set_last_error("pearson_coefficient: upload failed");
         return fail();
     }
-    if (ensure_tickets(d, 1) != 0) return fail();
+    if (ensure_tickets(d.work, 1) != 0) return fail();
     if (launch(ctx, d, KC_PEARSON, st, [&] {
             pearson_kernel<double><<<dim3(n_chunks, 1), PEARSON_THREADS, 0, st>>>(
                 static_cast<const double*>(d.in_src[0].p), static_cast<const double*>(d.in_smp[0].p), 0, 0,
-                n, nullptr, n, partials, static_cast<unsigned int*>(d.tickets.p), n_chunks, d_res);
+                n, nullptr, n, partials, static_cast<unsigned int*>(d.work.tickets.p), n_chunks, d_res);
         }) != 0) return fail();
     if (cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) {

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -40,7 +41,6 @@ enum KernelClass {
     KC_COL_INV,      // K_C  inverse column pass + |r| argmax epilogue
     KC_SMALL_FFT,    // single-CTA transform for short lengths
     KC_PEARSON,      // window statistics + coefficient + result record
-    KC_PIPELINE,     // wave pipeline: K_A, K_B, K_C, K_P of four consecutive waves in one launch
     KC_COUNT
 };
 
@@ -60,9 +60,47 @@ struct PinnedBuf {
     void release();
 };
 
+// Pinned bounce buffers for PAGEABLE host inputs: the host memcpy of piece k + 1 overlaps the
+// DMA of piece k and the stream stays asynchronous (a cudaMemcpyAsync straight from pageable
+// memory is staged by the driver and blocks the calling thread for the whole transfer).
+struct StageRing {
+    static constexpr int N = 4;
+    static constexpr size_t PIECE = (size_t)4 << 20;
+    PinnedBuf buf[N];
+    cudaEvent_t ev[N] = {nullptr, nullptr, nullptr, nullptr};
+    bool pending[N] = {false, false, false, false};
+    int next = 0;
+    void release() {
+        for (int i = 0; i < N; i++) {
+            buf[i].release();
+            if (ev[i]) cudaEventDestroy(ev[i]);
+            ev[i] = nullptr; pending[i] = false;
+        }
+    }
+};
+
 struct ProfileRecord { int cls; cudaEvent_t e0, e1; };
 
 struct FftPlan;   // fft_plan.h
+
+// Scratch of one in-flight batch: everything enqueue_batch writes besides the caller's result
+// records.  A set is used by one stream at a time; `done` (recorded after every enqueue) orders a
+// later enqueue on a DIFFERENT stream behind the previous one, so stream-ordered callers may mix
+// streams on one context without corrupting planes, argmax keys or ticket counters.
+struct WorkSet {
+    DevBuf ws;            // transform workspace (direct: r[]; fft: A/B planes)
+    DevBuf peaks;         // PairPeak per in-flight pair
+    DevBuf partials;      // PearsonPartial
+    DevBuf tickets;       // per-pair completion counters of the Pearson kernel
+    cudaEvent_t done = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool used = false;
+    void release() {
+        ws.release(); peaks.release(); partials.release(); tickets.release();
+        if (done) cudaEventDestroy(done);
+        done = nullptr; used = false;
+    }
+};
 
 struct DeviceState {
     int device = -1;
@@ -70,18 +108,17 @@ struct DeviceState {
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;        // compute
     cudaStream_t copy_stream = nullptr;   // uploads for the host-facing batch call
-    DevBuf ws;            // transform workspace (direct: r[]; fft: A/B planes)
-    DevBuf peaks;         // PairPeak per in-flight pair
-    DevBuf partials;      // PearsonPartial
-    DevBuf tickets;       // per-pair completion counters of the Pearson kernel
+    WorkSet work;         // scratch of the batch entry points (serialised by the context mutex)
     DevBuf results;       // audiosync_cuda_result for host-facing calls
     DevBuf in_src[2], in_smp[2];          // device copies of host inputs (double buffered)
     PinnedBuf h_results;
-    PinnedBuf h_stage[2];                 // staging for pageable host inputs
+    StageRing stage;                      // bounce buffers for pageable host inputs
     cudaEvent_t ev_up[2] = {nullptr, nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr};
     std::map<size_t, std::shared_ptr<FftPlan>> plans;   // by sample_len
-    // profiling
+    std::mutex plan_mu;   // plans are built once and shared by concurrent callers
+    // profiling (prof_mu: launches may come from concurrent drop-in callers)
+    std::mutex prof_mu;
     std::vector<ProfileRecord> prof_pending;
     std::vector<cudaEvent_t> event_pool;
     uint64_t prof_launches[KC_COUNT] = {0};
@@ -107,13 +144,31 @@ struct ResidentSession {
 
 }  // namespace asc
 
+namespace asc {
+// One in-flight drop-in cross_correlation() call: its own stream, input mirrors, scratch and
+// result buffers, so concurrent callers overlap each other's upload and kernels like the
+// reference's callers do (its mutex covers only FFTW planning, src/cross_correlation.c:33-44).
+struct DropinSlot {
+    DeviceState* dev = nullptr;
+    cudaStream_t stream = nullptr;
+    WorkSet work;
+    DevBuf in_src, in_smp, d_res;
+    PinnedBuf h_res;
+    StageRing stage;
+    bool busy = false;
+};
+}  // namespace asc
+
 struct audiosync_cuda_ctx {
     std::vector<asc::DeviceState> devs;
     std::mutex mu;
+    std::vector<std::unique_ptr<asc::DropinSlot>> slots;   // drop-in callers (default context)
+    std::mutex slot_mu;
+    std::condition_variable slot_cv;
+    size_t slot_next = 0;
     int path = AUDIOSYNC_CUDA_PATH_AUTO;
     int wave_pairs = 0;
     bool profile = false;
-    bool pipeline = false;    // wave pipeline kernel for multi-wave batches (measured 2-4 % slower than a launch per stage)
     std::atomic<uint64_t> launches{0};
     asc::ResidentSession resident;           // drop-in cross_correlation() only (default context)
 

@@ -508,20 +508,6 @@ ASC_HD void fill_twiddles(cplx (&w)[R]) {
     });
 }
 
-// Passes with a short sub-stride (1 < S < ASC_TW_FULL_BELOW) hold ALL R - 1 rows of their
-// table -- a few hundred bytes that stay in L1 -- and read every twiddle instead of forming
-// the non-power-of-two ones as products (fp32-pipe work traded for L1 hits).
-#ifndef ASC_TW_FULL_BELOW
-#define ASC_TW_FULL_BELOW 0
-#endif
-constexpr bool tw_full(int S) { return S > 1 && S < ASC_TW_FULL_BELOW; }
-constexpr int tw_pow_rows(int radix) {
-    int n = 0;
-    for (int k = 1; k < radix; k *= 2) n++;
-    return n;
-}
-constexpr int tw_rows(int radix, int S) { return tw_full(S) ? radix - 1 : tw_pow_rows(radix); }
-
 template <int R>
 ASC_HD void pass_twiddles(const cplx* __restrict__ tw, int S, int j, cplx (&w)[R]) {
     static_for<1, R>([&](auto K) {
@@ -533,19 +519,6 @@ ASC_HD void pass_twiddles(const cplx* __restrict__ tw, int S, int j, cplx (&w)[R
     });
     fill_twiddles<R>(w);
 }
-// the same for a compile-time sub-stride: picks the full-table form where the plan has one
-template <int R, int S>
-ASC_HD void pass_twiddles_s(const cplx* __restrict__ tw, int j, cplx (&w)[R]) {
-    if constexpr (tw_full(S)) {
-        static_for<1, R>([&](auto K) {
-            constexpr int k = decltype(K)::value;
-            w[k] = ldg(tw + (k - 1) * S + j);
-        });
-    } else {
-        pass_twiddles<R>(tw, S, j, w);
-    }
-}
-
 // ---------------------------------------------------------------- radix list
 // In-place decimation-in-frequency order: pass p has radix r(p) and
 // sub-stride s(p) = n / (r(0) * ... * r(p)); after all passes position
@@ -578,7 +551,7 @@ struct RadixList {
     }
     static constexpr int tw_offset(int p) {
         int off = 0;
-        for (int i = 0; i < p; i++) off += tw_rows(r(i), stride(i)) * stride(i);
+        for (int i = 0; i < p; i++) off += npow(r(i)) * stride(i);
         return off;
     }
     static constexpr int tw_total() { return tw_offset(count); }

@@ -45,9 +45,6 @@ namespace asc {
 #ifndef ASC_COLFWD_STEP
 #define ASC_COLFWD_STEP 1    // K_A last pass: W_M^(n2*f0) stepped from item to item (see ColFwdKernel)
 #endif
-#ifndef ASC_ROW_GROUPS
-#define ASC_ROW_GROUPS 0     // K_B: source / sample rows (forward) and the two product rows (inverse) as two thread groups
-#endif
 #ifndef ASC_SPLIT_FENCE_EVERY
 #define ASC_SPLIT_FENCE_EVERY 2   // split phase: compiler fence after every n-th e1 step (0: none): four items in flight (none: +0.14, 1: +0.1 us/pair)
 #endif
@@ -284,7 +281,7 @@ struct ColFwdKernel {
                                 }
                             }
                             dft_reg<R, -1>(v);
-                            pass_twiddles_s<R, S>(p.tw + RL::tw_offset(ps), j, t);
+                            pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
                             buf[i0 * COL_T + c] = v[0];
                             static_for<1, R>([&](auto K) {
                                 constexpr int k = decltype(K)::value;
@@ -500,7 +497,7 @@ struct ColInvKernel {
                         if (i0 == S - 1 && c == COL_T - 1) mbar_inval(mbar);   // overwritten below
                     }
                     dft_reg<R, +1>(v);
-                    pass_twiddles_s<R, S>(p.tw + RL::tw_offset(ps), j, t);
+                    pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
                     buf[i0 * COL_T + c] = v[0];
                     static_for<1, R>([&](auto K) {
                         constexpr int k = decltype(K)::value;
@@ -659,8 +656,6 @@ struct RowFusedKernel {
     static_assert(M2 % 2 == 0, "row length must be even (16-byte chunks, bulk store size)");
     static_assert(P >= 2, "row plans need at least two passes");
     static constexpr bool ROW_TMA = ASC_ROW_TMA != 0;
-    static constexpr bool ROW_GROUPS = ASC_ROW_GROUPS != 0;
-    static_assert(!ROW_GROUPS || (NT % 64 == 0), "two thread groups of whole warps");
     static_assert(!ROW_TMA || (S0 * R0 == M2 && S0 >= 16), "pass 0 must own the last two points of a row as its last two items");
 
     // A pass whose sub-stride S is below 16 (but not 1) would have half-warps
@@ -784,7 +779,7 @@ struct RowFusedKernel {
                     row[i0] = v[0];
                     if constexpr (S > 1) {
                         cplx t[R];
-                        pass_twiddles_s<R, S>(p.tw + RL::tw_offset(ps), j, t);
+                        pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
                         static_for<1, R>([&](auto K) {
                             constexpr int k = decltype(K)::value;
                             row[i0 + k * S] = cmul(v[k], t[k]);
@@ -798,17 +793,9 @@ struct RowFusedKernel {
                 }
             }
         };
-        if constexpr (ROW_GROUPS) {
-            // the source rows and the sample rows are independent until the split: two thread
-            // groups, each with its own barrier between the passes (more independent phases per SM)
-            ex.template grouped_passes<2, P>([&](int grp, int lt, int gsz, auto PP) {
-                fwd_pass(PP, lt, gsz, 2 * grp, 1, nrows);
-            });
-        } else {
-            static_for<0, P>([&](auto PP) {
-                ex.phase([&](int tid) { fwd_pass(PP, tid, NT, 0, two ? 1 : 2, 2 * nrows); });   // slots 0,1,2,3 or 0,2
-            });
-        }
+        static_for<0, P>([&](auto PP) {
+            ex.phase([&](int tid) { fwd_pass(PP, tid, NT, 0, two ? 1 : 2, 2 * nrows); });   // slots 0,1,2,3 or 0,2
+        });
 
         // ---- split + conj-multiply + merge, in place into the source rows.
         {
@@ -917,7 +904,7 @@ struct RowFusedKernel {
                     v[0] = row[i0];
                     if constexpr (S > 1) {
                         cplx t[R];
-                        pass_twiddles_s<R, S>(p.tw + RL::tw_offset(ps), j, t);
+                        pass_twiddles<R>(p.tw + RL::tw_offset(ps), S, j, t);
                         static_for<1, R>([&](auto Q) {
                             constexpr int q = decltype(Q)::value;
                             v[q] = cmulc(row[i0 + q * S], t[q]);
@@ -947,15 +934,9 @@ struct RowFusedKernel {
                 if constexpr (last) fence_async_proxy();   // rows are read by the bulk store below
             }
         };
-        if constexpr (ROW_GROUPS) {
-            ex.template grouped_passes<2, P>([&](int grp, int lt, int gsz, auto PP) {
-                inv_pass(PP, lt, gsz, grp, grp < nrows ? 1 : 0);
-            });
-        } else {
-            static_for<0, P>([&](auto PP) {
-                ex.phase([&](int tid) { inv_pass(PP, tid, NT, 0, nrows); });
-            });
-        }
+        static_for<0, P>([&](auto PP) {
+            ex.phase([&](int tid) { inv_pass(PP, tid, NT, 0, nrows); });
+        });
 
         // ---- the product rows leave through the TMA unit, back in place (row k1 of plane 0).
         ex.single([&]() {
@@ -971,8 +952,7 @@ struct RowFusedKernel {
 // kernel bodies (shared with the CPU emulator) instantiate cleanly; the host
 // side of them is never called.
 struct DeviceExec {
-    // Block coordinates the kernel body sees.  The plain entry copies blockIdx; the wave
-    // pipeline kernel (pipeline.cuh) assigns them from its role schedule.
+    // Block coordinates the kernel body sees (the entry copies blockIdx).
     int x_ = 0, y_ = 0, z_ = 0;
     ASC_HD int bx() const { return x_; }
     ASC_HD int by() const { return y_; }
@@ -981,23 +961,6 @@ struct DeviceExec {
     ASC_HD void phase(F&& f) {
 #if defined(__CUDA_ARCH__)
         f((int)threadIdx.x);
-        __syncthreads();
-#endif
-    }
-    // NPASS passes on NG independent thread groups (blockDim / NG threads each, whole warps):
-    // f(group, local thread, group size, IC<pass>).  The passes of a group are separated by a
-    // barrier among that group's threads only (named barrier 1 + group); a CTA barrier follows.
-    template <int NG, int NPASS, class F>
-    ASC_HD void grouped_passes(F&& f) {
-#if defined(__CUDA_ARCH__)
-        const int gsz = (int)blockDim.x / NG;
-        const int grp = (int)threadIdx.x / gsz;
-        const int lt = (int)threadIdx.x - grp * gsz;
-        static_for<0, NPASS>([&](auto PS) {
-            f(grp, lt, gsz, PS);
-            if constexpr (decltype(PS)::value + 1 < NPASS)
-                asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(gsz) : "memory");
-        });
         __syncthreads();
 #endif
     }

@@ -26,62 +26,36 @@ struct Plan144k {
     using Col = RadixList<10, 6, 5>;     // M1 = 300
     using Row = RadixList<4, 8, 15>;     // M2 = 480
     static constexpr int NT_COL = 160, NT_ROW = 128;
-    static constexpr bool PIPELINE = false;
 };
 struct Plan288k {
     static constexpr long long L = 288000;
     using Col = RadixList<10, 6, 5>;     // M1 = 300
     using Row = RadixList<4, 16, 15>;    // M2 = 960
     static constexpr int NT_COL = 160, NT_ROW = 256;
-    static constexpr bool PIPELINE = false;
 };
 struct Plan480k {
     static constexpr long long L = 480000;
     using Col = RadixList<10, 10, 4>;    // M1 = 400
     using Row = RadixList<5, 16, 15>;    // M2 = 1200
     static constexpr int NT_COL = 320, NT_ROW = 320;
-    static constexpr bool PIPELINE = false;
 };
 struct Plan720k {
     static constexpr long long L = 720000;
     using Col = RadixList<10, 10, 6>;    // M1 = 600
     using Row = RadixList<5, 16, 15>;    // M2 = 1200
     static constexpr int NT_COL = 320, NT_ROW = 320;
-    static constexpr bool PIPELINE = false;
 };
 struct Plan960k {
     static constexpr long long L = 960000;
     using Col = RadixList<10, 10, 4>;    // M1 = 400
     using Row = RadixList<10, 16, 15>;   // M2 = 2400
     static constexpr int NT_COL = 320, NT_ROW = 320;
-    static constexpr bool PIPELINE = false;
 };
-#ifndef ASC_NT_COL_1440K
-#define ASC_NT_COL_1440K 320
-#endif
-#ifndef ASC_NT_ROW_1440K
-#define ASC_NT_ROW_1440K 320
-#endif
-#ifndef ASC_1440K_VARIANT
-#define ASC_1440K_VARIANT 0
-#endif
 struct Plan1440k {
     static constexpr long long L = 1440000;
-#if ASC_1440K_VARIANT == 0           // the product's plan
     using Col = RadixList<10, 10, 6>;    // M1 = 600
     using Row = RadixList<10, 16, 15>;   // M2 = 2400
-    static constexpr int NT_COL = ASC_NT_COL_1440K, NT_ROW = ASC_NT_ROW_1440K;
-    static constexpr bool PIPELINE = true;
-#elif ASC_1440K_VARIANT == 1         // measured alternative (slower), kept buildable for A/B runs
-    using Col = RadixList<20, 20>;       // M1 = 400: two passes per column tile
-    using Row = RadixList<15, 16, 15>;   // M2 = 3600: 115.2 KB of rows, 2 CTAs per SM
-#ifndef ASC_V1_NT_ROW
-#define ASC_V1_NT_ROW 480
-#endif
-    static constexpr int NT_COL = 320, NT_ROW = ASC_V1_NT_ROW;
-    static constexpr bool PIPELINE = false;
-#endif
-    // column radix orders 6.10.10 and 10.6.10 (last pass radix 10) measured: K_A +0.2 us/pair, K_C -0.03
+    static constexpr int NT_COL = 320, NT_ROW = 320;
 };
 
 using StaticPlans = std::tuple<Plan144k, Plan288k, Plan480k, Plan720k, Plan960k, Plan1440k>;
@@ -152,11 +126,6 @@ inline std::vector<cplx> build_pass_tables(const std::vector<int>& radices) {
     for (size_t p = 0; p < radices.size(); p++) {
         prod *= radices[p];
         const long long s = n / prod, m = s * radices[p];
-        if (tw_full((int)s)) {      // short sub-stride: every multiple (see pass_twiddles_s)
-            for (int k = 1; k < radices[p]; k++)
-                for (long long j = 0; j < s; j++) t.push_back(unit_root(j * k, m));
-            continue;
-        }
         for (int k = 1; k < radices[p]; k *= 2)
             for (long long j = 0; j < s; j++) t.push_back(unit_root(j * k, m));
     }

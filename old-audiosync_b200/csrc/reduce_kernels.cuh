@@ -172,8 +172,7 @@ constexpr int PEARSON_CHUNK = PEARSON_THREADS * PEARSON_PER_THREAD;   // 16384 (
 
 struct PearsonPartial { double sx, sy, sxx, syy, sxy; };
 
-// Shared scratch of one Pearson CTA (static in the stand-alone kernel, carved
-// from the dynamic buffer in the wave pipeline kernel).
+// Shared scratch of one Pearson CTA.
 template <int NTP>
 struct PearsonShared {
     double piv[2];

@@ -23,15 +23,6 @@ struct HostExec {
     void phase(F&& f) {
         for (int t = 0; t < nt; t++) f(t);
     }
-    template <int NG, int NPASS, class F>
-    void grouped_passes(F&& f) {
-        // groups are independent: run them one after the other, pass by pass
-        const int gsz = nt / NG;
-        for (int g = 0; g < NG; g++)
-            static_for<0, NPASS>([&](auto PS) {
-                for (int t = 0; t < gsz; t++) f(g, t, gsz, PS);
-            });
-    }
     template <class F>
     void single(F&& f) { f(); }
     bool any(bool b) const { return b; }

@@ -300,7 +300,7 @@ def test_residency_uploads_only_new_frames_and_matches(ac, capi, pid):
             res = [ac.cross_correlation_ptr(sb.ptr, mb.ptr, L) for L in Ls]
             c1, b1, h1 = ac.dropin_stats()
             out[resident] = (res, c1 - c0, b1 - b0, h1 - h0)
-        ac.set_residency(True)
+        ac.set_residency(False)
     assert out[False][0] == out[True][0]                       # identical (ret, lag, coef), bit for bit
     assert out[False][1:] == (6, 8 * 3 * sum(Ls), 0)
     assert out[True][1:] == (6, 8 * 3 * Ls[-1], 5)            # first call opens the session, five reuse it
@@ -343,6 +343,29 @@ def test_residency_guards(ac, capi):
     ac.cross_correlation_ptr(a.ctypes.data, b.ctypes.data, L1)
     ac.cross_correlation_ptr(a.ctypes.data, b.ctypes.data, L2)
     assert ac.dropin_stats()[2] == h
+    ac.set_residency(False)
+
+
+def test_default_reads_the_host_buffers_on_every_call(ac, capi):
+    """Reference semantics (src/cross_correlation.c reads its arguments afresh on every call):
+    residency is opt-in, so with the default setting an in-place edit of ONE already-submitted
+    sample between two growing calls on the same library-allocated buffers is seen.  The edit
+    plants an impulse pair that dominates the correlation at a known lag."""
+    L1, L2 = 144000, 288000
+    src, smp = capi.synth_pair(SEED, 4, L2)
+    with ac.RealBuffer(2 * L2) as sb, ac.RealBuffer(L2) as mb:
+        sb.array[:] = src; mb.array[:] = smp
+        h0 = ac.dropin_stats()[2]
+        first = ac.cross_correlation_ptr(sb.ptr, mb.ptr, L1)
+        assert first == ac.cross_correlation(src[:2 * L1], smp[:L1])
+        # one sample of each prefix rewritten in place: a huge coincident impulse at lag 777
+        sb.array[1000 + 777] = 1.0e6; mb.array[1000] = 1.0e6
+        edited_src = np.array(sb.array); edited_smp = np.array(mb.array)
+        second = ac.cross_correlation_ptr(sb.ptr, mb.ptr, L2)
+        o = capi.cross_correlation(edited_src, edited_smp)
+        assert o["lag"] == 777
+        assert second[:2] == (o["ret"], o["lag"]) and close(second[2], o["coef"])
+        assert ac.dropin_stats()[2] == h0                      # no resident session was used
 
 
 # ------------------------------------------------------------------ second peak / torch surface
@@ -528,57 +551,6 @@ def test_full_size_batch_recovers_injected_lags(ac, ctx, capi):
         assert (0.994 < c < 0.996) if pid % 4 != 3 else (0.79 < c < 0.81)
 
 
-@pytest.mark.parametrize("dtype_name", ["f32", "f64"])
-def test_wave_pipeline_matches_stage_per_launch(ac, capi, dtype_name):
-    """Multi-wave batches of the L = 1,440,000 plan run through the wave pipeline kernel (one
-    launch = K_A of wave k, K_B of wave k-1, K_C of wave k-2, K_P of wave k-3).  The transform
-    and argmax are the same code: raw index, lag and peak must be bit-identical to the
-    launch-per-stage path; the coefficient differs only by the Pearson chunking (fp32 partial
-    sums regrouped: 1e-6 relative allowed, 1e-4 is the path's tolerance).
-    Ragged last wave (11 pairs, waves of 3) and golden values are covered too."""
-    import torch
-    L, n = 1440000, 11
-    dtype = ac.F32 if dtype_name == "f32" else ac.F64
-    out = {}
-    for pipe in (False, True):
-        with ac.Context([0]) as c:
-            c.set_wave_pairs(3)
-            c.set_pipeline(pipe)
-            l0 = c.launch_count()
-            res, _, _ = _batch_on_device(ac, c, SEED, 0, n, L, dtype)
-            out[pipe] = (res.copy(), c.launch_count() - l0)
-    a, b = out[False][0], out[True][0]
-    for k in ("raw_index", "lag", "peak", "ret", "success"):
-        assert np.array_equal(a[k], b[k]), k
-    assert np.allclose(a["coef"], b["coef"], rtol=1e-6, atol=0)
-    # launches: synth + 4 per wave  vs  synth + (waves + 3)
-    assert out[False][1] == 1 + 4 * 4 and out[True][1] == 1 + 4 + 3
-    gold = {c["pair_id"]: c for c in _pairs() if c["L"] == L}
-    for pid in range(n):
-        assert int(b["lag"][pid]) == capi.synth_true_lag(SEED, pid, L)
-        if pid in gold:
-            g = gold[pid]
-            assert int(b["raw_index"][pid]) == g["raw_index"] and int(b["ret"][pid]) == g["ret"]
-            assert close(float(b["coef"][pid]), g["coef"]) and close(float(b["peak"][pid]), g["peak"])
-
-
-def test_wave_pipeline_repeated_calls_are_deterministic(ac):
-    """Ring buffers, ticket counters and peak slots are reused across calls: three back-to-back
-    pipelined batches (different pair ids, ragged sizes) each equal a fresh context's answer."""
-    L = 1440000
-    with ac.Context([0]) as c:
-        c.set_wave_pairs(2)
-        runs = [(_batch_on_device(ac, c, SEED + 9, first, n, L)[0].copy(), first, n)
-                for first, n in ((0, 7), (3, 5), (1, 9))]
-    for res, first, n in runs:
-        with ac.Context([0]) as c:
-            c.set_pipeline(False)
-            ref = _batch_on_device(ac, c, SEED + 9, first, n, L)[0]
-        for k in ("raw_index", "lag", "peak", "ret", "success"):
-            assert np.array_equal(res[k], ref[k]), (k, first, n)
-        assert np.allclose(res["coef"], ref["coef"], rtol=1e-6, atol=0)
-
-
 def test_scaling_and_negation_properties(ac, ctx, capi):
     """r is bilinear: scaling the sample by a power of two scales the peak exactly and leaves
     lag and coefficient unchanged; negating it flips the peak sign and the coefficient."""
@@ -619,18 +591,50 @@ def test_pinned_allocator_roundtrip(ac, capi):
 
 
 def test_concurrent_callers(ac, capi):
+    """Eight threads, three calls each, more callers than slots: every answer equals the
+    single-threaded one (each caller leases its own stream / mirrors / scratch)."""
     L = 144000
     pairs = [capi.synth_pair(SEED, i, L) for i in range(4)]
-    out = [None] * 4
+    single = [ac.cross_correlation(*p) for p in pairs]
+    out = [[None] * 3 for _ in range(8)]
 
-    def work(i):
-        out[i] = ac.cross_correlation(*pairs[i])
+    def work(t):
+        for k in range(3):
+            out[t][k] = ac.cross_correlation(*pairs[(t + k) % 4])
 
-    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
     [t.start() for t in th]
     [t.join() for t in th]
-    for i in range(4):
-        assert out[i][0] == 0 and out[i][1] == capi.synth_true_lag(SEED, i, L)
+    for t in range(8):
+        for k in range(3):
+            i = (t + k) % 4
+            assert out[t][k] == single[i]
+            assert out[t][k][0] == 0 and out[t][k][1] == capi.synth_true_lag(SEED, i, L)
+
+
+def test_streams_may_be_mixed_on_one_context(ac, ctx, capi):
+    """Stream-ordered device calls on DIFFERENT streams share the context's scratch: each call is
+    ordered behind the previous user of it, so back-to-back calls on two side streams (and the
+    library's own stream) without any host synchronisation all return the single-stream answers."""
+    import torch
+    L, n = 144000, 6
+    src = torch.empty(3, n * 2 * L, dtype=torch.float32, device="cuda:0")
+    smp = torch.empty(3, n * L, dtype=torch.float32, device="cuda:0")
+    res = torch.zeros(3, n * ac.RESULT_DTYPE.itemsize, dtype=torch.uint8, device="cuda:0")
+    for k in range(3):
+        ctx.synth_pairs(0, SEED + 40 + k, 0, n, L, ac.F32, src[k].data_ptr(), smp[k].data_ptr())
+    ctx.synchronize(0)
+    streams = [torch.cuda.Stream("cuda:0"), torch.cuda.Stream("cuda:0")]
+    for rep in range(4):
+        for k in range(3):
+            st = streams[k].cuda_stream if k < 2 else 0
+            ctx.xcorr_batch_device(0, src[k].data_ptr(), smp[k].data_ptr(), n, L, ac.F32, res[k].data_ptr(), st)
+    torch.cuda.synchronize()
+    ctx.synchronize(0)
+    for k in range(3):
+        r = res[k].cpu().numpy().view(ac.RESULT_DTYPE)
+        for i in range(n):
+            assert int(r["lag"][i]) == capi.synth_true_lag(SEED + 40 + k, i, L) and int(r["ret"][i]) == 0
 
 
 def test_profile_and_launch_accounting(ac, capi):
