@@ -112,7 +112,7 @@ enum {
     AUDIOSYNC_CUDA_PATH_DIRECT = 2   /* any length: O(L^2) time-domain correlation, fp64   */
 };
 
-/* One record per pair, 48 bytes, identical on host and device. */
+/* One record per pair, 64 bytes, identical on host and device. */
 typedef struct audiosync_cuda_result {
     int64_t lag;        /* folded lag in frames, [-L, L-1]  (cross_correlation.c:256-271)  */
     double  coef;       /* Pearson coefficient or NaN                                      */
@@ -120,9 +120,16 @@ typedef struct audiosync_cuda_result {
     int32_t ret;        /* 0 / -1 exactly as cross_correlation() would return              */
     int32_t success;    /* ret == 0 && coef >= 0.95   (src/audiosync.c:254)                */
     int64_t raw_index;  /* argmax index before folding, [0, 2L)                            */
-    double  second;     /* second peak: largest |r[i]|, i != raw_index (0 if none); the    */
-                        /* peak is unique when (|peak| - second) / |peak| is well above    */
-                        /* the arithmetic's 1e-6 -- a by-product of the argmax reduction   */
+    double  second;     /* second peak: largest |r[i]|, i != raw_index (0 if none) -- a    */
+                        /* by-product of the argmax reduction                              */
+    double  margin;     /* (|peak| - second) / |peak| (0 when peak == 0): the peak is      */
+                        /* unique when this is well above the arithmetic's 1e-6            */
+    double  ncc;        /* normalised correlation at the peak: peak / (N * sqrt(Sx2*Sy2)), */
+                        /* N = 2*sample_len, Sx2 / Sy2 = sum of squares of the two aligned */
+                        /* windows the coefficient is taken over (cross_correlation.c      */
+                        /* :256-271); for lag >= 0 the cosine similarity of the windows.   */
+                        /* Empty or all-zero window: peak / 0 (+-inf, or NaN when peak is   */
+                        /* 0 too).  SURVEY 8f rank 4.                                       */
 } audiosync_cuda_result;
 
 /* devices == NULL or n_devices <= 0: use every visible device.

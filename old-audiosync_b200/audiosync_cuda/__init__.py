@@ -35,10 +35,11 @@ MIN_CONFIDENCE = 0.95                                             # audiosync.h:
 SAMPLE_RATE = 48000                                               # audiosync.h:14
 INTERV_SAMPLE = [s * SAMPLE_RATE for s in (3, 6, 10, 15, 20, 30)]  # src/audiosync.c:50-57
 
-# mirrors struct audiosync_cuda_result (48 bytes)
+# mirrors struct audiosync_cuda_result (64 bytes)
 RESULT_DTYPE = np.dtype([("lag", "<i8"), ("coef", "<f8"), ("peak", "<f8"),
-                         ("ret", "<i4"), ("success", "<i4"), ("raw_index", "<i8"), ("second", "<f8")])
-assert RESULT_DTYPE.itemsize == 48
+                         ("ret", "<i4"), ("success", "<i4"), ("raw_index", "<i8"), ("second", "<f8"),
+                         ("margin", "<f8"), ("ncc", "<f8")])
+assert RESULT_DTYPE.itemsize == 64
 
 # every symbol include/audiosync_cuda.h declares
 EXPORTED_SYMBOLS = [
@@ -432,7 +433,7 @@ class Context:
 
     def xcorr_batch_records(self, sources_ptr: int, samples_ptr: int, n_pairs: int, sample_len: int,
                             dtype: int, memspace: int) -> np.ndarray:
-        """Whole result records (``RESULT_DTYPE``: lag, coef, peak, ret, success, raw_index, second)."""
+        """Whole result records (``RESULT_DTYPE``: lag, coef, peak, ret, success, raw_index, second, margin, ncc)."""
         res = np.zeros(n_pairs, RESULT_DTYPE)
         rc = lib().audiosync_cuda_xcorr_batch_results(self._h, sources_ptr, samples_ptr, n_pairs, sample_len,
                                                       dtype, memspace, res.ctypes.data)
@@ -445,7 +446,7 @@ class Context:
         ``sources`` [n, 2L] and ``samples`` [n, L]: contiguous float32 or float64 tensors on one
         device of this context.  The kernels are enqueued on torch's CURRENT stream of that
         device, reading the tensors in place; the 48-byte records land in ``out`` (a uint8
-        CUDA tensor of n * 48 bytes, allocated when omitted).  With ``sync`` the records come
+        CUDA tensor of n * 64 bytes, allocated when omitted).  With ``sync`` the records come
         back as a NumPy structured array (``RESULT_DTYPE``); otherwise the device tensor is
         returned and the caller orders later work on the same stream.
         """
@@ -464,7 +465,7 @@ class Context:
         if out is None:
             out = torch.empty(n * RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         elif out.device != dev or out.dtype != torch.uint8 or out.numel() < n * RESULT_DTYPE.itemsize:
-            raise ValueError("out must be a uint8 tensor of n * 48 bytes on the same device")
+            raise ValueError("out must be a uint8 tensor of n * 64 bytes on the same device")
         stream = torch.cuda.current_stream(dev).cuda_stream
         if stream == 0:
             # a NULL handle would select the library's own stream: order it after torch's default

@@ -181,8 +181,9 @@ struct PearsonShared {
 };
 
 // Finishes one pair from the summed statistics (thread 0 of the finishing CTA).
+// px, py: the pivots the sums were shifted by (sum x^2 = sxx + 2 px sx + n px^2).
 __device__ __forceinline__ void pearson_finish(const PearsonPartial& s, const Window& w, long long raw,
-                                               double peak, double second,
+                                               double peak, double second, double px, double py, long long L,
                                                audiosync_cuda_result* __restrict__ out)
 {
     // n == 0 -> 0/0 = NaN, like the reference's empty pointer range.
@@ -199,6 +200,13 @@ __device__ __forceinline__ void pearson_finish(const PearsonPartial& s, const Wi
     r.success = (r.ret == 0 && coef >= 0.95) ? 1 : 0;       // src/audiosync.c:254
     r.raw_index = raw;
     r.second = second;
+    // peak quality: margin of the peak over the second peak, and the peak
+    // normalised by the energies of the two windows (unshifted sums of squares)
+    const double ap = fabs(peak);
+    r.margin = ap > 0.0 ? (ap - second) / ap : (ap == 0.0 ? 0.0 : peak);   // NaN peak -> NaN
+    const double ex = s.sxx + 2.0 * px * s.sx + n * px * px;
+    const double ey = s.syy + 2.0 * py * s.sy + n * py * py;
+    r.ncc = peak / (2.0 * (double)L * sqrt(ex * ey));
     *out = r;
 }
 
@@ -352,8 +360,21 @@ __device__ __forceinline__ void pearson_block(
             s.syy += __shfl_xor_sync(0xffffffffu, s.syy, o);
             s.sxy += __shfl_xor_sync(0xffffffffu, s.sxy, o);
         }
+        // the pivots again (this CTA's chunk may lie beyond the window and never have formed them);
+        // fp32 inputs were shifted by the pivots rounded to fp32
+        double px = 0.0, py = 0.0;
+        if (w.n > 0) {
+            const long long k = ((long long)t * w.n) >> 5;
+            px = (double)x[k]; py = (double)y[k];
+            for (int o = 16; o > 0; o >>= 1) {
+                px += __shfl_xor_sync(0xffffffffu, px, o);
+                py += __shfl_xor_sync(0xffffffffu, py, o);
+            }
+            px *= (1.0 / 32.0); py *= (1.0 / 32.0);
+            if constexpr (sizeof(T) == 4) { px = (double)(float)px; py = (double)(float)py; }
+        }
         if (t == 0) {
-            pearson_finish(s, w, raw, peak, second, results + pair);
+            pearson_finish(s, w, raw, peak, second, px, py, L, results + pair);
             tickets[pair] = 0u;       // ready for the next wave
         }
     }

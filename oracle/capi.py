@@ -120,8 +120,11 @@ def cross_correlation(source: np.ndarray, sample: np.ndarray):
     lag, coef, ex = C.c_long(0), C.c_double(0.0), OracleExtra()
     ret = lib().oracle_cross_correlation(_dptr(source), _dptr(sample), L,
                                          C.byref(lag), C.byref(coef), C.byref(ex))
-    return dict(ret=ret, lag=lag.value, coef=coef.value, raw_index=ex.raw_index,
-                peak=ex.peak, second=ex.second, r0=ex.r0)
+    out = dict(ret=ret, lag=lag.value, coef=coef.value, raw_index=ex.raw_index,
+               peak=ex.peak, second=ex.second, r0=ex.r0)
+    from . import xcorr_numpy
+    out.update(xcorr_numpy.peak_quality(source, sample, ex.raw_index, ex.peak, ex.second))
+    return out
 
 
 def ref_cross_correlation(source: np.ndarray, sample: np.ndarray):
@@ -129,8 +132,10 @@ def ref_cross_correlation(source: np.ndarray, sample: np.ndarray):
     R = ref_lib()
     if R is None:
         raise RuntimeError("oracle/_ref/libaudiosync_ref.so not built")
-    source = np.array(source, dtype=np.float64, copy=True)
-    sample = np.array(sample, dtype=np.float64, copy=True)
+    # no copies here: the reference never writes to its inputs (src/cross_correlation.c:130-132),
+    # and this call sits inside bench.py's timed loops
+    source = np.ascontiguousarray(source, dtype=np.float64)
+    sample = np.ascontiguousarray(sample, dtype=np.float64)
     L = sample.shape[0]
     lag, coef = C.c_long(0), C.c_double(0.0)
     ret = R.cross_correlation(_dptr(source), _dptr(sample), L, C.byref(lag), C.byref(coef))

@@ -52,8 +52,33 @@ def correlation(source: np.ndarray, sample: np.ndarray) -> np.ndarray:
     return np.fft.irfft(fa * np.conj(fb), n=N) * N
 
 
+def windows(source: np.ndarray, sample: np.ndarray, idx: int):
+    """Fold + aligned windows of src/cross_correlation.c:256-271: (lag, source window, sample window)."""
+    L = sample.shape[0]
+    if idx >= L:                                  # :256-263
+        lag = (idx % L) - L
+        return lag, source[0:L + lag], sample[-lag:L]
+    return idx, source[idx:idx + L], sample[0:L]  # :264-270
+
+
+def peak_quality(source: np.ndarray, sample: np.ndarray, raw_index: int, peak: float, second: float):
+    """Peak-quality outputs of the batched records (not in the reference, which
+    only thresholds the Pearson coefficient): margin of the peak over the second peak and the
+    peak normalised by the energies of the aligned windows of :256-271,
+        margin = (|peak| - second) / |peak|            (0 when peak == 0)
+        ncc    = peak / (N * sqrt(sum wx^2 * sum wy^2)),  N = 2L  (peak carries FFTW's factor N)."""
+    source = np.asarray(source, np.float64); sample = np.asarray(sample, np.float64)
+    L = sample.shape[0]
+    _, wx, wy = windows(source, sample, raw_index)
+    ap = abs(peak)
+    margin = (ap - second) / ap if ap > 0 else (0.0 if ap == 0 else float("nan"))
+    with np.errstate(all="ignore"):
+        ncc = float(np.float64(peak) / (np.float64(2 * L) * np.sqrt(np.sum(wx * wx) * np.sum(wy * wy))))
+    return dict(margin=float(margin), ncc=ncc)
+
+
 def cross_correlation(source: np.ndarray, sample: np.ndarray):
-    """Returns dict(ret, lag, coef, raw_index, peak, second)."""
+    """Returns dict(ret, lag, coef, raw_index, peak, second, margin, ncc)."""
     source = np.asarray(source, np.float64)
     sample = np.asarray(sample, np.float64)
     L = sample.shape[0]
@@ -72,8 +97,9 @@ def cross_correlation(source: np.ndarray, sample: np.ndarray):
         wy = sample[0:L]
     coef = pearson(wx, wy)
     ret = -1 if coef != coef else 0               # :276
-    return dict(ret=ret, lag=int(lag), coef=coef, raw_index=idx, peak=float(r[idx]),
-                second=second)
+    out = dict(ret=ret, lag=int(lag), coef=coef, raw_index=idx, peak=float(r[idx]), second=second)
+    out.update(peak_quality(source, sample, idx, out["peak"], second))
+    return out
 
 
 # ------------------------------------------------------------ synthetic pairs

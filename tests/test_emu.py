@@ -157,3 +157,22 @@ def test_tma_tile_boxes_cover_the_staged_rows(emu):
             assert 0 <= r0 and r0 + br <= rows
             covered.update(range(r0, r0 + br))
         assert covered == set(range(rows))
+
+
+def _hard_144k():
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    d = json.load(open(os.path.join(HERE, "golden", "hard.json")))
+    return [c for c in d["cases"] if c["L"] == 144000]
+
+
+@pytest.mark.parametrize("case", _hard_144k(), ids=lambda c: "%s-%.0e" % (c["kind"], c["margin"] or 0))
+def test_emulated_kernels_resolve_low_margins_and_edges(emu, case):
+    """The fp32 four-step kernel bodies on the hard goldens at L = 144,000: peaks 3e-4 .. 1e-2 apart,
+    lags 0 / +-1 / L-1, idx == L, idx == L + 1 and the all-zero sample -- raw index bit-exact."""
+    import hard_cases as hc
+    src, smp = hc.build(case, np.float32)
+    idx, peak, used = run_emu(emu, src, smp)
+    assert used == 0 and idx == case["raw_index"]
+    assert abs(peak - case["peak"]) <= 1e-4 * abs(case["peak"])
+    assert abs(emu.emu_last_second() - case["second"]) <= 1e-4 * case["second"] + 1e-6 * abs(case["peak"])

@@ -16,6 +16,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+import sys
+sys.path.insert(0, os.path.join(HERE, "golden"))
 KAT = json.load(open(os.path.join(HERE, "golden", "kat.json")))
 SYNTH = json.load(open(os.path.join(HERE, "golden", "synth.json")))
 RTOL = 1e-4
@@ -45,6 +47,8 @@ def ctx(ac):
 def close(a, b, rtol=RTOL):
     if a != a or b != b:
         return a != a and b != b
+    if a == b:                       # also equal infinities
+        return True
     return abs(a - b) <= rtol * max(abs(a), abs(b), 1e-300)
 
 
@@ -149,6 +153,51 @@ def test_device_generator_is_bit_identical(ac, ctx, capi):
         for i in range(n):
             s, p = capi.synth_pair(SEED + 7, 3 + i, L, npdt)
             assert np.array_equal(hs[i], s) and np.array_equal(hp[i], p)
+
+
+# ------------------------------------------------------------------ low-margin and edge goldens
+HARD = json.load(open(os.path.join(HERE, "golden", "hard.json")))
+
+
+def _hard_id(c):
+    return "%s-L%d-%s" % (c["kind"], c["L"], "m%.0e" % c["margin"] if c["kind"] in ("echo", "periodic")
+                          else "-".join("%s%s" % kv for kv in sorted(c["params"].items()) if kv[0] != "seed"))
+
+
+def _check_hard(c, ret, lag, coef, rec=None):
+    assert ret == c["ret"] and lag == c["lag"]                       # bit-exact lag, identical ret
+    if c["coef"] is None:
+        assert coef != coef
+    else:
+        assert close(coef, c["coef"])
+    assert (ret == 0 and coef >= 0.95) == c["success"]
+    if rec is not None:
+        assert int(rec["raw_index"]) == c["raw_index"] and bool(rec["success"]) == c["success"]
+        assert close(float(rec["peak"]), c["peak"])
+        assert abs(float(rec["second"]) - c["second"]) <= RTOL * c["second"] + 1e-6 * abs(c["peak"])
+        assert abs(float(rec["margin"]) - c["margin"]) <= 3e-5
+        if c["ncc"] is None:
+            assert rec["ncc"] != rec["ncc"]
+        else:
+            assert close(float(rec["ncc"]), c["ncc"])
+
+
+@pytest.mark.parametrize("case", HARD["cases"], ids=_hard_id)
+def test_hard_goldens_dropin_and_batch(ac, ctx, case):
+    """Outputs of the compiled reference on inputs an fp32 transform can get wrong (tests/golden/
+    hard_cases.py): two lags 3e-4 / 1e-3 / 1e-2 of the peak apart at every interval length, lags
+    0, +-1, L-1, the fold boundary idx == L and L + 1 (src/cross_correlation.c:256-276) and the
+    all-zero sample, at L = 144,000 and 1,440,000 -- through the unchanged C signature (f64
+    host) and through the batched records (fp32, the headline configuration)."""
+    import hard_cases as hc
+    L = case["L"]
+    src, smp = hc.build(case, np.float64)
+    ret, lag, coef = ac.cross_correlation(src, smp)
+    _check_hard(case, ret, lag, coef)
+    s32, m32 = hc.build(case, np.float32)
+    assert np.array_equal(s32.astype(np.float64), src)                  # exact in fp32 by construction
+    rec = ctx.xcorr_batch_records(s32.ctypes.data, m32.ctypes.data, 1, L, ac.F32, ac.HOST)[0]
+    _check_hard(case, int(rec["ret"]), int(rec["lag"]), float(rec["coef"]), rec)
 
 
 # ------------------------------------------------------------------ oracle, many shapes
@@ -386,6 +435,41 @@ def test_second_peak_all_paths_vs_oracle(ac, capi, L):
                 assert int(rec["raw_index"][i]) == o["raw_index"] and int(rec["lag"][i]) == o["lag"]
                 assert close(float(rec["peak"][i]), o["peak"])
                 assert abs(float(rec["second"][i]) - o["second"]) <= RTOL * o["second"] + 1e-6 * abs(o["peak"])
+                # peak quality: margin and normalised correlation vs the NumPy restatement
+                assert abs(float(rec["margin"][i]) - o["margin"]) <= 1e-4
+                assert close(float(rec["ncc"][i]), o["ncc"])
+
+
+@pytest.mark.parametrize("dtype_name", ["f32", "f64"])
+def test_peak_quality_both_lag_signs_and_degenerate_windows(ac, ctx, capi, dtype_name):
+    """margin / ncc of the result records (oracle/xcorr_numpy.py: peak_quality).  Positive lags: ncc
+    is the cosine similarity of the aligned windows; negative lags use the shorter window of
+    cross_correlation.c:256-263; an empty window (idx == L) gives peak / 0 = inf, an all-zero one 0 / 0 = NaN."""
+    from oracle import xcorr_numpy
+    npdt = np.float32 if dtype_name == "f32" else np.float64
+    dt = ac.F32 if dtype_name == "f32" else ac.F64
+    L, n = 144000, 8
+    srcs = np.empty((n, 2 * L), npdt); smps = np.empty((n, L), npdt)
+    for i in range(n):
+        srcs[i], smps[i] = capi.synth_pair(SEED + 17, i, L, npdt)
+    rec = ctx.xcorr_batch_records(srcs.ctypes.data, smps.ctypes.data, n, L, dt, ac.HOST)
+    signs = set()
+    for i in range(n):
+        o = xcorr_numpy.cross_correlation(srcs[i].astype(np.float64), smps[i].astype(np.float64))
+        assert int(rec["raw_index"][i]) == o["raw_index"]
+        signs.add(o["lag"] >= 0)
+        assert abs(float(rec["margin"][i]) - o["margin"]) <= 1e-4 and 0.9 < o["margin"] <= 1.0
+        assert close(float(rec["ncc"][i]), o["ncc"])
+        if o["lag"] >= 0:
+            assert -1.0 <= float(rec["ncc"][i]) <= 1.0
+    assert signs == {True, False}
+    # empty window (idx == L) and all-zero sample: NaN, like the coefficient
+    src = np.zeros((1, 2 * L), npdt); smp = np.zeros((1, L), npdt); smp[0, 0] = 1.0; src[0, L] = 1.0
+    r = ctx.xcorr_batch_records(src.ctypes.data, smp.ctypes.data, 1, L, dt, ac.HOST)
+    assert int(r["raw_index"][0]) == L and np.isinf(r["ncc"][0]) and float(r["margin"][0]) > 0.9999   # peak / 0
+    smp[:] = 0
+    r = ctx.xcorr_batch_records(src.ctypes.data, smp.ctypes.data, 1, L, dt, ac.HOST)
+    assert float(r["peak"][0]) == 0.0 and float(r["margin"][0]) == 0.0 and r["ncc"][0] != r["ncc"][0]
 
 
 def test_second_peak_of_a_tie_equals_the_peak(ac):

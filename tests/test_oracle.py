@@ -167,3 +167,51 @@ def test_synth_batch_threads():
         assert np.array_equal(a[k], b[k], equal_nan=True)
     for pid in range(6):
         assert a["lags"][pid] == capi.synth_true_lag(0x5EED, pid, 3600)
+
+
+def test_peak_quality_restatement_against_brute_force():
+    """oracle/xcorr_numpy.peak_quality (margin, normalised correlation) against
+    a direct evaluation: r by the O(L^2) circular sum, windows by the reference's fold."""
+    from oracle import xcorr_numpy
+    rng = np.random.default_rng(5)
+    for L, shift in ((16, 3), (50, -7), (64, 0), (33, -5)):
+        base = rng.standard_normal(3 * L)
+        src = base[L:3 * L].copy()
+        smp = base[L + shift:2 * L + shift] + 0.05 * rng.standard_normal(L)
+        N = 2 * L
+        r = np.array([N * sum(src[(n + j) % N] * smp[n] for n in range(L)) for j in range(N)])
+        o = xcorr_numpy.cross_correlation(src, smp)
+        idx = xcorr_numpy.max_abs_index(r)
+        assert o["raw_index"] == idx and o["lag"] == shift
+        mag = np.abs(r); mag[idx] = -1
+        assert abs(o["margin"] - (abs(r[idx]) - mag.max()) / abs(r[idx])) < 1e-9
+        lag, wx, wy = xcorr_numpy.windows(src, smp, idx)
+        assert lag == shift
+        assert abs(o["ncc"] - r[idx] / (N * np.sqrt((wx * wx).sum() * (wy * wy).sum()))) < 1e-9
+        if shift >= 0:
+            assert abs(o["ncc"] - (wx * wy).sum() / np.sqrt((wx * wx).sum() * (wy * wy).sum())) < 1e-9
+        c = capi.cross_correlation(src, smp)                  # the C restatement carries the same fields
+        assert abs(c["margin"] - o["margin"]) < 1e-9 and abs(c["ncc"] - o["ncc"]) < 1e-9
+
+
+def _hard_cases(max_L):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hard.json")))
+    return [c for c in d["cases"] if c["L"] <= max_L]
+
+
+@pytest.mark.parametrize("case", _hard_cases(288000), ids=lambda c: "%s-L%d-%.0e" % (c["kind"], c["L"], c["margin"] or 0))
+def test_oracle_reproduces_hard_goldens(case):
+    """The restatement and the NumPy cross-check against the compiled reference's recorded outputs on
+    the low-margin / edge inputs (tests/golden/hard.json; generator tests/golden/make_hard.py)."""
+    import hard_cases as hc
+    src, smp = hc.build(case)
+    for o in (capi.cross_correlation(src, smp), xn.cross_correlation(src, smp)):
+        assert (o["ret"], o["lag"], o["raw_index"]) == (case["ret"], case["lag"], case["raw_index"])
+        if case["coef"] is None:
+            assert o["coef"] != o["coef"]
+        else:
+            assert abs(o["coef"] - case["coef"]) <= 1e-9 * abs(case["coef"])
+        assert abs(o["peak"] - case["peak"]) <= 1e-9 * abs(case["peak"]) + 1e-12
+        assert abs(o["margin"] - case["margin"]) <= 1e-7

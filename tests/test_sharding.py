@@ -44,7 +44,8 @@ def _records_for(first, count):
         s, p = capi.synth_pair(SEED, first + i, L)
         o = capi.cross_correlation(s, p)
         rec[i] = (o["lag"], o["coef"], o["peak"], o["ret"],
-                  int(o["ret"] == 0 and o["coef"] >= ac.MIN_CONFIDENCE), o["raw_index"], o["second"])
+                  int(o["ret"] == 0 and o["coef"] >= ac.MIN_CONFIDENCE), o["raw_index"], o["second"],
+                  o["margin"], o["ncc"])
     return rec
 
 
