@@ -105,11 +105,19 @@ typedef struct audiosync_cuda_ctx audiosync_cuda_ctx;
 enum { AUDIOSYNC_CUDA_F32 = 0, AUDIOSYNC_CUDA_F64 = 1 };
 enum { AUDIOSYNC_CUDA_HOST = 0, AUDIOSYNC_CUDA_DEVICE = 1 };
 
-/* Which transform path a given sample_len takes. */
+/* Which transform path a given sample_len takes.  AUTO: the static four-step kernels for the
+ * six lengths of the reference's interval schedule (src/audiosync.c:50-57); the fp64
+ * time-domain kernel below 4,096 frames (where the reference's own unit tests live); a
+ * single-CTA FFT for short even 2/3/5-smooth lengths; the runtime-radix four-step kernels for
+ * EVERY other length -- 2/3/5-smooth lengths at their own size, all others (odd, prime
+ * factors > 5) embedded in the next suitable smooth length N' >= 3 * sample_len, which gives the
+ * same r[0 .. 2L) -- so that, like the reference's per-call FFTW plans
+ * (src/cross_correlation.c:34, :237), every length costs O(N log N).  Lengths for which no plan
+ * fits the device (above ~7 million frames) are refused with -1. */
 enum {
     AUDIOSYNC_CUDA_PATH_AUTO   = 0,
-    AUDIOSYNC_CUDA_PATH_FFT    = 1,  /* 2/3/5-smooth even lengths: Stockham/four-step FFT  */
-    AUDIOSYNC_CUDA_PATH_DIRECT = 2   /* any length: O(L^2) time-domain correlation, fp64   */
+    AUDIOSYNC_CUDA_PATH_FFT    = 1,  /* a transform wherever one exists (also below 4,096 frames)   */
+    AUDIOSYNC_CUDA_PATH_DIRECT = 2   /* O(L^2) time-domain correlation, fp64; up to 65,536 frames   */
 };
 
 /* One record per pair, 64 bytes, identical on host and device. */
@@ -217,6 +225,12 @@ int audiosync_cuda_synchronize(audiosync_cuda_ctx *ctx, int device);
 /* Tuning / test knobs (default behaviour matches the reference's). */
 int  audiosync_cuda_set_path(audiosync_cuda_ctx *ctx, int path);          /* AUTO / FFT / DIRECT */
 int  audiosync_cuda_set_wave_pairs(audiosync_cuda_ctx *ctx, int pairs);   /* pairs per kernel wave, 0 = auto */
+/* fp64-ARITHMETIC validation mode: every transform runs on the double-precision instantiation
+ * of the runtime-radix kernels (the reference computes in double complex throughout,
+ * src/cross_correlation.c:187-239) and the argmax on full double keys -- several times slower
+ * than the fp32 product path, peak values within 1e-12 of an fp64 FFT.  A second oracle for the
+ * fp32 kernels; env AUDIOSYNC_CUDA_PRECISE=1 selects it for the drop-in cross_correlation(). */
+int  audiosync_cuda_set_precise(audiosync_cuda_ctx *ctx, int on);
 void audiosync_cuda_set_debug(int on);                                    /* same effect as global_debug */
 /* Describes the plan for a length, e.g.
  * "fft L=1440000 M1=600 M2=2400 col=6x10x10 row=8x10x30 static". Returns the

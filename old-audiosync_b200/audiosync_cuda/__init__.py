@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     "audiosync_cuda_create", "audiosync_cuda_destroy", "audiosync_cuda_device_count",
     "audiosync_cuda_xcorr_batch", "audiosync_cuda_xcorr_batch_results", "audiosync_cuda_xcorr_batch_device",
     "audiosync_cuda_synth_pairs", "audiosync_cuda_synchronize",
-    "audiosync_cuda_set_path", "audiosync_cuda_set_wave_pairs", "audiosync_cuda_set_debug",
+    "audiosync_cuda_set_path", "audiosync_cuda_set_wave_pairs", "audiosync_cuda_set_debug", "audiosync_cuda_set_precise",
     "audiosync_cuda_set_residency", "audiosync_cuda_dropin_stats",
     "audiosync_cuda_pool_create", "audiosync_cuda_pool_destroy", "audiosync_cuda_pool_reset",
     "audiosync_cuda_pool_append", "audiosync_cuda_pool_fill", "audiosync_cuda_pool_run",
@@ -112,6 +112,8 @@ def lib() -> C.CDLL:
     L.audiosync_cuda_synchronize.argtypes = [vp, i32]
     L.audiosync_cuda_set_path.restype = i32
     L.audiosync_cuda_set_path.argtypes = [vp, i32]
+    L.audiosync_cuda_set_precise.restype = i32
+    L.audiosync_cuda_set_precise.argtypes = [vp, i32]
     L.audiosync_cuda_set_wave_pairs.restype = i32
     L.audiosync_cuda_set_wave_pairs.argtypes = [vp, i32]
     L.audiosync_cuda_set_residency.restype = None
@@ -380,6 +382,10 @@ class Context:
 
     def set_path(self, path: int):
         self._check(lib().audiosync_cuda_set_path(self._h, path), "set_path")
+
+    def set_precise(self, on: bool):
+        """fp64 arithmetic in the transforms (validation mode; see include/audiosync_cuda.h)."""
+        self._check(lib().audiosync_cuda_set_precise(self._h, 1 if on else 0), "set_precise")
 
     def set_wave_pairs(self, pairs: int):
         self._check(lib().audiosync_cuda_set_wave_pairs(self._h, pairs), "set_wave_pairs")

@@ -21,6 +21,7 @@
 #include "fft_kernels.cuh"
 #include "fft_plan.h"
 #include "fft_small.cuh"
+#include "gen_plan.h"
 #include "reduce_kernels.cuh"
 
 // The reference defines `volatile int global_debug` in src/audiosync.c:37 and its
@@ -94,6 +95,9 @@ struct FftPlan {
     DevBuf col_tw, col_tc, row_tw, row_rev, row_tab, m_lo, m_hi;   // static four-step
     DevBuf wm, wn;                                   // short-length kernel
     SmallPlan small;
+    GenShape gen{};                                  // runtime-radix four-step kernels
+    DevBuf g_wcol, g_wrow, g_lo, g_hi, g_p2f_col, g_p2f_row, g_f2p_row;
+    double peak_scale = 1.0;                         // r_reference = r_kernel * peak_scale
     // enqueues the transform kernels for `pairs` pairs (planes/r in ws)
     // (src, smp, dtype, src_pitch, smp_pitch [elements between pairs], workspace, peaks, pairs, stream)
     std::function<int(audiosync_cuda_ctx*, DeviceState&, const void*, const void*, int, long long, long long,
@@ -101,12 +105,15 @@ struct FftPlan {
     ~FftPlan() {
         col_tw.release(); col_tc.release(); row_tw.release(); row_rev.release(); row_tab.release(); m_lo.release(); m_hi.release();
         wm.release(); wn.release();
+        g_wcol.release(); g_wrow.release(); g_lo.release(); g_hi.release();
+        g_p2f_col.release(); g_p2f_row.release(); g_f2p_row.release();
     }
 };
 
-static int upload(DevBuf& b, const std::vector<cplx>& v) {
-    if (b.ensure(v.size() * sizeof(cplx)) != 0) return -1;
-    ASC_CUDA_OK(cudaMemcpy(b.p, v.data(), v.size() * sizeof(cplx), cudaMemcpyHostToDevice));
+template <class E>
+static int upload(DevBuf& b, const std::vector<E>& v) {
+    if (b.ensure(v.size() * sizeof(E)) != 0) return -1;
+    ASC_CUDA_OK(cudaMemcpy(b.p, v.data(), v.size() * sizeof(E), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -360,6 +367,95 @@ static int build_small_plan(FftPlan* plan, long long L) {
     return 0;
 }
 
+// ------------------------------------------------- runtime-radix four-step plans (any length)
+template <class K>
+static int prepare_gen_kernel(size_t smem) {
+    if (smem > 48 * 1024)
+        ASC_CUDA_OK(cudaFuncSetAttribute(gen_kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return 0;
+}
+
+template <typename T, typename InT>
+static int run_generic_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
+                            long long sp, long long mp, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
+    typedef typename GenTraits<T>::C C;
+    const GenShape& sh = plan->gen;
+    C* planes = static_cast<C*>(ws);
+    const C* wcol = static_cast<const C*>(plan->g_wcol.p);
+    const C* wrow = static_cast<const C*>(plan->g_wrow.p);
+    const C* lo = static_cast<const C*>(plan->g_lo.p);
+    const C* hi = static_cast<const C*>(plan->g_hi.p);
+    const int* p2f_col = static_cast<const int*>(plan->g_p2f_col.p);
+    const int* p2f_row = static_cast<const int*>(plan->g_p2f_row.p);
+    const int* f2p_row = static_cast<const int*>(plan->g_f2p_row.p);
+    {
+        using K = GenColFwdKernel<T, InT>;
+        typename K::Params p{static_cast<const InT*>(src), static_cast<const InT*>(smp), planes, peaks, wcol, lo, hi,
+                             p2f_col, sh, sp, mp};
+        const dim3 grid((sh.M2 + K::CT - 1) / K::CT, 2, pairs);
+        if (launch(ctx, d, KC_COL_FWD, st, [&] {
+                launch_stage(gen_kernel_entry<K>, grid, dim3(K::THREADS), K::smem_bytes(sh), st, p);
+            }) != 0) return -1;
+    }
+    {
+        using K = GenRowFusedKernel<T>;
+        typename K::Params p{planes, wrow, lo, hi, p2f_row, f2p_row, sh};
+        const dim3 grid(sh.M1 / 2 + 1, 1, pairs);
+        if (launch(ctx, d, KC_ROW_FUSED, st, [&] {
+                launch_stage(gen_kernel_entry<K>, grid, dim3(K::THREADS), K::smem_bytes(sh), st, p);
+            }) != 0) return -1;
+    }
+    {
+        using K = GenColInvKernel<T>;
+        typename K::Params p{planes, peaks, wcol, p2f_col, sh, reinterpret_cast<T*>(planes)};
+        const dim3 grid(pairs, (sh.M2 + K::CT - 1) / K::CT, 1);
+        if (launch(ctx, d, KC_COL_INV, st, [&] {
+                launch_stage(gen_kernel_entry<K>, grid, dim3(K::THREADS), K::smem_bytes(sh), st, p);
+            }) != 0) return -1;
+    }
+    if constexpr (sizeof(T) == 8) {
+        // fp64: r[0 .. 2L) of pair i sits in its (dead) sample plane; full double keys
+        const double* r = reinterpret_cast<const double*>(planes) + 2 * sh.M;
+        if (launch(ctx, d, KC_ARGMAX_F64, st, [&] {
+                argmax_f64_kernel<<<pairs, 1024, 0, st>>>(r, 2 * sh.L, 4 * sh.M, peaks);
+            }) != 0) return -1;
+    }
+    return 0;
+}
+
+template <typename T>
+static int build_generic_plan_t(FftPlan* plan) {
+    typedef typename GenTraits<T>::C C;
+    const GenShape& sh = plan->gen;
+    const GenTables<C> tb = gen_build_tables<C>(sh);
+    if (upload(plan->g_wcol, tb.wcol) != 0 || upload(plan->g_wrow, tb.wrow) != 0 || upload(plan->g_lo, tb.m_lo) != 0 ||
+        upload(plan->g_hi, tb.m_hi) != 0 || upload(plan->g_p2f_col, tb.p2f_col) != 0 ||
+        upload(plan->g_p2f_row, tb.p2f_row) != 0 || upload(plan->g_f2p_row, tb.f2p_row) != 0)
+        return -1;
+    if (prepare_gen_kernel<GenColFwdKernel<T, float>>(GenColFwdKernel<T, float>::smem_bytes(sh)) != 0 ||
+        prepare_gen_kernel<GenColFwdKernel<T, double>>(GenColFwdKernel<T, double>::smem_bytes(sh)) != 0 ||
+        prepare_gen_kernel<GenRowFusedKernel<T>>(GenRowFusedKernel<T>::smem_bytes(sh)) != 0 ||
+        prepare_gen_kernel<GenColInvKernel<T>>(GenColInvKernel<T>::smem_bytes(sh)) != 0)
+        return -1;
+    plan->run_wave = [plan](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp, int dtype,
+                            long long sp, long long mp, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
+        return dtype == AUDIOSYNC_CUDA_F32 ? run_generic_wave<T, float>(plan, ctx, d, src, smp, sp, mp, ws, peaks, pairs, st)
+                                           : run_generic_wave<T, double>(plan, ctx, d, src, smp, sp, mp, ws, peaks, pairs, st);
+    };
+    return 0;
+}
+
+static int build_generic_plan(FftPlan* plan, long long L, bool precise) {
+    plan->kind = PATH_GENERIC_FFT;
+    plan->L = L;
+    if (!gen_make_shape(L, precise, &plan->gen)) return -1;
+    plan->M1 = plan->gen.M1; plan->M2 = plan->gen.M2;
+    plan->ws_bytes_per_pair = (size_t)2 * plan->gen.M * (precise ? sizeof(cplxd) : sizeof(cplx));
+    plan->peak_scale = gen_peak_scale(plan->gen);
+    plan->desc = gen_describe(plan->gen, precise);
+    return precise ? build_generic_plan_t<double>(plan) : build_generic_plan_t<float>(plan);
+}
+
 template <typename InT>
 static int run_direct_wave(long long L, audiosync_cuda_ctx* ctx, DeviceState& d, const void* src,
                            const void* smp, long long sp, long long mp, void* ws, PairPeak* peaks, int pairs,
@@ -372,7 +468,7 @@ static int run_direct_wave(long long L, audiosync_cuda_ctx* ctx, DeviceState& d,
                                                                   static_cast<const InT*>(smp), r, L, sp, mp);
         }) != 0) return -1;
     return launch(ctx, d, KC_ARGMAX_F64, st, [&] {
-        argmax_f64_kernel<<<pairs, 1024, 0, st>>>(r, N, peaks);
+        argmax_f64_kernel<<<pairs, 1024, 0, st>>>(r, N, N, peaks);
     });
 }
 
@@ -393,12 +489,17 @@ static int build_direct_plan(FftPlan* plan, long long L) {
 // plans are cached per device and per (L, forced path)
 static FftPlan* get_plan(audiosync_cuda_ctx* ctx, DeviceState& d, long long L) {
     std::lock_guard<std::mutex> plk(d.plan_mu);
-    const size_t key = (size_t)L * 4 + (size_t)ctx->path;
+    const size_t key = (size_t)L * 8 + (size_t)ctx->path * 2 + (ctx->precise ? 1 : 0);
     auto it = d.plans.find(key);
     if (it != d.plans.end()) return it->second.get();
     auto plan = std::make_shared<FftPlan>();
-    const PathKind kind = choose_path(L, ctx->path);
+    const PathKind kind = choose_path(L, ctx->path, ctx->precise);
     int rc = -1;
+    if (kind == PATH_NONE) {
+        set_last_error("sample_len %lld: no transform plan fits the device and the O(L^2) kernel is not used above %lld frames",
+                       L, DIRECT_MAX_L);
+        return nullptr;
+    }
     if (kind == PATH_STATIC_FFT) {
         for_each_static_plan([&](auto P) {
             using PT = decltype(P);
@@ -406,10 +507,15 @@ static FftPlan* get_plan(audiosync_cuda_ctx* ctx, DeviceState& d, long long L) {
         });
     } else if (kind == PATH_SMALL_FFT) {
         rc = build_small_plan(plan.get(), L);
+    } else if (kind == PATH_GENERIC_FFT) {
+        rc = build_generic_plan(plan.get(), L, ctx->precise);
     } else {
         rc = build_direct_plan(plan.get(), L);
     }
-    if (rc != 0) return nullptr;
+    if (rc != 0) {
+        if (g_last_error[0] == 0) set_last_error("could not build a plan for sample_len %lld", L);
+        return nullptr;
+    }
     d.plans[key] = plan;
     return plan.get();
 }
@@ -426,6 +532,9 @@ static int default_wave_pairs(const FftPlan* plan, size_t n_pairs) {
         w = std::max(16LL, std::min(1024LL, w));
     } else if (plan->kind == PATH_SMALL_FFT) {
         w = 16384;
+    } else if (plan->kind == PATH_GENERIC_FFT) {
+        // ~6 GB of planes per wave at most, at least a few hundred CTAs per launch
+        w = std::max(1LL, std::min(1024LL, (6LL << 30) / (long long)std::max<size_t>(plan->ws_bytes_per_pair, 1)));
     } else {
         const long long per = (long long)plan->ws_bytes_per_pair;
         w = std::max(1LL, std::min(1024LL, (256LL << 20) / std::max(1LL, per)));
@@ -483,13 +592,13 @@ static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, WorkSet& work,
             rc = launch(ctx, d, KC_PEARSON, st, [&] {
                 launch_stage(pearson_kernel<float>, grid, dim3(PEARSON_THREADS), 0, st,
                     reinterpret_cast<const float*>(s), reinterpret_cast<const float*>(m), src_pitch, smp_pitch, L,
-                    (const PairPeak*)peaks, 0LL, partials, tickets, n_chunks, d_results + p0);
+                    (const PairPeak*)peaks, 0LL, plan->peak_scale, partials, tickets, n_chunks, d_results + p0);
             });
         } else {
             rc = launch(ctx, d, KC_PEARSON, st, [&] {
                 launch_stage(pearson_kernel<double>, grid, dim3(PEARSON_THREADS), 0, st,
                     reinterpret_cast<const double*>(s), reinterpret_cast<const double*>(m), src_pitch, smp_pitch, L,
-                    (const PairPeak*)peaks, 0LL, partials, tickets, n_chunks, d_results + p0);
+                    (const PairPeak*)peaks, 0LL, plan->peak_scale, partials, tickets, n_chunks, d_results + p0);
             });
         }
         if (rc != 0) return -1;
@@ -748,6 +857,12 @@ int audiosync_cuda_device_count(const audiosync_cuda_ctx* ctx) { return ctx ? (i
 int audiosync_cuda_set_path(audiosync_cuda_ctx* ctx, int path) {
     if (!ctx || path < AUDIOSYNC_CUDA_PATH_AUTO || path > AUDIOSYNC_CUDA_PATH_DIRECT) return -1;
     ctx->path = path;
+    return 0;
+}
+
+int audiosync_cuda_set_precise(audiosync_cuda_ctx* ctx, int on) {
+    if (!ctx) return -1;
+    ctx->precise = on != 0;
     return 0;
 }
 
@@ -1105,6 +1220,8 @@ static audiosync_cuda_ctx* default_ctx() {
         if (audiosync_cuda_create(&c, ids.empty() ? nullptr : ids.data(), (int)ids.size()) != 0) return nullptr;
         const char* p = getenv("AUDIOSYNC_CUDA_PATH");
         if (p && !strcmp(p, "direct")) c->path = AUDIOSYNC_CUDA_PATH_DIRECT;
+        const char* pr = getenv("AUDIOSYNC_CUDA_PRECISE");
+        if (pr && atoi(pr) != 0) c->precise = true;
         const char* ns = getenv("AUDIOSYNC_CUDA_DROPIN_SLOTS");
         const int per_dev = std::max(1, std::min(16, ns ? atoi(ns) : 3));
         for (int k = 0; k < per_dev; k++)
@@ -1287,7 +1404,7 @@ double pearson_coefficient(double* source_start, const double* source_end, doubl
     if (launch(ctx, d, KC_PEARSON, st, [&] {
             pearson_kernel<double><<<dim3(n_chunks, 1), PEARSON_THREADS, 0, st>>>(
                 static_cast<const double*>(d.in_src[0].p), static_cast<const double*>(d.in_smp[0].p), 0, 0,
-                n, nullptr, n, partials, static_cast<unsigned int*>(d.work.tickets.p), n_chunks, d_res);
+                n, nullptr, n, 1.0, partials, static_cast<unsigned int*>(d.work.tickets.p), n_chunks, d_res);
         }) != 0) return fail();
     if (cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
         cudaStreamSynchronize(st) != cudaSuccess) {

@@ -168,6 +168,7 @@ struct audiosync_cuda_ctx {
     size_t slot_next = 0;
     int path = AUDIOSYNC_CUDA_PATH_AUTO;
     int wave_pairs = 0;
+    bool precise = false;     // fp64 ARITHMETIC in the transforms (validation mode)
     bool profile = false;
     std::atomic<uint64_t> launches{0};
     asc::ResidentSession resident;           // drop-in cross_correlation() only (default context)

@@ -127,6 +127,29 @@ ASC_HD cplx cconj(cplx a) { return cmake(a.x, -a.y); }
 ASC_HD cplx cmul_pi(cplx a) { return cmake(-a.y, a.x); }
 ASC_HD cplx cmul_ni(cplx a) { return cmake(a.y, -a.x); }
 
+// ---- the same operations on double2 (fp64-arithmetic validation mode and nothing else: plain
+// fma / add, no packed forms exist).  Selected by overload; scalar_of<C> names the real type.
+typedef double2 cplxd;
+ASC_HD cplxd cmake(double a, double b) { cplxd r; r.x = a; r.y = b; return r; }
+ASC_HD cplxd cadd(cplxd a, cplxd b) { return cmake(a.x + b.x, a.y + b.y); }
+ASC_HD cplxd csub(cplxd a, cplxd b) { return cmake(a.x - b.x, a.y - b.y); }
+ASC_HD cplxd cscale(cplxd a, double s) { return cmake(a.x * s, a.y * s); }
+ASC_HD cplxd caxpy(double s, cplxd b, cplxd a) { return cmake(fma(b.x, s, a.x), fma(b.y, s, a.y)); }
+ASC_HD cplxd cmul(cplxd a, cplxd b) { return cmake(fma(a.x, b.x, -(a.y * b.y)), fma(a.y, b.x, a.x * b.y)); }
+ASC_HD cplxd cmulc(cplxd a, cplxd b) { return cmake(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -(a.x * b.y))); }
+ASC_HD cplxd cadd_i(cplxd a, cplxd b) { return cmake(a.x - b.y, a.y + b.x); }
+ASC_HD cplxd csub_i(cplxd a, cplxd b) { return cmake(a.x + b.y, a.y - b.x); }
+ASC_HD cplxd caxpy_i(double s, cplxd b, cplxd a) { return cmake(fma(-b.y, s, a.x), fma(b.x, s, a.y)); }
+ASC_HD cplxd caxmy_i(double s, cplxd b, cplxd a) { return cmake(fma(b.y, s, a.x), fma(-b.x, s, a.y)); }
+ASC_HD cplxd cmul_const(cplxd v, double wr, double wi) { return cmake(fma(-v.y, wi, v.x * wr), fma(v.x, wi, v.y * wr)); }
+ASC_HD cplxd cconj(cplxd a) { return cmake(a.x, -a.y); }
+ASC_HD cplxd cmul_pi(cplxd a) { return cmake(-a.y, a.x); }
+ASC_HD cplxd cmul_ni(cplxd a) { return cmake(a.y, -a.x); }
+
+template <class C> struct scalar_of;
+template <> struct scalar_of<cplx> { typedef float type; };
+template <> struct scalar_of<cplxd> { typedef double type; };
+
 template <typename T>
 ASC_HD T ldg(const T* p) {
 #if defined(__CUDA_ARCH__)
@@ -343,8 +366,9 @@ constexpr int first_factor(int r) {
 
 // Multiply v by exp(DIR * 2*pi*i * T / R) with the constant folded; exact
 // cases (1, -1, +-i, the eighth roots) use adds only.
-template <int T_, int R, int DIR>
-ASC_HD cplx mul_root(cplx v) {
+template <int T_, int R, int DIR, class C = cplx>
+ASC_HD C mul_root(C v) {
+    typedef typename scalar_of<C>::type real;
     constexpr int t = ((T_ % R) + R) % R;
     if constexpr (t == 0) {
         return v;
@@ -356,12 +380,12 @@ ASC_HD cplx mul_root(cplx v) {
         return DIR > 0 ? cmul_ni(v) : cmul_pi(v);
     } else {
         constexpr ct::cd w = ct::unit((long long)DIR * t, R);
-        constexpr float wr = (float)w.re, wi = (float)w.im;
+        constexpr real wr = (real)w.re, wi = (real)w.im;
         if constexpr (8 * t == R || 8 * t == 3 * R || 8 * t == 5 * R || 8 * t == 7 * R) {
             // |wr| == |wi| == sqrt(1/2): (sr + i si) v = sr v + si (i v), then one scale
-            constexpr float h = 0.70710678118654752440f;
+            constexpr real h = (real)0.70710678118654752440;
             constexpr bool same = (wr > 0) == (wi > 0);
-            const cplx u = same ? cadd_i(v, v) : csub_i(v, v);     // v +- i v
+            const C u = same ? cadd_i(v, v) : csub_i(v, v);     // v +- i v
             return cscale(u, wr > 0 ? h : -h);
         } else {
             return cmul_const(v, wr, wi);
@@ -371,43 +395,45 @@ ASC_HD cplx mul_root(cplx v) {
 
 // ------------------------------------------------------ register butterflies
 // dft_reg<R, DIR>(v): v[k] <- sum_n v[n] exp(DIR*2*pi*i*n*k/R), natural order
-// in and out, all indices compile-time (v stays in registers).
-template <int R, int DIR>
+// in and out, all indices compile-time (v stays in registers).  C = cplx (packed fp32, the
+// product) or cplxd (fp64 validation mode).
+template <int R, int DIR, class C = cplx>
 struct DftReg;
 
-template <int DIR>
-struct DftReg<1, DIR> {
-    static ASC_HD void run(cplx (&)[1]) {}
+template <int DIR, class C>
+struct DftReg<1, DIR, C> {
+    static ASC_HD void run(C (&)[1]) {}
 };
 
-template <int DIR>
-struct DftReg<2, DIR> {
-    static ASC_HD void run(cplx (&v)[2]) {
-        cplx a = v[0], b = v[1];
+template <int DIR, class C>
+struct DftReg<2, DIR, C> {
+    static ASC_HD void run(C (&v)[2]) {
+        C a = v[0], b = v[1];
         v[0] = cadd(a, b);
         v[1] = csub(a, b);
     }
 };
 
-template <int DIR>
-struct DftReg<3, DIR> {
-    static ASC_HD void run(cplx (&v)[3]) {
-        constexpr float s60 = (DIR > 0 ? 1.f : -1.f) * 0.86602540378443864676f;
-        const cplx a = v[0], b = v[1], c = v[2];
-        const cplx t1 = cadd(b, c);
-        const cplx t2 = caxpy(-0.5f, t1, a);
-        const cplx d = csub(b, c);
+template <int DIR, class C>
+struct DftReg<3, DIR, C> {
+    static ASC_HD void run(C (&v)[3]) {
+        typedef typename scalar_of<C>::type real;
+        constexpr real s60 = (real)((DIR > 0 ? 1.0 : -1.0) * 0.86602540378443864676);
+        const C a = v[0], b = v[1], c = v[2];
+        const C t1 = cadd(b, c);
+        const C t2 = caxpy((real)-0.5, t1, a);
+        const C d = csub(b, c);
         v[0] = cadd(a, t1);
         v[1] = caxpy_i(s60, d, t2);      // t2 + i s60 d
         v[2] = caxmy_i(s60, d, t2);      // t2 - i s60 d
     }
 };
 
-template <int DIR>
-struct DftReg<4, DIR> {
-    static ASC_HD void run(cplx (&v)[4]) {
-        const cplx s0 = cadd(v[0], v[2]), s1 = csub(v[0], v[2]);
-        const cplx s2 = cadd(v[1], v[3]), s3 = csub(v[1], v[3]);
+template <int DIR, class C>
+struct DftReg<4, DIR, C> {
+    static ASC_HD void run(C (&v)[4]) {
+        const C s0 = cadd(v[0], v[2]), s1 = csub(v[0], v[2]);
+        const C s2 = cadd(v[1], v[3]), s3 = csub(v[1], v[3]);
         v[0] = cadd(s0, s2);
         v[2] = csub(s0, s2);
         if constexpr (DIR > 0) { v[1] = cadd_i(s1, s3); v[3] = csub_i(s1, s3); }
@@ -415,21 +441,22 @@ struct DftReg<4, DIR> {
     }
 };
 
-template <int DIR>
-struct DftReg<5, DIR> {
-    static ASC_HD void run(cplx (&v)[5]) {
-        constexpr float c1 = 0.30901699437494742410f;    // cos(2pi/5)
-        constexpr float c2 = -0.80901699437494742410f;   // cos(4pi/5)
-        constexpr float sg = DIR > 0 ? 1.f : -1.f;
-        constexpr float s1 = sg * 0.95105651629515357212f;  // sin(2pi/5)
-        constexpr float s2 = sg * 0.58778525229247312917f;  // sin(4pi/5)
-        const cplx x0 = v[0];
-        const cplx a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
-        const cplx a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
-        const cplx p1 = caxpy(c2, a2, caxpy(c1, a1, x0));
-        const cplx p2 = caxpy(c1, a2, caxpy(c2, a1, x0));
-        const cplx u1 = caxpy(s2, b2, cscale(b1, s1));
-        const cplx u2 = caxpy(-s1, b2, cscale(b1, s2));
+template <int DIR, class C>
+struct DftReg<5, DIR, C> {
+    static ASC_HD void run(C (&v)[5]) {
+        typedef typename scalar_of<C>::type real;
+        constexpr real c1 = (real)0.30901699437494742410;    // cos(2pi/5)
+        constexpr real c2 = (real)-0.80901699437494742410;   // cos(4pi/5)
+        constexpr double sg = DIR > 0 ? 1.0 : -1.0;
+        constexpr real s1 = (real)(sg * 0.95105651629515357212);  // sin(2pi/5)
+        constexpr real s2 = (real)(sg * 0.58778525229247312917);  // sin(4pi/5)
+        const C x0 = v[0];
+        const C a1 = cadd(v[1], v[4]), b1 = csub(v[1], v[4]);
+        const C a2 = cadd(v[2], v[3]), b2 = csub(v[2], v[3]);
+        const C p1 = caxpy(c2, a2, caxpy(c1, a1, x0));
+        const C p2 = caxpy(c1, a2, caxpy(c2, a1, x0));
+        const C u1 = caxpy(s2, b2, cscale(b1, s1));
+        const C u2 = caxpy(-s1, b2, cscale(b1, s2));
         v[0] = cadd(cadd(x0, a1), a2);
         v[1] = cadd_i(p1, u1);
         v[4] = csub_i(p1, u1);
@@ -442,7 +469,7 @@ struct DftReg<5, DIR> {
 //  gcd(A,B) == 1: prime-factor (Good-Thomas) map, no twiddles:
 //      n = (B*n1 + A*n2) mod R,  k = the unique k with k%A == k1, k%B == k2.
 //  otherwise: Cooley-Tukey, n = A*n2 + n1, k = B*k1 + k2, twiddle W_R^(n1*k2).
-template <int R, int DIR>
+template <int R, int DIR, class C>
 struct DftReg {
     static constexpr int A = ct::first_factor(R);
     static constexpr int B = R / A;
@@ -455,31 +482,31 @@ struct DftReg {
         return -1;
     }
 
-    static ASC_HD void run(cplx (&v)[R]) {
-        cplx t[R];   // t[n1 * B + k2]
+    static ASC_HD void run(C (&v)[R]) {
+        C t[R];   // t[n1 * B + k2]
         static_for<0, A>([&](auto N1) {
             constexpr int n1 = decltype(N1)::value;
-            cplx u[B];
+            C u[B];
             static_for<0, B>([&](auto N2) {
                 constexpr int n2 = decltype(N2)::value;
                 constexpr int src = PFA ? (B * n1 + A * n2) % R : (A * n2 + n1);
                 u[n2] = v[src];
             });
-            DftReg<B, DIR>::run(u);
+            DftReg<B, DIR, C>::run(u);
             static_for<0, B>([&](auto K2) {
                 constexpr int k2 = decltype(K2)::value;
                 if constexpr (PFA) t[n1 * B + k2] = u[k2];
-                else t[n1 * B + k2] = mul_root<n1 * k2, R, DIR>(u[k2]);
+                else t[n1 * B + k2] = mul_root<n1 * k2, R, DIR, C>(u[k2]);
             });
         });
         static_for<0, B>([&](auto K2) {
             constexpr int k2 = decltype(K2)::value;
-            cplx u[A];
+            C u[A];
             static_for<0, A>([&](auto N1) {
                 constexpr int n1 = decltype(N1)::value;
                 u[n1] = t[n1 * B + k2];
             });
-            DftReg<A, DIR>::run(u);
+            DftReg<A, DIR, C>::run(u);
             static_for<0, A>([&](auto K1) {
                 constexpr int k1 = decltype(K1)::value;
                 constexpr int dst = PFA ? crt(k1, k2) : (B * k1 + k2);
@@ -489,8 +516,8 @@ struct DftReg {
     }
 };
 
-template <int R, int DIR>
-ASC_HD void dft_reg(cplx (&v)[R]) { DftReg<R, DIR>::run(v); }
+template <int R, int DIR, class C>
+ASC_HD void dft_reg(C (&v)[R]) { DftReg<R, DIR, C>::run(v); }
 
 // w[k] = exp(-2*pi*i*j*k/(S*R)) for k = 1..R-1 from the power-of-two table
 // entries of one pass (tw points at the pass's table): k = 2^i is a load,

@@ -93,7 +93,8 @@ inline bool has_static_plan(long long L) {
 }
 
 // --------------------------------------------------------------- twiddles
-inline cplx unit_root(long long a, long long base) {   // exp(-2*pi*i*a/base)
+// exp(-2*pi*i*a/base) as (cos, -sin) in long double
+inline void unit_root_ld(long long a, long long base, long double* re, long double* im) {
     a %= base;
     const long double two_pi = 6.283185307179586476925286766559005768L;
     // reduce to the first octant so that sinl/cosl see a small argument
@@ -113,7 +114,19 @@ inline cplx unit_root(long long a, long long base) {   // exp(-2*pi*i*a/base)
         case 6: { cs((long double)(a - 3.0L * base / 4.0L)); long double t = c; c = s; s = -t; } break;
         default: { cs((long double)(base - a)); s = -s; } break;
     }
-    return cmake((float)c, (float)(-s));
+    *re = c; *im = -s;
+}
+inline cplx unit_root(long long a, long long base) {   // rounded once to fp32
+    long double re, im;
+    unit_root_ld(a, base, &re, &im);
+    return cmake((float)re, (float)im);
+}
+template <class C>
+inline C unit_root_as(long long a, long long base) {    // fp32 or fp64
+    long double re, im;
+    unit_root_ld(a, base, &re, &im);
+    typedef typename scalar_of<C>::type real;
+    return cmake((real)re, (real)im);
 }
 
 // Pass tables for an in-place DIF radix list (layout: RadixList::tw_offset):
@@ -210,23 +223,6 @@ inline bool make_small_plan(long long L, SmallPlan* out) {
     }
     *out = pl;
     return true;
-}
-
-enum PathKind { PATH_STATIC_FFT, PATH_SMALL_FFT, PATH_DIRECT };
-
-// Below this length AUTO prefers the fp64 time-domain kernel: it costs
-// microseconds and keeps fp64 accuracy where the reference's own tests live
-// (tests/test_cross_correlation.c T7: sin(i), L = 1000, has two peaks that
-// differ by 1.2e-9 relative -- unresolvable by an fp32 transform).
-constexpr long long DIRECT_AUTO_BELOW = 4096;
-
-inline PathKind choose_path(long long L, int forced) {
-    if (forced == AUDIOSYNC_CUDA_PATH_DIRECT) return PATH_DIRECT;
-    SmallPlan sp;
-    if (has_static_plan(L)) return PATH_STATIC_FFT;
-    if (forced != AUDIOSYNC_CUDA_PATH_FFT && L < DIRECT_AUTO_BELOW) return PATH_DIRECT;
-    if (make_small_plan(L, &sp)) return PATH_SMALL_FFT;
-    return PATH_DIRECT;   // also when FFT is forced but no plan exists
 }
 
 }  // namespace asc

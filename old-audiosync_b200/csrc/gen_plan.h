@@ -1,0 +1,238 @@
+// gen_plan.h -- host-side planner of the runtime-radix four-step kernels (fft_generic.cuh):
+// radix lists with the fewest passes, the M1 x M2 split, the embedding length for sample_len
+// values that are not 2/3/5-smooth, and the tables.  Shared by the product library and the CPU
+// emulator.  The reference plans per call for any length (src/cross_correlation.c:34, :237);
+// this is the counterpart, cached per length by the caller.
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <vector>
+
+#include "fft_generic.cuh"
+#include "fft_plan.h"
+
+namespace asc {
+
+// Shared memory one CTA of the generic kernels may use (227 KB opt-in per CTA on sm_100, some
+// slack left for the driver's reservation).
+constexpr size_t GEN_SMEM_MAX = 220 * 1024;
+constexpr int GEN_RADICES[] = {16, 15, 12, 10, 9, 8, 6, 5, 4, 3, 2};
+
+// Fewest-pass factorisation of n into supported radices (0 passes: impossible).
+inline int gen_min_passes(int n, std::map<int, int>& memo) {
+    if (n == 1) return 0;
+    auto it = memo.find(n);
+    if (it != memo.end()) return it->second;
+    int best = 1 << 20;
+    for (int r : GEN_RADICES)
+        if (n % r == 0) {
+            const int sub = gen_min_passes(n / r, memo);
+            if (sub + 1 < best) best = sub + 1;
+        }
+    memo[n] = best;
+    return best;
+}
+
+inline bool gen_make_axis(int n, GenAxis* ax) {
+    std::map<int, int> memo;
+    const int np = gen_min_passes(n, memo);
+    if (n < 2 || np > GEN_MAX_PASSES) return false;
+    ax->n = n;
+    ax->npass = 0;
+    int rest = n;
+    // largest radix first among the choices that keep the pass count minimal: the stride-1 pass
+    // ends up with the smallest radix
+    while (rest > 1) {
+        bool found = false;
+        for (int r : GEN_RADICES)
+            if (rest % r == 0 && gen_min_passes(rest / r, memo) == gen_min_passes(rest, memo) - 1) {
+                ax->radix[ax->npass++] = r;
+                rest /= r;
+                found = true;
+                break;
+            }
+        if (!found) return false;
+    }
+    long long prod = 1;
+    for (int p = 0; p < ax->npass; p++) {
+        prod *= ax->radix[p];
+        ax->stride[p] = (int)(n / prod);
+    }
+    return true;
+}
+
+inline std::vector<int> gen_pos2freq(const GenAxis& ax) {
+    std::vector<int> t(ax.n);
+    for (int i = 0; i < ax.n; i++) {
+        int rest = i, k = 0, weight = 1;
+        for (int p = 0; p < ax.npass; p++) {
+            const int d = rest / ax.stride[p];
+            rest -= d * ax.stride[p];
+            k += d * weight;
+            weight *= ax.radix[p];
+        }
+        t[i] = k;
+    }
+    return t;
+}
+inline std::vector<int> gen_freq2pos(const GenAxis& ax) {
+    const std::vector<int> p2f = gen_pos2freq(ax);
+    std::vector<int> t(ax.n);
+    for (int i = 0; i < ax.n; i++) t[p2f[i]] = i;
+    return t;
+}
+
+// Relative cost of a split (lower is better), 0 = unusable.  elem = bytes per complex point.
+inline double gen_split_cost(long long M, int M1, int elem, int ct) {
+    const long long M2 = M / M1;
+    if (M1 < 2 || M2 < 2 || M2 > (1 << 20)) return 0.0;
+    const size_t tile = (size_t)M1 * ct * elem, rows = (size_t)4 * (M2 + M2 / 8 + 1) * elem;
+    if (tile > GEN_SMEM_MAX || rows > GEN_SMEM_MAX) return 0.0;
+    std::map<int, int> memo;
+    const int pc = gen_min_passes(M1, memo), pr = gen_min_passes((int)M2, memo);
+    if (pc > GEN_MAX_PASSES || pr > GEN_MAX_PASSES) return 0.0;
+    // column passes: forward on 1.5 signals + inverse on 1; row passes: forward on 2, inverse on 1
+    // a pass keeps GEN_THREADS threads busy only if the CTA has that many butterflies (radix ~10)
+    auto util = [](double butterflies) { const double u = butterflies / GEN_THREADS; return u > 1.0 ? 1.0 : (u < 0.25 ? 0.25 : u); };
+    double cost = 2.5 * pc / util((double)M1 * ct / 10.0) + 3.0 * pr / util(4.0 * (double)M2 / 10.0);
+    // fewer resident CTAs per SM when a CTA's buffer exceeds a third / half of the SM
+    auto occupancy_penalty = [](size_t bytes) { return bytes > 110 * 1024 ? 1.3 : (bytes > 74 * 1024 ? 1.12 : 1.0); };
+    cost *= occupancy_penalty(tile) * occupancy_penalty(rows);
+    if (M2 % ct != 0) cost *= 1.25;            // ragged last tile, rows not 128-byte aligned
+    return cost;
+}
+
+inline bool gen_choose_split(long long M, int elem, int ct, int* M1_out, double* cost_out) {
+    double best = 0.0;
+    int best_m1 = 0;
+    for (long long d = 2; d <= 2048 && d <= M; d++) {
+        if (M % d != 0) continue;
+        const double c = gen_split_cost(M, (int)d, elem, ct);
+        if (c > 0.0 && (best == 0.0 || c < best)) { best = c; best_m1 = (int)d; }
+    }
+    if (best == 0.0) return false;
+    *M1_out = best_m1;
+    if (cost_out) *cost_out = best;
+    return true;
+}
+
+// The plan for a sample_len: the exact length when it is 2/3/5-smooth and splits, otherwise the
+// cheapest embedding length M >= ceil(3L / 2) among the smooth numbers up to 15 % above the
+// smallest one.  is_double: fp64 arithmetic (16-byte points, 8-column tiles).
+inline bool gen_make_shape(long long L, bool is_double, GenShape* out) {
+    const int elem = is_double ? 16 : 8, ct = is_double ? 8 : 16;
+    if (L < 1) return false;
+    GenShape sh{};
+    sh.L = L;
+    int m1 = 0;
+    double cost = 0.0;
+    if (is_235_smooth(L) && gen_choose_split(L, elem, ct, &m1, &cost)) {
+        sh.M = L;
+        sh.src_ext = 2 * L;
+    } else {
+        const long long lo = (3 * L + 1) / 2;
+        std::vector<long long> cand;
+        for (long long a = 1; a <= 4 * lo; a *= 2)
+            for (long long b = a; b <= 4 * lo; b *= 3)
+                for (long long c = b; c <= 4 * lo; c *= 5)
+                    if (c >= lo) cand.push_back(c);
+        std::sort(cand.begin(), cand.end());
+        double best = 0.0;
+        long long best_m = 0;
+        int best_m1 = 0;
+        long long first_ok = 0;
+        for (long long m : cand) {
+            if (first_ok && (double)m > 1.15 * (double)first_ok) break;
+            int mm1;
+            double c;
+            if (!gen_choose_split(m, elem, ct, &mm1, &c)) continue;
+            if (!first_ok) first_ok = m;
+            const double total = c * (double)m;
+            if (best == 0.0 || total < best) { best = total; best_m = m; best_m1 = mm1; }
+        }
+        if (best_m == 0) return false;
+        sh.M = best_m;
+        sh.src_ext = 3 * L;
+        m1 = best_m1;
+    }
+    sh.M1 = m1;
+    sh.M2 = (int)(sh.M / m1);
+    if (!gen_make_axis(sh.M1, &sh.col) || !gen_make_axis(sh.M2, &sh.row)) return false;
+    *out = sh;
+    return true;
+}
+
+// r_reference = r_computed * gen_peak_scale: the split/merge leaves a factor 2 (its 1/2 is not
+// applied in the generic kernels) and an embedded transform carries N' = 2M instead of N = 2L.
+inline double gen_peak_scale(const GenShape& sh) { return 0.5 * (double)sh.L / (double)sh.M; }
+
+template <class C>
+struct GenTables {
+    std::vector<C> wcol, wrow, m_lo, m_hi;
+    std::vector<int> p2f_col, p2f_row, f2p_row;
+};
+
+template <class C>
+inline GenTables<C> gen_build_tables(const GenShape& sh) {
+    GenTables<C> t;
+    t.wcol.resize(sh.M1);
+    for (int a = 0; a < sh.M1; a++) t.wcol[a] = unit_root_as<C>(a, sh.M1);
+    t.wrow.resize(sh.M2);
+    for (int a = 0; a < sh.M2; a++) t.wrow[a] = unit_root_as<C>(a, sh.M2);
+    t.m_lo.resize(1u << TW2_BITS);
+    for (long long a = 0; a < (long long)t.m_lo.size(); a++) t.m_lo[a] = unit_root_as<C>(a, sh.M);
+    const long long nh = ((sh.M - 1) >> TW2_BITS) + 1;
+    t.m_hi.resize(nh);
+    for (long long b = 0; b < nh; b++) t.m_hi[b] = unit_root_as<C>(b << TW2_BITS, sh.M);
+    t.p2f_col = gen_pos2freq(sh.col);
+    t.p2f_row = gen_pos2freq(sh.row);
+    t.f2p_row = gen_freq2pos(sh.row);
+    return t;
+}
+
+inline std::string gen_describe(const GenShape& sh, bool is_double) {
+    std::string d = "fft L=" + std::to_string(sh.L) + " M=" + std::to_string(sh.M) + " M1=" + std::to_string(sh.M1) +
+                    " M2=" + std::to_string(sh.M2) + " col=";
+    for (int i = 0; i < sh.col.npass; i++) d += (i ? "x" : "") + std::to_string(sh.col.radix[i]);
+    d += " row=";
+    for (int i = 0; i < sh.row.npass; i++) d += (i ? "x" : "") + std::to_string(sh.row.radix[i]);
+    d += sh.M == sh.L ? " generic four-step" : " generic four-step, embedded (N'=2M>=3L)";
+    d += is_double ? " fp64" : " fp32";
+    return d;
+}
+
+// ------------------------------------------------------------- path choice
+enum PathKind { PATH_STATIC_FFT, PATH_SMALL_FFT, PATH_DIRECT, PATH_GENERIC_FFT, PATH_NONE };
+
+// Below this length AUTO prefers the fp64 time-domain kernel: it costs
+// microseconds and keeps fp64 accuracy where the reference's own tests live
+// (tests/test_cross_correlation.c T7: sin(i), L = 1000, has two peaks that
+// differ by 1.2e-9 relative -- unresolvable by an fp32 transform).
+constexpr long long DIRECT_AUTO_BELOW = 4096;
+// The O(L^2) kernel is never chosen above this length (2 * L^2 = 8.6e9 fp64 FMAs, a millisecond
+// on B200); longer inputs without a transform plan are refused, not ground through.
+constexpr long long DIRECT_MAX_L = 65536;
+// Shortest length the runtime-radix kernels are used for when a transform is asked for.
+constexpr long long GEN_MIN_L = 256;
+
+// precise: fp64 ARITHMETIC (validation mode).  The direct kernel is fp64 already; every
+// transform then runs on the fp64 instantiation of the runtime-radix kernels.
+inline PathKind choose_path(long long L, int forced, bool precise = false) {
+    if (forced == AUDIOSYNC_CUDA_PATH_DIRECT) return L <= DIRECT_MAX_L ? PATH_DIRECT : PATH_NONE;
+    GenShape gs;
+    if (precise) {
+        if (L >= (forced == AUDIOSYNC_CUDA_PATH_FFT ? GEN_MIN_L : DIRECT_AUTO_BELOW) && gen_make_shape(L, true, &gs))
+            return PATH_GENERIC_FFT;
+        return L <= DIRECT_MAX_L ? PATH_DIRECT : PATH_NONE;
+    }
+    if (has_static_plan(L)) return PATH_STATIC_FFT;
+    if (forced != AUDIOSYNC_CUDA_PATH_FFT && L < DIRECT_AUTO_BELOW) return PATH_DIRECT;
+    SmallPlan sp;
+    if (make_small_plan(L, &sp)) return PATH_SMALL_FFT;
+    if (L >= GEN_MIN_L && gen_make_shape(L, false, &gs)) return PATH_GENERIC_FFT;
+    return L <= DIRECT_MAX_L ? PATH_DIRECT : PATH_NONE;   // short lengths without a plan (FFT forced on a tiny odd L)
+}
+
+}  // namespace asc

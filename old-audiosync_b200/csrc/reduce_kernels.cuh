@@ -112,11 +112,12 @@ __device__ __forceinline__ KeyF64 key_shfl_xor(KeyF64 k, int o) {
     return c;
 }
 
+// `pitch`: doubles between consecutive pairs' arrays (N when packed).
 __global__ void __launch_bounds__(1024)
-argmax_f64_kernel(const double* __restrict__ r, long long N, PairPeak* __restrict__ peaks)
+argmax_f64_kernel(const double* __restrict__ r, long long N, long long pitch, PairPeak* __restrict__ peaks)
 {
     __shared__ KeyF64 s_k[32];
-    const double* rp = r + (size_t)blockIdx.x * (size_t)N;
+    const double* rp = r + (size_t)blockIdx.x * (size_t)pitch;
     const double ninf = -INFINITY, pinf = INFINITY;
     KeyF64 best; best.v = ninf; best.i = 0x7fffffffffffffffLL; best.a = 0.0; best.s = 0.0;
     for (long long i = threadIdx.x; i < N; i += blockDim.x) {
@@ -218,7 +219,7 @@ template <typename T, int NTP>
 __device__ __forceinline__ void pearson_block(
     const T* __restrict__ sources, const T* __restrict__ samples,
     long long src_pitch, long long smp_pitch, long long L,
-    const PairPeak* __restrict__ peaks, long long explicit_n,
+    const PairPeak* __restrict__ peaks, long long explicit_n, double peak_scale,
     PearsonPartial* __restrict__ partials, unsigned int* __restrict__ tickets,
     int n_chunks, audiosync_cuda_result* __restrict__ results,
     int pair, int chunk, int t, PearsonShared<NTP>& sh)
@@ -234,6 +235,9 @@ __device__ __forceinline__ void pearson_block(
         peak = p.resolved ? p.peak : (double)argmax_key_value(p.key);
         second = p.resolved ? p.second
                             : (p.second_bits != 0u ? (double)float_from_order_bits(p.second_bits) : 0.0);
+        // the transform's own scale -> the reference's (FFTW c2r: x N); powers of two for the static plans
+        peak *= peak_scale;
+        second *= peak_scale;
         w = fold_index(raw, L);
     }
     const T* __restrict__ x = sources + (size_t)pair * (size_t)src_pitch + w.xoff;
@@ -385,13 +389,13 @@ template <typename T>
 __global__ void __launch_bounds__(PEARSON_THREADS)
 pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
                long long src_pitch, long long smp_pitch, long long L,
-               const PairPeak* __restrict__ peaks, long long explicit_n,
+               const PairPeak* __restrict__ peaks, long long explicit_n, double peak_scale,
                PearsonPartial* __restrict__ partials, unsigned int* __restrict__ tickets,
                int n_chunks, audiosync_cuda_result* __restrict__ results)
 {
     __shared__ PearsonShared<PEARSON_THREADS> sh;
     pdl_prologue();
-    pearson_block<T, PEARSON_THREADS>(sources, samples, src_pitch, smp_pitch, L, peaks, explicit_n, partials,
+    pearson_block<T, PEARSON_THREADS>(sources, samples, src_pitch, smp_pitch, L, peaks, explicit_n, peak_scale, partials,
                                       tickets, n_chunks, results, (int)blockIdx.y, (int)blockIdx.x,
                                       (int)threadIdx.x, sh);
 }

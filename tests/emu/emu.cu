@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "fft_plan.h"
+#include "gen_plan.h"
 
 using namespace asc;
 
@@ -115,6 +116,71 @@ static int run_small(const InT* source, const InT* sample, long long L, PairPeak
     return 0;
 }
 
+// ---- runtime-radix kernels (fft_generic.cuh): T = arithmetic type, InT = input type
+template <typename T, typename InT>
+static int run_generic(const InT* source, const InT* sample, long long L, long long* raw_index, double* peak_value,
+                       double* second_value, char* desc, size_t desc_len) {
+    typedef typename GenTraits<T>::C C;
+    GenShape sh;
+    if (!gen_make_shape(L, sizeof(T) == 8, &sh)) return -1;
+    if (desc) snprintf(desc, desc_len, "%s", gen_describe(sh, sizeof(T) == 8).c_str());
+    const GenTables<C> tb = gen_build_tables<C>(sh);
+    std::vector<C> planes(2 * sh.M);
+    PairPeak pk;
+    memset(&pk, 0, sizeof(pk));
+    pk.key = 12345ull; pk.second_bits = 777u;   // garbage: G_A must clear both
+    {
+        using K = GenColFwdKernel<T, InT>;
+        typename K::Params p{source, sample, planes.data(), &pk, tb.wcol.data(), tb.m_lo.data(), tb.m_hi.data(),
+                             tb.p2f_col.data(), sh, 2 * L, L};
+        std::vector<C> smem(K::smem_bytes(sh) / sizeof(C) + 1);
+        for (int sig = 0; sig < 2; sig++)
+            for (int tile = 0; tile < (sh.M2 + K::CT - 1) / K::CT; tile++) {
+                HostExec ex{tile, sig, 0, K::THREADS};
+                K::run(ex, p, smem.data());
+            }
+    }
+    {
+        using K = GenRowFusedKernel<T>;
+        typename K::Params p{planes.data(), tb.wrow.data(), tb.m_lo.data(), tb.m_hi.data(), tb.p2f_row.data(),
+                             tb.f2p_row.data(), sh};
+        std::vector<C> smem(K::smem_bytes(sh) / sizeof(C) + 1);
+        for (int r = 0; r <= sh.M1 / 2; r++) {
+            HostExec ex{r, 0, 0, K::THREADS};
+            K::run(ex, p, smem.data());
+        }
+    }
+    {
+        using K = GenColInvKernel<T>;
+        typename K::Params p{planes.data(), &pk, tb.wcol.data(), tb.p2f_col.data(), sh, reinterpret_cast<T*>(planes.data())};
+        std::vector<C> smem(K::smem_bytes(sh) / sizeof(C) + 1);
+        for (int tile = 0; tile < (sh.M2 + K::CT - 1) / K::CT; tile++) {
+            HostExec ex{0, tile, 0, K::THREADS};
+            K::run(ex, p, smem.data());
+        }
+    }
+    const double scale = gen_peak_scale(sh);
+    if (sizeof(T) == 4) {
+        *raw_index = (long long)argmax_key_index(pk.key);
+        *peak_value = (double)argmax_key_value(pk.key) * scale;
+        *second_value = (pk.second_bits ? (double)float_from_order_bits(pk.second_bits) : 0.0) * scale;
+    } else {
+        // fp64: r[0 .. 2L) sits in plane 1; resolve like argmax_f64_kernel (reference :52-67)
+        const T* r = reinterpret_cast<const T*>(planes.data()) + 2 * sh.M;
+        long long best = 0;
+        double bv = (double)r[0];
+        for (long long i = 1; i < 2 * L; i++)
+            if (fabs((double)r[i]) > bv) { bv = fabs((double)r[i]); best = i; }
+        double second = 0.0;
+        for (long long i = 0; i < 2 * L; i++)
+            if (i != best && fabs((double)r[i]) > second) second = fabs((double)r[i]);
+        *raw_index = best;
+        *peak_value = (double)r[best] * scale;
+        *second_value = second * scale;
+    }
+    return 0;
+}
+
 static double g_last_second = 0.0;   // second peak of the last emu_any call
 
 template <typename InT>
@@ -132,6 +198,11 @@ static int emu_any(const InT* source, const InT* sample, long long L, int forced
         });
     } else if (kind == PATH_SMALL_FFT) {
         rc = run_small<InT>(source, sample, L, &pk);
+    } else if (kind == PATH_GENERIC_FFT) {
+        double second = 0.0;
+        rc = run_generic<float, InT>(source, sample, L, raw_index, peak_value, &second, nullptr, 0);
+        g_last_second = second;
+        return rc;
     } else {
         return -2;   // direct path has no transform to emulate
     }
@@ -145,6 +216,24 @@ static int emu_any(const InT* source, const InT* sample, long long L, int forced
 extern "C" {
 
 double emu_last_second(void) { return g_last_second; }
+
+// runtime-radix four-step kernels; precise != 0: fp64 arithmetic.  desc receives the plan text.
+int emu_generic_f32(const float* source, const float* sample, long long L, int precise, long long* raw_index,
+                    double* peak_value, double* second_value, char* desc, size_t desc_len) {
+    return precise ? run_generic<double, float>(source, sample, L, raw_index, peak_value, second_value, desc, desc_len)
+                   : run_generic<float, float>(source, sample, L, raw_index, peak_value, second_value, desc, desc_len);
+}
+int emu_generic_f64(const double* source, const double* sample, long long L, int precise, long long* raw_index,
+                    double* peak_value, double* second_value, char* desc, size_t desc_len) {
+    return precise ? run_generic<double, double>(source, sample, L, raw_index, peak_value, second_value, desc, desc_len)
+                   : run_generic<float, double>(source, sample, L, raw_index, peak_value, second_value, desc, desc_len);
+}
+int emu_generic_describe(long long L, int precise, char* desc, size_t desc_len) {
+    GenShape sh;
+    if (!gen_make_shape(L, precise != 0, &sh)) return -1;
+    snprintf(desc, desc_len, "%s", gen_describe(sh, precise != 0).c_str());
+    return 0;
+}
 
 int emu_xcorr_f32(const float* source, const float* sample, long long L, int forced,
                   long long* raw_index, double* peak_value, int* path) {
@@ -170,6 +259,7 @@ unsigned emu_key_index(unsigned long long k) { return argmax_key_index(k); }
 float emu_key_value(unsigned long long k) { return argmax_key_value(k); }
 
 int emu_path_for(long long L, int forced) { return (int)choose_path(L, forced); }
+int emu_path_for_precise(long long L, int forced) { return (int)choose_path(L, forced, true); }
 
 // box geometry of the TMA-staged column tiles (fft_kernels.cuh)
 int emu_tile_boxes(int rows) { return tile_boxes(rows); }

@@ -39,6 +39,12 @@ def emu():
     E.emu_key_value.restype = C.c_float
     E.emu_key_value.argtypes = [C.c_ulonglong]
     E.emu_path_for.argtypes = [C.c_longlong, C.c_int]
+    E.emu_path_for_precise.argtypes = [C.c_longlong, C.c_int]
+    gsig = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
+            C.POINTER(C.c_double), C.c_char_p, C.c_size_t]
+    E.emu_generic_f32.argtypes = gsig
+    E.emu_generic_f64.argtypes = gsig
+    E.emu_generic_describe.argtypes = [C.c_longlong, C.c_int, C.c_char_p, C.c_size_t]
     E.emu_last_second.restype = C.c_double
     return E
 
@@ -94,9 +100,21 @@ def test_static_plans_cover_interval_schedule(emu):
     for L in (2, 6, 10, 12, 1000, 2000):
         assert emu.emu_path_for(L, PATH_AUTO) == 2          # short: fp64 direct by default
         assert emu.emu_path_for(L, PATH_FFT) == 1           # ... FFT when asked for
-    for L in (1, 5, 7, 14, 4374 * 2 + 1, 24000, 10 ** 6):
+    for L in (1, 5, 7, 14):
         assert emu.emu_path_for(L, PATH_AUTO) == 2          # PATH_DIRECT
         assert emu.emu_path_for(L, PATH_FFT) == 2
+    # every other length has an O(N log N) plan: the runtime-radix four-step kernels, at the
+    # length itself when it is 2/3/5-smooth, embedded in N' >= 3L otherwise (odd, other primes)
+    for L in (4374 * 2 + 1, 4099, 10007, 24000, 65536, 100000, 10 ** 6, 1048576, 1440002, 2 * 3 ** 12, 5 * 10 ** 6):
+        assert emu.emu_path_for(L, PATH_AUTO) == 3          # PATH_GENERIC_FFT
+    for L in (257, 1001, 2187):                             # short, no single-CTA plan: generic when a transform is asked for
+        assert emu.emu_path_for(L, PATH_AUTO) == 2 and emu.emu_path_for(L, PATH_FFT) == 3
+    assert emu.emu_path_for(40 * 10 ** 6, PATH_AUTO) == 4   # PATH_NONE: refused, never O(L^2)
+    assert emu.emu_path_for(10 ** 6, 2) == 4                # forced direct above 65,536 frames: refused
+    # fp64-arithmetic mode: the schedule lengths leave the static fp32 kernels
+    for L in (144000, 1440000, 24000, 10007):
+        assert emu.emu_path_for_precise(L, PATH_AUTO) == 3
+    assert emu.emu_path_for_precise(1000, PATH_AUTO) == 2   # the direct kernel is fp64 already
 
 
 @pytest.mark.parametrize("L", [2, 4, 6, 8, 10, 12, 16, 18, 20, 30, 36, 48, 50, 100, 250, 486, 1000,
@@ -176,3 +194,84 @@ def test_emulated_kernels_resolve_low_margins_and_edges(emu, case):
     assert used == 0 and idx == case["raw_index"]
     assert abs(peak - case["peak"]) <= 1e-4 * abs(case["peak"])
     assert abs(emu.emu_last_second() - case["second"]) <= 1e-4 * case["second"] + 1e-6 * abs(case["peak"])
+
+
+# ------------------------------------------------------------------ runtime-radix kernels (any length)
+
+def run_generic(E, src, smp, f64=False, precise=False):
+    L = len(smp)
+    idx, pk, sec = C.c_longlong(), C.c_double(), C.c_double()
+    desc = C.create_string_buffer(256)
+    dt = np.float64 if f64 else np.float32
+    s = np.ascontiguousarray(src, dt); p = np.ascontiguousarray(smp, dt)
+    fn = E.emu_generic_f64 if f64 else E.emu_generic_f32
+    rc = fn(s.ctypes.data, p.ctypes.data, L, int(precise), C.byref(idx), C.byref(pk), C.byref(sec), desc, 256)
+    assert rc == 0
+    return idx.value, pk.value, sec.value, desc.value.decode()
+
+
+GENERIC_LENGTHS = [256, 257, 1001, 2187, 4099, 6561, 8749, 10007, 24000, 39366, 65536, 100000, 250000]
+
+
+@pytest.mark.parametrize("L", GENERIC_LENGTHS)
+def test_generic_kernels_any_length_vs_oracle(emu, L):
+    """fft_generic.cuh bodies on the CPU: 2/3/5-smooth lengths at their own size, everything else
+    (odd, prime, 7-smooth ...) embedded in N' >= 3L -- raw index exact, peak and second peak within
+    the fp32 tolerance; the fp64 instantiation within 1e-12 of the fp64 oracle."""
+    from oracle import xcorr_numpy
+    for pid in (0, 1):
+        src, smp = capi.synth_pair(0xFACE, pid, L)
+        o = xcorr_numpy.cross_correlation(src, smp)
+        assert o["margin"] > 1e-3
+        idx, peak, sec, desc = run_generic(emu, src, smp)
+        assert idx == o["raw_index"], desc
+        assert abs(peak - o["peak"]) <= 1e-5 * abs(o["peak"])
+        assert abs(sec - o["second"]) <= 1e-4 * o["second"] + 1e-6 * abs(o["peak"])
+        idx, peak, sec, desc = run_generic(emu, src, smp, f64=True, precise=True)
+        assert idx == o["raw_index"] and "fp64" in desc
+        assert abs(peak - o["peak"]) <= 1e-12 * abs(o["peak"])
+        assert abs(sec - o["second"]) <= 1e-9 * abs(o["peak"])
+    n = L
+    for q in (2, 3, 5):
+        while n % q == 0:
+            n //= q
+    assert ("embedded" in desc) == (n != 1)
+
+
+def test_generic_plan_shapes():
+    """The planner: every radix supported, passes minimal, both buffers within one SM's shared memory."""
+    import re
+    E = C.CDLL(os.path.join(HERE, "emu", "libasc_emu.so"))
+    E.emu_generic_describe.argtypes = [C.c_longlong, C.c_int, C.c_char_p, C.c_size_t]
+    for L in [256, 4099, 24000, 100000, 250000, 10 ** 6, 1048576, 1440002, 1440000, 3 * 10 ** 6, 5 * 10 ** 6, 7 * 10 ** 6 + 1]:
+        for precise in (0, 1):
+            buf = C.create_string_buffer(256)
+            rc = E.emu_generic_describe(L, precise, buf, 256)
+            if rc != 0:
+                assert L > 3 * 10 ** 6, (L, precise)       # only very long inputs may lack a plan
+                continue
+            d = buf.value.decode()
+            m = re.search(r"M=(\d+) M1=(\d+) M2=(\d+) col=([0-9x]+) row=([0-9x]+)", d)
+            M, M1, M2 = int(m.group(1)), int(m.group(2)), int(m.group(3))
+            col = [int(x) for x in m.group(4).split("x")]; row = [int(x) for x in m.group(5).split("x")]
+            assert M1 * M2 == M and np.prod(col) == M1 and np.prod(row) == M2
+            assert all(r in (2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16) for r in col + row)
+            assert (M == L) or (2 * M >= 3 * L and M <= 1.2 * 1.5 * L + 64)
+            elem, ct = (16, 8) if precise else (8, 16)
+            assert M1 * ct * elem <= 220 * 1024 and 4 * (M2 + M2 // 8 + 1) * elem <= 220 * 1024
+            assert len(col) <= 6 and len(row) <= 6, d
+
+
+@pytest.mark.parametrize("case", _hard_144k(), ids=lambda c: "%s-%.0e" % (c["kind"], c["margin"] or 0))
+def test_fp64_arithmetic_mode_on_hard_goldens(emu, case):
+    """The fp64 instantiation (audiosync_cuda_set_precise) as a second oracle: on the low-margin /
+    edge inputs at L = 144,000 it reproduces the compiled reference's raw index, its peak to
+    1e-12 and its second peak, and the fp32 runtime-radix kernels agree on the index."""
+    import hard_cases as hc
+    src, smp = hc.build(case, np.float64)
+    idx, peak, sec, _ = run_generic(emu, src, smp, f64=True, precise=True)
+    assert idx == case["raw_index"]
+    assert abs(peak - case["peak"]) <= 1e-12 * abs(case["peak"]) + 1e-300
+    assert abs(sec - case["second"]) <= 1e-9 * abs(case["peak"]) + 1e-300
+    idx32, _, _, _ = run_generic(emu, src, smp)
+    assert idx32 == case["raw_index"]

@@ -200,6 +200,88 @@ def test_hard_goldens_dropin_and_batch(ac, ctx, case):
     _check_hard(case, int(rec["ret"]), int(rec["lag"]), float(rec["coef"]), rec)
 
 
+# ------------------------------------------------------------------ any length: runtime-radix plans
+GEN_LENGTHS = [4099, 8749, 10007, 24000, 100000, 250000, 1000000, 1048576, 1440002]
+
+
+@pytest.mark.parametrize("L", GEN_LENGTHS)
+def test_generic_plan_any_length_vs_oracle(ac, ctx, capi, L):
+    """The reference plans FFTW per call for whatever sample_len arrives (src/cross_correlation.c:34,
+    :141-142, :237).  Lengths outside the interval schedule run the runtime-radix four-step
+    kernels: 2/3/5-smooth ones at their own size, odd / prime-factor ones embedded in N' >= 3L.
+    Device-resident fp32 batch and the f64 drop-in call against the NumPy (pocketfft) oracle."""
+    from oracle import xcorr_numpy
+    desc = ctx.describe_plan(L)
+    assert "generic four-step" in desc and "fp32" in desc, desc
+    n = 3
+    res, d_src, d_smp = _batch_on_device(ac, ctx, SEED + 50, 0, n, L)
+    for i in range(n):
+        src, smp = capi.synth_pair(SEED + 50, i, L)
+        o = xcorr_numpy.cross_correlation(src, smp)
+        r = res[i]
+        assert o["margin"] > 1e-4
+        assert int(r["raw_index"]) == o["raw_index"] and int(r["lag"]) == o["lag"] == capi.synth_true_lag(SEED + 50, i, L)
+        assert int(r["ret"]) == o["ret"] and bool(r["success"]) == (o["ret"] == 0 and o["coef"] >= 0.95)
+        assert close(float(r["coef"]), o["coef"]) and close(float(r["peak"]), o["peak"])
+        assert abs(float(r["second"]) - o["second"]) <= RTOL * o["second"] + 1e-6 * abs(o["peak"])
+        assert abs(float(r["margin"]) - o["margin"]) <= 1e-4 and close(float(r["ncc"]), o["ncc"])
+        if i == 0:
+            ret, lag, coef = ac.cross_correlation(src, smp)          # unchanged C signature, f64 host
+            assert (ret, lag) == (o["ret"], o["lag"]) and close(coef, o["coef"])
+
+
+def test_generic_plan_edges_off_schedule(ac, ctx, capi):
+    """idx == L, idx == L + 1, all-zero sample and a NaN input on an embedded (odd) length."""
+    import hard_cases as hc
+    L = 100001
+    for case in (dict(kind="impulse", L=L, params=dict(i_src=L, i_smp=0)),
+                 dict(kind="impulse", L=L, params=dict(i_src=0, i_smp=L - 1)),
+                 dict(kind="zero_sample", L=L, params=dict(seed=3)),
+                 dict(kind="lag", L=L, params=dict(seed=4, lag=L - 1)),
+                 dict(kind="lag", L=L, params=dict(seed=5, lag=-1))):
+        src, smp = hc.build(case, np.float32)
+        o = capi.cross_correlation(src.astype(np.float64), smp.astype(np.float64))
+        rec = ctx.xcorr_batch_records(src.ctypes.data, smp.ctypes.data, 1, L, ac.F32, ac.HOST)[0]
+        assert (int(rec["ret"]), int(rec["lag"]), int(rec["raw_index"])) == (o["ret"], o["lag"], o["raw_index"]), case
+        assert close(float(rec["coef"]), o["coef"]) and close(float(rec["peak"]), o["peak"])
+    src, smp = capi.synth_pair(SEED, 0, L, np.float32)
+    src = src.copy(); src[L // 3] = np.nan
+    rec = ctx.xcorr_batch_records(src.ctypes.data, smp.ctypes.data, 1, L, ac.F32, ac.HOST)[0]
+    assert int(rec["ret"]) == -1 and int(rec["lag"]) == 0 and rec["coef"] != rec["coef"]
+    with pytest.raises(ac.AudiosyncCudaError):                      # no plan fits: refused, never O(L^2)
+        ctx.describe_plan(40 * 10 ** 6)
+
+
+# ------------------------------------------------------------------ fp64-arithmetic validation mode
+
+@pytest.mark.parametrize("L", [144000, 288000, 480000, 720000, 960000, 1440000])
+def test_precise_mode_is_a_second_oracle_at_schedule_lengths(ac, capi, L):
+    """audiosync_cuda_set_precise: the transforms in fp64 arithmetic (reference :187-239 computes in
+    double complex).  Against the compiled reference's goldens: raw index exact, peak within 1e-12,
+    coefficient within 1e-10, on the white-noise pairs AND the low-margin / edge pairs; and the
+    fp32 product path agrees with it on every index."""
+    import hard_cases as hc
+    with ac.Context([0]) as cp, ac.Context([0]) as cf:
+        cp.set_precise(True)
+        assert "fp64" in cp.describe_plan(L) and "static" in cf.describe_plan(L)
+        cases = [(c, capi.synth_pair(c["seed"], c["pair_id"], L)) for c in _pairs() if c["L"] == L]
+        cases += [(c, hc.build(c, np.float64)) for c in HARD["cases"] if c["L"] == L]
+        for c, (src, smp) in cases:
+            rp = cp.xcorr_batch_records(src.ctypes.data, smp.ctypes.data, 1, L, ac.F64, ac.HOST)[0]
+            rf = cf.xcorr_batch_records(src.ctypes.data, smp.ctypes.data, 1, L, ac.F64, ac.HOST)[0]
+            assert int(rp["raw_index"]) == c["raw_index"] == int(rf["raw_index"])
+            assert int(rp["lag"]) == c["lag"] and int(rp["ret"]) == c["ret"]
+            assert abs(float(rp["peak"]) - c["peak"]) <= 1e-12 * abs(c["peak"])
+            assert abs(float(rp["second"]) - c["second"]) <= 1e-9 * abs(c["peak"])
+            if c["coef"] is None:
+                assert rp["coef"] != rp["coef"]
+            else:
+                assert abs(float(rp["coef"]) - c["coef"]) <= 1e-10 * abs(c["coef"])
+            # the fp32 kernels against the fp64 ones: peak 1e-5, margin 3e-5
+            assert abs(float(rf["peak"]) - float(rp["peak"])) <= 1e-5 * abs(float(rp["peak"]))
+            assert abs(float(rf["margin"]) - float(rp["margin"])) <= 3e-5
+
+
 # ------------------------------------------------------------------ oracle, many shapes
 
 @pytest.mark.parametrize("L", [1, 2, 3, 5, 6, 7, 8, 9, 10, 11, 12, 50, 63, 64, 250, 255, 256, 257, 1000, 1001, 2187])
