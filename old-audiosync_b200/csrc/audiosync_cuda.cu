@@ -17,11 +17,7 @@
 #include <map>
 #include <thread>
 
-#include "context.h"
-#include "fft_kernels.cuh"
-#include "fft_plan.h"
-#include "fft_small.cuh"
-#include "gen_plan.h"
+#include "plan_host.h"
 #include "reduce_kernels.cuh"
 
 // The reference defines `volatile int global_debug` in src/audiosync.c:37 and its
@@ -85,245 +81,6 @@ int PinnedBuf::ensure(size_t need) {
 }
 void PinnedBuf::release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
 
-// -------------------------------------------------------------------- plan
-struct FftPlan {
-    PathKind kind = PATH_DIRECT;
-    long long L = 0;
-    int M1 = 0, M2 = 0;
-    std::string desc;
-    size_t ws_bytes_per_pair = 0;
-    DevBuf col_tw, col_tc, row_tw, row_rev, row_tab, m_lo, m_hi;   // static four-step
-    DevBuf wm, wn;                                   // short-length kernel
-    SmallPlan small;
-    GenShape gen{};                                  // runtime-radix four-step kernels
-    DevBuf g_wcol, g_wrow, g_lo, g_hi, g_p2f_col, g_p2f_row, g_f2p_row;
-    double peak_scale = 1.0;                         // r_reference = r_kernel * peak_scale
-    // enqueues the transform kernels for `pairs` pairs (planes/r in ws)
-    // (src, smp, dtype, src_pitch, smp_pitch [elements between pairs], workspace, peaks, pairs, stream)
-    std::function<int(audiosync_cuda_ctx*, DeviceState&, const void*, const void*, int, long long, long long,
-                      void*, PairPeak*, int, cudaStream_t)> run_wave;
-    ~FftPlan() {
-        col_tw.release(); col_tc.release(); row_tw.release(); row_rev.release(); row_tab.release(); m_lo.release(); m_hi.release();
-        wm.release(); wn.release();
-        g_wcol.release(); g_wrow.release(); g_lo.release(); g_hi.release();
-        g_p2f_col.release(); g_p2f_row.release(); g_f2p_row.release();
-    }
-};
-
-template <class E>
-static int upload(DevBuf& b, const std::vector<E>& v) {
-    if (b.ensure(v.size() * sizeof(E)) != 0) return -1;
-    ASC_CUDA_OK(cudaMemcpy(b.p, v.data(), v.size() * sizeof(E), cudaMemcpyHostToDevice));
-    return 0;
-}
-
-// ------------------------------------------------------------------ launch
-template <class F>
-static int launch(audiosync_cuda_ctx* ctx, DeviceState& d, int cls, cudaStream_t st, F&& fn) {
-    ProfileRecord rec{cls, nullptr, nullptr};
-    const bool prof = ctx->profile;
-    if (prof) {
-        std::lock_guard<std::mutex> lk(d.prof_mu);
-        for (cudaEvent_t* e : {&rec.e0, &rec.e1}) {
-            if (!d.event_pool.empty()) { *e = d.event_pool.back(); d.event_pool.pop_back(); }
-            else ASC_CUDA_OK(cudaEventCreate(e));
-        }
-        ASC_CUDA_OK(cudaEventRecord(rec.e0, st));
-    }
-    fn();
-    ASC_CUDA_OK(cudaGetLastError());
-    if (prof) {
-        ASC_CUDA_OK(cudaEventRecord(rec.e1, st));
-        std::lock_guard<std::mutex> lk(d.prof_mu);
-        d.prof_pending.push_back(rec);
-    }
-    ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    return 0;
-}
-
-// ------------------------------------------------------------ tensor maps
-// Column tiles are staged by the TMA unit from 3-D views [slice][row][2*M2 floats] of the
-// caller's arrays and of the workspace planes.  The descriptors are encoded on the host per
-// launch (cuTensorMapEncodeTiled, reached through the runtime: the library does not link
-// libcuda) and travel as grid-constant kernel parameters.
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn tensor_map_encoder() {
-    static const EncodeTiledFn fn = [] {
-        if (getenv("AUDIOSYNC_CUDA_NO_TMA_TILES")) return (EncodeTiledFn) nullptr;   // diagnostic knob: cp.async staging of the column tiles
-        void* f = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
-            q != cudaDriverEntryPointSuccess) {
-            cudaGetLastError();
-            f = nullptr;
-        }
-        return reinterpret_cast<EncodeTiledFn>(f);
-    }();
-    return fn;
-}
-// [slices][rows][2*M2 floats], `slice_pitch_bytes` between slices; box = 32 floats x box_rows x 1.
-static int make_tile_map(CUtensorMap* tm, const void* base, int M2, int rows, size_t slice_pitch_bytes,
-                         size_t slices, int box_rows) {
-    EncodeTiledFn enc = tensor_map_encoder();
-    if (!enc) return -1;
-    const cuuint64_t gdim[3] = {(cuuint64_t)2 * M2, (cuuint64_t)rows, (cuuint64_t)std::max<size_t>(slices, 1)};
-    const cuuint64_t gstride[2] = {(cuuint64_t)M2 * sizeof(cplx), (cuuint64_t)slice_pitch_bytes};
-    const cuuint32_t box[3] = {32u, (cuuint32_t)box_rows, 1u};
-    const cuuint32_t estride[3] = {1u, 1u, 1u};
-    // L2 promotion measured (64 / 128 / 256 B): no gain, 256 B costs K_C 0.25 us/pair
-    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstride, box, estride,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : -1;   // the caller falls back to cp.async staging
-}
-
-// Stage launches of the static path: programmatic dependent launch (see pdl_prologue).
-static bool pdl_enabled() {
-    static const bool on = getenv("AUDIOSYNC_CUDA_NO_PDL") == nullptr;   // diagnostic knob: plain stream-ordered launches
-    return on;
-}
-template <class... KArgs, class... Args>
-static void launch_stage(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);   // errors surface through cudaGetLastError in launch()
-}
-
-template <class K>
-static int prepare_kernel(size_t smem) {
-    if (smem > 48 * 1024)
-        ASC_CUDA_OK(cudaFuncSetAttribute(fft_kernel_entry<K>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return 0;
-}
-
-template <class P>
-static int run_static_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d,
-                           const void* src, const void* smp, int dtype, long long src_pitch,
-                           long long smp_pitch, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
-    using Col = typename P::Col;
-    using Row = typename P::Row;
-    constexpr int M1 = Col::n, M2 = Row::n;
-    cplx* planes = static_cast<cplx*>(ws);
-    const cplx* col_tw = static_cast<const cplx*>(plan->col_tw.p);
-    const cplx* row_tw = static_cast<const cplx*>(plan->row_tw.p);
-    const cplx* col_tc = static_cast<const cplx*>(plan->col_tc.p);
-    const cplx* row_rev = static_cast<const cplx*>(plan->row_rev.p);
-    const cplx* row_tab = static_cast<const cplx*>(plan->row_tab.p);
-    const cplx* m_lo = static_cast<const cplx*>(plan->m_lo.p);
-    const cplx* m_hi = static_cast<const cplx*>(plan->m_hi.p);
-    const dim3 grid_a(M2 / COL_T, 2, pairs);
-    auto col_fwd = [&](auto KK, const auto* s_in, const auto* m_in) -> int {
-        using K = decltype(KK);
-        typename K::Params p{s_in, m_in, planes, peaks, col_tw, col_tc, m_lo, m_hi, P::L, src_pitch, smp_pitch};
-        return launch(ctx, d, KC_COL_FWD, st, [&] {
-            launch_stage(fft_kernel_entry<K>, grid_a, dim3(K::THREADS), K::SMEM, st, p);
-        });
-    };
-    if (dtype == AUDIOSYNC_CUDA_F32) {
-        // cp.async staging needs 16-byte aligned rows: every pair / row offset is a multiple
-        // of 16 bytes, so only the base pointers decide.
-        static const bool no_async = getenv("AUDIOSYNC_CUDA_NOASYNC") != nullptr;   // experiment knob
-        const bool aligned = !no_async && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(smp)) & 15u) == 0 &&
-                             src_pitch % 4 == 0 && smp_pitch % 4 == 0;
-        const float* s_in = static_cast<const float*>(src);
-        const float* m_in = static_cast<const float*>(smp);
-        int rc;
-        using KT = ColFwdKernel<Col, Row::n, P::NT_COL, float, 2>;
-        typename KT::Params pt{s_in, m_in, planes, peaks, col_tw, col_tc, m_lo, m_hi, P::L, src_pitch, smp_pitch};
-        if (aligned && tensor_map_encoder() &&
-            make_tile_map(&pt.tm_src, s_in, M2, M1, (size_t)src_pitch * sizeof(float), (size_t)pairs,
-                          tile_box_rows(KT::SRC_ROWS)) == 0 &&
-            make_tile_map(&pt.tm_smp, m_in, M2, M1 / 2, (size_t)smp_pitch * sizeof(float), (size_t)pairs,
-                          tile_box_rows(KT::SMP_ROWS)) == 0) {
-            rc = launch(ctx, d, KC_COL_FWD, st, [&] {
-                launch_stage(fft_kernel_entry<KT>, grid_a, dim3(KT::THREADS), KT::SMEM, st, pt);
-            });
-        } else {
-            rc = aligned ? col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, float, 1>{}, s_in, m_in)
-                         : col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, float, 0>{}, s_in, m_in);
-        }
-        if (rc != 0) return -1;
-    } else {
-        if (col_fwd(ColFwdKernel<Col, Row::n, P::NT_COL, double, 0>{}, static_cast<const double*>(src),
-                    static_cast<const double*>(smp)) != 0) return -1;
-    }
-    {
-        using K = RowFusedKernel<Row, Col::n, P::NT_ROW>;
-        typename K::Params p{planes, row_tw, row_rev, m_lo, m_hi, P::L, row_tab};
-        const dim3 grid(M1 / 2 + 1, 1, pairs);
-        if (launch(ctx, d, KC_ROW_FUSED, st, [&] {
-                launch_stage(fft_kernel_entry<K>, grid, dim3(K::THREADS), K::SMEM, st, p);
-            }) != 0) return -1;
-    }
-    using KCT = ColInvKernel<Col, Row::n, P::NT_COL, true>;
-    typename KCT::Params pct{planes, peaks, col_tw, P::L};
-    if (tensor_map_encoder() &&
-        make_tile_map(&pct.tm, planes, M2, M1, (size_t)P::L * sizeof(cplx), (size_t)2 * pairs,
-                      tile_box_rows(KCT::TMA_ROWS)) == 0) {
-        const dim3 grid(pairs, M2 / COL_T, 1);
-        if (launch(ctx, d, KC_COL_INV, st, [&] {
-                launch_stage(fft_kernel_entry<KCT>, grid, dim3(KCT::THREADS), KCT::SMEM, st, pct);
-            }) != 0) return -1;
-    } else {
-        using K = ColInvKernel<Col, Row::n, P::NT_COL>;
-        typename K::Params p{planes, peaks, col_tw, P::L};
-        const dim3 grid(pairs, M2 / COL_T, 1);
-        if (launch(ctx, d, KC_COL_INV, st, [&] {
-                launch_stage(fft_kernel_entry<K>, grid, dim3(K::THREADS), K::SMEM, st, p);
-            }) != 0) return -1;
-    }
-    return 0;
-}
-
-
-template <class P>
-static int build_static_plan(FftPlan* plan) {
-    using Col = typename P::Col;
-    using Row = typename P::Row;
-    plan->kind = PATH_STATIC_FFT;
-    plan->L = P::L;
-    plan->M1 = Col::n;
-    plan->M2 = Row::n;
-    plan->ws_bytes_per_pair = (size_t)2 * P::L * sizeof(cplx);
-    std::string d = "fft L=" + std::to_string(P::L) + " M1=" + std::to_string(Col::n) +
-                    " M2=" + std::to_string(Row::n) + " col=";
-    for (int i = 0; i < Col::count; i++) d += (i ? "x" : "") + std::to_string(Col::r(i));
-    d += " row=";
-    for (int i = 0; i < Row::count; i++) d += (i ? "x" : "") + std::to_string(Row::r(i));
-    d += " static four-step fp32";
-    plan->desc = d;
-    std::vector<cplx> m_lo, m_hi;
-    build_two_level(P::L, P::L - 1, m_lo, m_hi);
-    if (upload(plan->col_tw, build_pass_tables(radix_vector<Col>())) != 0 ||
-        upload(plan->row_tw, build_pass_tables(radix_vector<Row>())) != 0 ||
-        upload(plan->col_tc, build_col_tc(P::L, Col::weight(Col::count - 1))) != 0 ||
-        upload(plan->row_rev, build_row_rev<Row>()) != 0 ||
-        upload(plan->row_tab, build_row_tab<Row>(P::L, Col::n)) != 0 ||
-        upload(plan->m_lo, m_lo) != 0 || upload(plan->m_hi, m_hi) != 0)
-        return -1;
-    if (prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, 2>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, 2>::SMEM) != 0 ||
-        prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, 1>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, 1>::SMEM) != 0 ||
-        prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, float, 0>>(ColFwdKernel<Col, Row::n, P::NT_COL, float, 0>::SMEM) != 0 ||
-        prepare_kernel<ColFwdKernel<Col, Row::n, P::NT_COL, double, 0>>(ColFwdKernel<Col, Row::n, P::NT_COL, double, 0>::SMEM) != 0 ||
-        prepare_kernel<RowFusedKernel<Row, Col::n, P::NT_ROW>>(RowFusedKernel<Row, Col::n, P::NT_ROW>::SMEM) != 0 ||
-        prepare_kernel<ColInvKernel<Col, Row::n, P::NT_COL, true>>(ColInvKernel<Col, Row::n, P::NT_COL, true>::SMEM) != 0 ||
-        prepare_kernel<ColInvKernel<Col, Row::n, P::NT_COL>>(ColInvKernel<Col, Row::n, P::NT_COL>::SMEM) != 0)
-        return -1;
-    plan->run_wave = [plan](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
-                            int dtype, long long sp, long long mp, void* ws, PairPeak* peaks, int pairs,
-                            cudaStream_t st) {
-        return run_static_wave<P>(plan, ctx, d, src, smp, dtype, sp, mp, ws, peaks, pairs, st);
-    };
-    return 0;
-}
-
 template <typename InT>
 static int run_small_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d, const void* src,
                           const void* smp, long long sp, long long mp, PairPeak* peaks, int pairs,
@@ -363,84 +120,6 @@ static int build_small_plan(FftPlan* plan, long long L) {
                             cudaStream_t st) {
         return dtype == AUDIOSYNC_CUDA_F32 ? run_small_wave<float>(plan, ctx, d, src, smp, sp, mp, peaks, pairs, st)
                                            : run_small_wave<double>(plan, ctx, d, src, smp, sp, mp, peaks, pairs, st);
-    };
-    return 0;
-}
-
-// ------------------------------------------------- runtime-radix four-step plans (any length)
-template <class K>
-static int prepare_gen_kernel(size_t smem) {
-    if (smem > 48 * 1024)
-        ASC_CUDA_OK(cudaFuncSetAttribute(gen_kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return 0;
-}
-
-template <typename T, typename InT>
-static int run_generic_wave(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
-                            long long sp, long long mp, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
-    typedef typename GenTraits<T>::C C;
-    const GenShape& sh = plan->gen;
-    C* planes = static_cast<C*>(ws);
-    const C* wcol = static_cast<const C*>(plan->g_wcol.p);
-    const C* wrow = static_cast<const C*>(plan->g_wrow.p);
-    const C* lo = static_cast<const C*>(plan->g_lo.p);
-    const C* hi = static_cast<const C*>(plan->g_hi.p);
-    const int* p2f_col = static_cast<const int*>(plan->g_p2f_col.p);
-    const int* p2f_row = static_cast<const int*>(plan->g_p2f_row.p);
-    const int* f2p_row = static_cast<const int*>(plan->g_f2p_row.p);
-    {
-        using K = GenColFwdKernel<T, InT>;
-        typename K::Params p{static_cast<const InT*>(src), static_cast<const InT*>(smp), planes, peaks, wcol, lo, hi,
-                             p2f_col, sh, sp, mp};
-        const dim3 grid((sh.M2 + K::CT - 1) / K::CT, 2, pairs);
-        if (launch(ctx, d, KC_COL_FWD, st, [&] {
-                launch_stage(gen_kernel_entry<K>, grid, dim3(K::THREADS), K::smem_bytes(sh), st, p);
-            }) != 0) return -1;
-    }
-    {
-        using K = GenRowFusedKernel<T>;
-        typename K::Params p{planes, wrow, lo, hi, p2f_row, f2p_row, sh};
-        const dim3 grid(sh.M1 / 2 + 1, 1, pairs);
-        if (launch(ctx, d, KC_ROW_FUSED, st, [&] {
-                launch_stage(gen_kernel_entry<K>, grid, dim3(K::THREADS), K::smem_bytes(sh), st, p);
-            }) != 0) return -1;
-    }
-    {
-        using K = GenColInvKernel<T>;
-        typename K::Params p{planes, peaks, wcol, p2f_col, sh, reinterpret_cast<T*>(planes)};
-        const dim3 grid(pairs, (sh.M2 + K::CT - 1) / K::CT, 1);
-        if (launch(ctx, d, KC_COL_INV, st, [&] {
-                launch_stage(gen_kernel_entry<K>, grid, dim3(K::THREADS), K::smem_bytes(sh), st, p);
-            }) != 0) return -1;
-    }
-    if constexpr (sizeof(T) == 8) {
-        // fp64: r[0 .. 2L) of pair i sits in its (dead) sample plane; full double keys
-        const double* r = reinterpret_cast<const double*>(planes) + 2 * sh.M;
-        if (launch(ctx, d, KC_ARGMAX_F64, st, [&] {
-                argmax_f64_kernel<<<pairs, 1024, 0, st>>>(r, 2 * sh.L, 4 * sh.M, peaks);
-            }) != 0) return -1;
-    }
-    return 0;
-}
-
-template <typename T>
-static int build_generic_plan_t(FftPlan* plan) {
-    typedef typename GenTraits<T>::C C;
-    const GenShape& sh = plan->gen;
-    const GenTables<C> tb = gen_build_tables<C>(sh);
-    if (upload(plan->g_wcol, tb.wcol) != 0 || upload(plan->g_wrow, tb.wrow) != 0 || upload(plan->g_lo, tb.m_lo) != 0 ||
-        upload(plan->g_hi, tb.m_hi) != 0 || upload(plan->g_p2f_col, tb.p2f_col) != 0 ||
-        upload(plan->g_p2f_row, tb.p2f_row) != 0 || upload(plan->g_f2p_row, tb.f2p_row) != 0)
-        return -1;
-    if (prepare_gen_kernel<GenColFwdKernel<T, float>>(GenColFwdKernel<T, float>::smem_bytes(sh)) != 0 ||
-        prepare_gen_kernel<GenColFwdKernel<T, double>>(GenColFwdKernel<T, double>::smem_bytes(sh)) != 0 ||
-        prepare_gen_kernel<GenRowFusedKernel<T>>(GenRowFusedKernel<T>::smem_bytes(sh)) != 0 ||
-        prepare_gen_kernel<GenColInvKernel<T>>(GenColInvKernel<T>::smem_bytes(sh)) != 0)
-        return -1;
-    plan->run_wave = [plan](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp, int dtype,
-                            long long sp, long long mp, void* ws, PairPeak* peaks, int pairs, cudaStream_t st) {
-        return dtype == AUDIOSYNC_CUDA_F32 ? run_generic_wave<T, float>(plan, ctx, d, src, smp, sp, mp, ws, peaks, pairs, st)
-                                           : run_generic_wave<T, double>(plan, ctx, d, src, smp, sp, mp, ws, peaks, pairs, st);
     };
     return 0;
 }

@@ -172,6 +172,15 @@ ASC_HD void cp_async16(void* smem_dst, const void* gmem_src) {
     memcpy(smem_dst, gmem_src, 16);
 #endif
 }
+// the same for 8-byte elements (rows with an odd padding pitch are only 8-byte aligned)
+ASC_HD void cp_async8(void* smem_dst, const void* gmem_src) {
+#if defined(__CUDA_ARCH__)
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+#else
+    memcpy(smem_dst, gmem_src, 8);
+#endif
+}
 ASC_HD void cp_async_wait_all() {
 #if defined(__CUDA_ARCH__)
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -524,8 +533,8 @@ ASC_HD void dft_reg(C (&v)[R]) { DftReg<R, DIR, C>::run(v); }
 // any other k is the product w[hb(k)] * w[k - hb(k)] (at most 3 products deep
 // for R <= 16, i.e. a few ulp).  Trades LSU wavefronts for FMA-pipe work.
 // Fills w[k], k not a power of two, from the power-of-two entries already in w.
-template <int R>
-ASC_HD void fill_twiddles(cplx (&w)[R]) {
+template <int R, class C = cplx>
+ASC_HD void fill_twiddles(C (&w)[R]) {
     static_for<1, R>([&](auto K) {
         constexpr int k = decltype(K)::value;
         if constexpr ((k & (k - 1)) != 0) {

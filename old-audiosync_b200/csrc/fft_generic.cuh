@@ -28,21 +28,60 @@
 
 namespace asc {
 
+#ifndef ASC_GEN_MIN_CTAS
+#define ASC_GEN_MIN_CTAS 3       // resident CTAs per SM the fp32 runtime-radix kernels are compiled for (85 registers)
+#endif
 constexpr int GEN_MAX_PASSES = 8;
 constexpr int GEN_THREADS = 256;
+
+// Division of a small unsigned number by a runtime constant without a divide: q = n / d for
+// n < 2^31 (Granlund-Montgomery: m = ceil(2^(31 + ceil(log2 d)) / d)); powers of two shift.
+struct FastDiv { unsigned m, s; };
+inline FastDiv make_fastdiv(unsigned d) {
+    FastDiv f{0u, 0u};
+    unsigned l = 0;
+    while ((1u << l) < d) l++;                   // ceil(log2 d)
+    if ((1u << l) == d) { f.m = 0u; f.s = l; return f; }
+    const unsigned long long p = 1ull << (31 + l);
+    f.m = (unsigned)((p + d - 1) / d);
+    f.s = l - 1;
+    return f;
+}
+ASC_HD unsigned fast_div(unsigned n, FastDiv f) {
+#if defined(__CUDA_ARCH__)
+    return f.m ? (__umulhi(n, f.m) >> f.s) : (n >> f.s);
+#else
+    return f.m ? ((unsigned)(((unsigned long long)n * f.m) >> 32) >> f.s) : (n >> f.s);
+#endif
+}
 
 struct GenAxis {
     int n;                         // axis length
     int npass;
     int radix[GEN_MAX_PASSES];
     int stride[GEN_MAX_PASSES];    // s(p) = n / (r(0) * ... * r(p)); in-place DIF order as RadixList
+    FastDiv div_stride[GEN_MAX_PASSES];   // / s(p)
+    FastDiv div_items[GEN_MAX_PASSES];    // / (n / r(p)): butterflies of one row in pass p
 };
+
+// Twiddles W^(j*k), k = 1 .. R-1, of one butterfly from a full table of the axis (`step` = table
+// entries per unit of j*k): the power-of-two multiples are read, the others are products of two
+// or three of those (as in pass_twiddles) -- four table reads instead of fifteen at radix 16.
+template <int R, class C>
+ASC_HD void gen_twiddles(const C* __restrict__ tab, int j, int step, C (&w)[R]) {
+    static_for<1, R>([&](auto K) {
+        constexpr int k = decltype(K)::value;
+        if constexpr ((k & (k - 1)) == 0) w[k] = ldg(tab + j * (k * step));
+    });
+    fill_twiddles<R, C>(w);
+}
 
 struct GenShape {
     long long L;        // sample_len
     long long M;        // complex transform length; N' = 2M real points; M == L unless embedded
     long long src_ext;  // real points of the (periodically extended) source: 2L exact, 3L embedded
     int M1, M2;
+    int ct;             // columns per tile of the column kernels (fp32: 16 or 8, fp64: 8)
     GenAxis col, row;
 };
 
@@ -86,11 +125,26 @@ ASC_HD C gen_tw2(const C* __restrict__ lo, const C* __restrict__ hi, unsigned a)
 }
 
 // Packed point n = (real 2n, real 2n + 1) of a signal.  Source: x[i mod 2L] for i < src_ext, zero
-// beyond; sample: y[i] for i < L, zero beyond (the zero pad of reference :159-166).
+// beyond; sample: y[i] for i < L, zero beyond (the zero pad of reference :159-166).  Points below
+// `fast_pts` lie wholly inside the array proper and are read as one vector load (`vec`: the pair's
+// base is aligned to two elements).
 template <class C, typename InT>
-ASC_HD C gen_load_point(const InT* __restrict__ x, long long n, int sig, long long L, long long src_ext) {
+ASC_HD C gen_load_point(const InT* __restrict__ x, unsigned n, int sig, long long L, long long src_ext,
+                        unsigned fast_pts, bool vec) {
     typedef typename scalar_of<C>::type real;
-    const long long i0 = 2 * n, i1 = 2 * n + 1;
+    if (n < fast_pts) {
+        if (vec) {
+            if constexpr (sizeof(InT) == 4) {
+                const float2 d = ldg(reinterpret_cast<const float2*>(x) + n);
+                return cmake((real)d.x, (real)d.y);
+            } else {
+                const double2 d = ldg(reinterpret_cast<const double2*>(x) + n);
+                return cmake((real)d.x, (real)d.y);
+            }
+        }
+        return cmake((real)ldg(x + 2 * (size_t)n), (real)ldg(x + 2 * (size_t)n + 1));
+    }
+    const long long i0 = 2 * (long long)n, i1 = i0 + 1;
     real a = (real)0, b = (real)0;
     if (sig == 0) {
         if (i0 < src_ext) a = (real)ldg(x + (i0 < 2 * L ? i0 : i0 - 2 * L));
@@ -100,6 +154,18 @@ ASC_HD C gen_load_point(const InT* __restrict__ x, long long n, int sig, long lo
         if (i1 < L) b = (real)ldg(x + i1);
     }
     return cmake(a, b);
+}
+
+// W^k for k = 1 .. R-1 given the power-of-two powers in g[1], g[2], g[4], g[8]: at most three
+// products deep (k < 16).
+template <int K, class C>
+ASC_HD C gen_pow_from_pow2(const C (&g)[9]) {
+    if constexpr ((K & (K - 1)) == 0) {
+        return g[K];
+    } else {
+        constexpr int hb = (K >= 8) ? 8 : (K >= 4) ? 4 : 2;
+        return cmul(g[hb], gen_pow_from_pow2<K - hb, C>(g));
+    }
 }
 
 // Runs f(IC<R>) for the runtime radix r (one of the supported set).
@@ -124,13 +190,16 @@ constexpr bool gen_radix_supported(int r) {
 }
 
 // --------------------------------------------------------------------- G_A
-// Forward column pass of both signals: grid = (ceil(M2 / CT), 2, pairs).
-template <typename T, typename InT>
+// Forward column pass of both signals: grid = (ceil(M2 / CT), 2, pairs).  A thread keeps its
+// column (THREADS is a multiple of CT) and walks the butterflies of that column.
+template <typename T, typename InT, int CT_ = GenTraits<T>::CT>
 struct GenColFwdKernel {
     typedef typename GenTraits<T>::C C;
-    static constexpr int CT = GenTraits<T>::CT;
+    static constexpr int CT = CT_;
     static constexpr int THREADS = GEN_THREADS;
-    static constexpr int MIN_CTAS = sizeof(T) == 4 ? 2 : 1;
+    static constexpr int TR = THREADS / CT;          // butterflies of one column handled per sweep
+    static constexpr int MIN_CTAS = sizeof(T) == 4 ? ASC_GEN_MIN_CTAS : 1;
+    static_assert(THREADS % CT == 0, "a thread must keep its column");
 
     struct Params {
         const InT* sources;
@@ -143,6 +212,7 @@ struct GenColFwdKernel {
         const int* p2f_col;      // frequency held at position i after the DIF passes
         GenShape sh;
         long long src_pitch, smp_pitch;
+        int vec_src, vec_smp;    // the arrays may be read two elements at a time
     };
     static size_t smem_bytes(const GenShape& sh) { return (size_t)sh.M1 * CT * sizeof(C) + 16; }
 
@@ -155,41 +225,70 @@ struct GenColFwdKernel {
         const long long pair = ex.bz();
         const InT* __restrict__ x = sig == 0 ? p.sources + pair * p.src_pitch : p.samples + pair * p.smp_pitch;
         C* __restrict__ out = p.planes + (pair * 2 + sig) * sh.M;
+        const bool vec = sig == 0 ? p.vec_src != 0 : p.vec_smp != 0;
+        const long long fast_reals = sig == 0 ? (sh.src_ext < 2 * sh.L ? sh.src_ext : 2 * sh.L) : sh.L;
+        const unsigned fast_pts = (unsigned)(fast_reals / 2);
         const int P = sh.col.npass;
         for (int ps = 0; ps < P; ps++) {
             const int S = sh.col.stride[ps];
             const bool first = ps == 0, last = ps == P - 1;
             gen_dispatch_radix(sh.col.radix[ps], [&](auto RR) {
                 constexpr int R = decltype(RR)::value;
-                const int items = (M1 / R) * CT;
+                const int nbf = M1 / R;
                 const int tstep = M1 / (S * R);
+                const FastDiv dS = sh.col.div_stride[ps];
                 ex.phase([&](int tid) {
                     if (first && tid == 0 && ex.bx() == 0 && sig == 0) p.peaks[pair] = cleared_peak();
-                    for (int w = tid; w < items; w += THREADS) {
-                        const int c = w % CT, bf = w / CT;
-                        const int n2 = c0 + c;
-                        if (n2 >= M2) continue;
-                        const int blk = bf / S, j = bf - blk * S;
-                        const int i0 = blk * (S * R) + j;
-                        C v[R];
-                        static_for<0, R>([&](auto Q) {
-                            constexpr int q = decltype(Q)::value;
-                            if (first) v[q] = gen_load_point<C, InT>(x, (long long)(i0 + q * S) * M2 + n2, sig, sh.L, sh.src_ext);
-                            else v[q] = buf[(i0 + q * S) * CT + c];
-                        });
-                        dft_reg<R, -1, C>(v);
-                        if (!last) {
+                    const int c = tid % CT;
+                    const unsigned n2 = (unsigned)(c0 + c);
+                    if ((int)n2 >= M2) return;
+                    auto load = [&](int i0, C (&v)[R]) {
+                        if (first) {
+                            static_for<0, R>([&](auto Q) {
+                                constexpr int q = decltype(Q)::value;
+                                v[q] = gen_load_point<C, InT>(x, (unsigned)(i0 + q * S) * (unsigned)M2 + n2, sig, sh.L, sh.src_ext, fast_pts, vec);
+                            });
+                        } else {
+                            static_for<0, R>([&](auto Q) { v[decltype(Q)::value] = buf[(i0 + decltype(Q)::value * S) * CT + c]; });
+                        }
+                    };
+                    if (!last) {
+                        for (int bf = tid / CT; bf < nbf; bf += TR) {
+                            const int blk = (int)fast_div((unsigned)bf, dS), j = bf - blk * S;
+                            const int i0 = blk * (S * R) + j;
+                            C v[R];
+                            load(i0, v);
+                            dft_reg<R, -1, C>(v);
+                            C t[R];
+                            gen_twiddles<R, C>(p.wcol, j, tstep, t);
                             buf[i0 * CT + c] = v[0];
                             static_for<1, R>([&](auto K) {
                                 constexpr int k = decltype(K)::value;
-                                buf[(i0 + k * S) * CT + c] = cmul(v[k], ldg(p.wcol + j * k * tstep));
+                                buf[(i0 + k * S) * CT + c] = cmul(v[k], t[k]);
                             });
-                        } else {
-                            // S == 1: position i0 + k holds bin k1 = p2f[i0 + k]; times W_M^(n2 * k1)
-                            static_for<0, R>([&](auto K) {
+                        }
+                    } else {
+                        // S == 1: positions i0 .. i0+R-1 hold bins k1 = f0 + k * Wt (f0 = bin at i0, Wt = M1 / R).
+                        // W_M^(n2 * k1) = W_M^(n2 * f0) * (W_M^(n2 * Wt))^k: the second factor from four
+                        // per-thread constants (powers 1, 2, 4, 8), the first from the two-level table.
+                        const unsigned Wt = (unsigned)(M1 / R);
+                        C g[9];
+                        static_for<0, 4>([&](auto I) {
+                            constexpr int k = 1 << decltype(I)::value;
+                            if constexpr (k < R) g[k] = gen_tw2<C>(p.m_lo, p.m_hi, n2 * Wt * (unsigned)k);
+                        });
+                        for (int bf = tid / CT; bf < nbf; bf += TR) {
+                            const int i0 = bf * R;
+                            C v[R];
+                            load(i0, v);
+                            dft_reg<R, -1, C>(v);
+                            const unsigned f0 = (unsigned)ldg(p.p2f_col + i0);
+                            const C t0 = gen_tw2<C>(p.m_lo, p.m_hi, n2 * f0);
+                            C* __restrict__ o = out + (f0 * (unsigned)M2 + n2);
+                            o[0] = cmul(v[0], t0);
+                            static_for<1, R>([&](auto K) {
                                 constexpr int k = decltype(K)::value;
-                                const int k1 = ldg(p.p2f_col + i0 + k);
-                                out[(long long)k1 * M2 + n2] = cmul(v[k], gen_tw2<C>(p.m_lo, p.m_hi, (unsigned)n2 * (unsigned)k1));
+                                o[(size_t)k * Wt * (unsigned)M2] = cmul(v[k], cmul(t0, gen_pow_from_pow2<k, C>(g)));
                             });
                         }
                     }
@@ -201,19 +300,21 @@ struct GenColFwdKernel {
 
 // --------------------------------------------------------------------- G_B
 // Forward rows of both planes, split / conj-multiply / merge, inverse rows: grid = (M1/2 + 1, 1, pairs).
+// Rows are padded by one point per 128 bytes (phys), which keeps every pass -- also the stride-1
+// pass of an even radix, e.g. power-of-two lengths -- free of bank conflicts.
 template <typename T>
 struct GenRowFusedKernel {
     typedef typename GenTraits<T>::C C;
     static constexpr int PADSH = GenTraits<T>::PADSH;
     static constexpr int THREADS = GEN_THREADS;
-    static constexpr int MIN_CTAS = sizeof(T) == 4 ? 2 : 1;
+    static constexpr int MIN_CTAS = sizeof(T) == 4 ? ASC_GEN_MIN_CTAS : 1;
 
     struct Params {
         C* planes;
         const C* wrow;           // exp(-2*pi*i*t/M2), t < M2
+        const C* wpos;           // exp(-2*pi*i*freq_of_pos(e)/M2), position order (the split's twiddle)
         const C* m_lo;
         const C* m_hi;
-        const int* p2f_row;      // frequency at position
         const int* f2p_row;      // position of frequency
         GenShape sh;
     };
@@ -235,16 +336,23 @@ struct GenRowFusedKernel {
         C* __restrict__ plane_p = plane_s + sh.M;
         const int P = sh.row.npass;
 
-        // stage: slots 0,1 source rows (k1a, k1b); 2,3 sample rows
+        // stage: slots 0,1 source rows (k1a, k1b); 2,3 sample rows.  Asynchronous copies, one element
+        // each (the padded rows are element-aligned only), all in flight before the first wait.
         ex.phase([&](int tid) {
             for (int slot = 0; slot < 4; slot++) {
                 const int rr = slot & 1;
                 if (rr == 1 && !two) continue;
                 const C* __restrict__ g = (slot >= 2 ? plane_p : plane_s) + (long long)(rr ? k1b : k1a) * M2;
                 C* __restrict__ row = buf + slot * RP;
-                for (int e = tid; e < M2; e += THREADS) row[phys(e)] = ldg(g + e);
+                for (int e = tid; e < M2; e += THREADS) {
+                    if constexpr (sizeof(C) == 8) cp_async8(row + phys(e), g + e);
+                    else cp_async16(row + phys(e), g + e);
+                }
             }
+            cp_async_wait_all();
         });
+        // (element i0 + q * S of a padded row: when S is a multiple of the padding period the
+        // physical stride is the constant S + S / period -- the `regular` passes below)
         // forward DIF on 2 * nrows rows (slots 0,1,2,3 or 0,2)
         for (int ps = 0; ps < P; ps++) {
             const int S = sh.row.stride[ps];
@@ -253,20 +361,36 @@ struct GenRowFusedKernel {
                 const int per_row = M2 / R;
                 const int items = per_row * 2 * nrows;
                 const int tstep = M2 / (S * R);
+                const FastDiv dS = sh.row.div_stride[ps], dI = sh.row.div_items[ps];
+                const bool regular = (S & ((1 << PADSH) - 1)) == 0;
+                const int SP = S + (S >> PADSH);
                 ex.phase([&](int tid) {
                     for (int w = tid; w < items; w += THREADS) {
-                        const int bw = w / per_row, bf = w - bw * per_row;
+                        const int bw = (int)fast_div((unsigned)w, dI), bf = w - bw * per_row;
                         C* __restrict__ row = buf + (two ? bw : 2 * bw) * RP;
-                        const int blk = bf / S, j = bf - blk * S;
+                        const int blk = (int)fast_div((unsigned)bf, dS), j = bf - blk * S;
                         const int i0 = blk * (S * R) + j;
                         C v[R];
-                        static_for<0, R>([&](auto Q) { v[decltype(Q)::value] = row[phys(i0 + decltype(Q)::value * S)]; });
-                        dft_reg<R, -1, C>(v);
-                        row[phys(i0)] = v[0];
-                        static_for<1, R>([&](auto K) {
-                            constexpr int k = decltype(K)::value;
-                            row[phys(i0 + k * S)] = S > 1 ? cmul(v[k], ldg(p.wrow + j * k * tstep)) : v[k];
-                        });
+                        if (regular) {
+                            C* __restrict__ b0 = row + phys(i0);
+                            static_for<0, R>([&](auto Q) { v[decltype(Q)::value] = b0[decltype(Q)::value * SP]; });
+                            dft_reg<R, -1, C>(v);
+                            C t[R];
+                            gen_twiddles<R, C>(p.wrow, j, tstep, t);
+                            b0[0] = v[0];
+                            static_for<1, R>([&](auto K) { b0[decltype(K)::value * SP] = cmul(v[decltype(K)::value], t[decltype(K)::value]); });
+                        } else {
+                            static_for<0, R>([&](auto Q) { v[decltype(Q)::value] = row[phys(i0 + decltype(Q)::value * S)]; });
+                            dft_reg<R, -1, C>(v);
+                            row[phys(i0)] = v[0];
+                            if (S > 1) {
+                                C t[R];
+                                gen_twiddles<R, C>(p.wrow, j, tstep, t);
+                                static_for<1, R>([&](auto K) { row[phys(i0 + decltype(K)::value * S)] = cmul(v[decltype(K)::value], t[decltype(K)::value]); });
+                            } else {
+                                static_for<1, R>([&](auto K) { row[phys(i0 + decltype(K)::value)] = v[decltype(K)::value]; });
+                            }
+                        }
                     }
                 });
             });
@@ -281,7 +405,7 @@ struct GenRowFusedKernel {
                 C* __restrict__ zp_b = buf + 3 * RP;
                 for (int e = tid; e < M2; e += THREADS) {
                     const int pa = phys(e), pb = phys(M2 - 1 - e);
-                    const C w2 = cmul(ldg(p.wrow + ldg(p.p2f_row + e)), wk1);
+                    const C w2 = cmul(ldg(p.wpos + e), wk1);
                     C qk, qmk;
                     gen_split_mul_merge<C>(zs_a[pa], zs_b[pb], zp_a[pa], zp_b[pb], w2, qk, qmk);
                     zs_a[pa] = qk;
@@ -300,7 +424,7 @@ struct GenRowFusedKernel {
                         ea = e;
                         eb = M2 - 1 - e;
                     }
-                    const C w2 = cmul(ldg(p.wrow + ldg(p.p2f_row + ea)), wk1);
+                    const C w2 = cmul(ldg(p.wpos + ea), wk1);
                     const int pa = phys(ea), pb = phys(eb);
                     C qk, qmk;
                     gen_split_mul_merge<C>(zs[pa], zs[pb], zp[pa], zp[pb], w2, qk, qmk);
@@ -317,31 +441,47 @@ struct GenRowFusedKernel {
                 const int per_row = M2 / R;
                 const int items = per_row * nrows;
                 const int tstep = M2 / (S * R);
+                const FastDiv dS = sh.row.div_stride[ps], dI = sh.row.div_items[ps];
+                const bool regular = (S & ((1 << PADSH) - 1)) == 0;
+                const int SP = S + (S >> PADSH);
                 ex.phase([&](int tid) {
                     for (int w = tid; w < items; w += THREADS) {
-                        const int rw = w / per_row, bf = w - rw * per_row;
+                        const int rw = (int)fast_div((unsigned)w, dI), bf = w - rw * per_row;
                         C* __restrict__ row = buf + rw * RP;
-                        const int blk = bf / S, j = bf - blk * S;
+                        const int blk = (int)fast_div((unsigned)bf, dS), j = bf - blk * S;
                         const int i0 = blk * (S * R) + j;
                         C v[R];
-                        v[0] = row[phys(i0)];
-                        static_for<1, R>([&](auto Q) {
-                            constexpr int q = decltype(Q)::value;
-                            const C xq = row[phys(i0 + q * S)];
-                            v[q] = S > 1 ? cmulc(xq, ldg(p.wrow + j * q * tstep)) : xq;
-                        });
-                        dft_reg<R, +1, C>(v);
-                        static_for<0, R>([&](auto K) { row[phys(i0 + decltype(K)::value * S)] = v[decltype(K)::value]; });
+                        if (regular) {
+                            C* __restrict__ b0 = row + phys(i0);
+                            C t[R];
+                            gen_twiddles<R, C>(p.wrow, j, tstep, t);
+                            v[0] = b0[0];
+                            static_for<1, R>([&](auto Q) { v[decltype(Q)::value] = cmulc(b0[decltype(Q)::value * SP], t[decltype(Q)::value]); });
+                            dft_reg<R, +1, C>(v);
+                            static_for<0, R>([&](auto K) { b0[decltype(K)::value * SP] = v[decltype(K)::value]; });
+                        } else {
+                            v[0] = row[phys(i0)];
+                            if (S > 1) {
+                                C t[R];
+                                gen_twiddles<R, C>(p.wrow, j, tstep, t);
+                                static_for<1, R>([&](auto Q) { v[decltype(Q)::value] = cmulc(row[phys(i0 + decltype(Q)::value * S)], t[decltype(Q)::value]); });
+                            } else {
+                                static_for<1, R>([&](auto Q) { v[decltype(Q)::value] = row[phys(i0 + decltype(Q)::value)]; });
+                            }
+                            dft_reg<R, +1, C>(v);
+                            static_for<0, R>([&](auto K) { row[phys(i0 + decltype(K)::value * S)] = v[decltype(K)::value]; });
+                        }
                     }
                 });
             });
         }
         // natural order now: times conj W_M^(n2 * k1), back in place (row k1 of plane 0)
         ex.phase([&](int tid) {
-            for (int w = tid; w < M2 * nrows; w += THREADS) {
-                const int rw = w / M2, e = w - rw * M2;
-                const int k1 = rw ? k1b : k1a;
-                plane_s[(long long)k1 * M2 + e] = cmulc(buf[rw * RP + phys(e)], gen_tw2<C>(p.m_lo, p.m_hi, (unsigned)e * (unsigned)k1));
+            for (int rw = 0; rw < nrows; rw++) {
+                const unsigned k1 = (unsigned)(rw ? k1b : k1a);
+                C* __restrict__ o = plane_s + (size_t)k1 * (unsigned)M2;
+                for (int e = tid; e < M2; e += THREADS)
+                    o[e] = cmulc(buf[rw * RP + phys(e)], gen_tw2<C>(p.m_lo, p.m_hi, (unsigned)e * k1));
             }
         });
     }
@@ -351,12 +491,13 @@ struct GenRowFusedKernel {
 // Inverse column pass.  fp32: |r| argmax epilogue over the indices < limit (= 2L), the correlation
 // is never written.  fp64: r[0 .. limit) is written to `r_out` (the dead sample plane) and resolved
 // by argmax_f64_kernel, which keeps full double keys.  grid = (pairs, ceil(M2 / CT)).
-template <typename T>
+template <typename T, int CT_ = GenTraits<T>::CT>
 struct GenColInvKernel {
     typedef typename GenTraits<T>::C C;
-    static constexpr int CT = GenTraits<T>::CT;
+    static constexpr int CT = CT_;
     static constexpr int THREADS = GEN_THREADS;
-    static constexpr int MIN_CTAS = sizeof(T) == 4 ? 2 : 1;
+    static constexpr int TR = THREADS / CT;
+    static constexpr int MIN_CTAS = sizeof(T) == 4 ? ASC_GEN_MIN_CTAS : 1;
 
     struct Params {
         const C* planes;
@@ -378,84 +519,106 @@ struct GenColInvKernel {
         const int c0 = ex.by() * CT;
         const long long pair = ex.bx();
         const C* __restrict__ in = p.planes + pair * 2 * sh.M;
-        const long long limit = 2 * sh.L;
+        const unsigned limit = (unsigned)(2 * sh.L);          // < 2^31: M < 2^30
         const int P = sh.col.npass;
         for (int ps = 0; ps < P - 1; ps++) {
             const int S = sh.col.stride[ps];
             const bool first = ps == 0;
             gen_dispatch_radix(sh.col.radix[ps], [&](auto RR) {
                 constexpr int R = decltype(RR)::value;
-                const int items = (M1 / R) * CT;
+                const int nbf = M1 / R;
                 const int tstep = M1 / (S * R);
+                const FastDiv dS = sh.col.div_stride[ps];
                 ex.phase([&](int tid) {
-                    for (int w = tid; w < items; w += THREADS) {
-                        const int c = w % CT, bf = w / CT;
-                        const int n2 = c0 + c;
-                        if (n2 >= M2) continue;
-                        const int blk = bf / S, j = bf - blk * S;
+                    const int c = tid % CT;
+                    const int n2 = c0 + c;
+                    if (n2 >= M2) return;
+                    for (int bf = tid / CT; bf < nbf; bf += TR) {
+                        const int blk = (int)fast_div((unsigned)bf, dS), j = bf - blk * S;
                         const int i0 = blk * (S * R) + j;
                         C v[R];
-                        static_for<0, R>([&](auto Q) {
-                            constexpr int q = decltype(Q)::value;
-                            if (first) v[q] = ldg(in + (long long)(i0 + q * S) * M2 + n2);
-                            else v[q] = buf[(i0 + q * S) * CT + c];
-                        });
+                        if (first) {
+                            const C* __restrict__ g0 = in + ((unsigned)i0 * (unsigned)M2 + (unsigned)n2);
+                            static_for<0, R>([&](auto Q) { v[decltype(Q)::value] = ldg(g0 + (size_t)decltype(Q)::value * S * (unsigned)M2); });
+                        } else {
+                            static_for<0, R>([&](auto Q) { v[decltype(Q)::value] = buf[(i0 + decltype(Q)::value * S) * CT + c]; });
+                        }
                         dft_reg<R, +1, C>(v);
+                        C t[R];
+                        gen_twiddles<R, C>(p.wcol, j, tstep, t);
                         buf[i0 * CT + c] = v[0];
                         static_for<1, R>([&](auto K) {
                             constexpr int k = decltype(K)::value;
-                            buf[(i0 + k * S) * CT + c] = cmulc(v[k], ldg(p.wcol + j * k * tstep));
+                            buf[(i0 + k * S) * CT + c] = cmulc(v[k], t[k]);
                         });
                     }
                 });
             });
         }
-        // last pass (S == 1): packed point n = n1 * M2 + n2 carries r[2n] and r[2n + 1]
+        // last pass (S == 1): positions i0 .. i0+R-1 hold n1 = f0 + k * Wt; packed point
+        // n = n1 * M2 + n2 carries r[2n] (real part) and r[2n + 1] (imaginary part)
         const bool only = P == 1;
         gen_dispatch_radix(sh.col.radix[P - 1], [&](auto RR) {
             constexpr int R = decltype(RR)::value;
-            const int items = (M1 / R) * CT;
-            auto last_pass = [&](int tid, auto&& emit) {
-                for (int w = tid; w < items; w += THREADS) {
-                    const int c = w % CT, blk = w / CT;
-                    const int n2 = c0 + c;
-                    if (n2 >= M2) continue;
-                    const int i0 = blk * R;
-                    C v[R];
-                    static_for<0, R>([&](auto Q) {
-                        constexpr int q = decltype(Q)::value;
-                        if (only) v[q] = ldg(in + (long long)(i0 + q) * M2 + n2);
-                        else v[q] = buf[(i0 + q) * CT + c];
-                    });
-                    dft_reg<R, +1, C>(v);
-                    static_for<0, R>([&](auto K) {
-                        constexpr int k = decltype(K)::value;
-                        const long long n = (long long)ldg(p.p2f_col + i0 + k) * M2 + n2;
-                        emit(2 * n, v[k]);
-                    });
+            const int nbf = M1 / R;
+            const unsigned Wt = (unsigned)(M1 / R);
+            // butterfly bf of column n2 -> v[0 .. R), index of v[0].x
+            auto butterfly = [&](int bf, int c, int n2, C (&v)[R]) -> unsigned {
+                const int i0 = bf * R;
+                if (only) {
+                    const C* __restrict__ g0 = in + ((unsigned)i0 * (unsigned)M2 + (unsigned)n2);
+                    static_for<0, R>([&](auto Q) { v[decltype(Q)::value] = ldg(g0 + (size_t)decltype(Q)::value * (unsigned)M2); });
+                } else {
+                    static_for<0, R>([&](auto Q) { v[decltype(Q)::value] = buf[(i0 + decltype(Q)::value) * CT + c]; });
                 }
+                dft_reg<R, +1, C>(v);
+                return 2u * ((unsigned)ldg(p.p2f_col + i0) * (unsigned)M2 + (unsigned)n2);
             };
             if constexpr (sizeof(T) == 4) {
                 ex.phase_argmax(
                     [&](int tid) -> ArgmaxPair {
                         ArgmaxAcc acc;
-                        last_pass(tid, [&](long long i_re, C val) {
-                            if (i_re < limit) {
-                                if (i_re == 0) acc.consider_seed(val.x);
-                                else acc.consider(val.x, (uint32_t)i_re);
-                            }
-                            if (i_re + 1 < limit) acc.consider(val.y, (uint32_t)(i_re + 1));
-                        });
+                        const unsigned int seen = ex.peek_bits(&p.peaks[pair].second_bits);
+                        if (seen != 0u) acc.thr = float_from_order_bits(seen);
+                        const int c = tid % CT;
+                        const int n2 = c0 + c;
+                        if (n2 < M2)
+                        for (int bf = tid / CT; bf < nbf; bf += TR) {
+                            C v[R];
+                            const unsigned i_first = butterfly(bf, c, n2, v);
+                            // only values that reach the running second peak can matter
+                            float gm = fmaxf(fabsf(v[0].x), fabsf(v[0].y));
+                            static_for<1, R>([&](auto K) { gm = fmaxf(gm, fmaxf(fabsf(v[decltype(K)::value].x), fabsf(v[decltype(K)::value].y))); });
+                            if (!(gm >= acc.thr) && i_first != 0u && gm == gm) continue;
+                            static_for<0, R>([&](auto K) {
+                                constexpr int k = decltype(K)::value;
+                                const unsigned i_re = i_first + 2u * (unsigned)k * Wt * (unsigned)M2;
+                                if (i_re < limit) {
+                                    if (i_re == 0u) acc.consider_seed(v[k].x);
+                                    else acc.consider(v[k].x, i_re);
+                                }
+                                if (i_re + 1u < limit) acc.consider(v[k].y, i_re + 1u);
+                            });
+                        }
                         return acc.result();
                     },
                     &p.peaks[pair].key, &p.peaks[pair].second_bits, buf);
             } else {
                 T* __restrict__ r = p.r_out + (pair * 4 + 2) * sh.M;     // plane 1 of the pair, as reals
                 ex.phase([&](int tid) {
-                    last_pass(tid, [&](long long i_re, C val) {
-                        if (i_re < limit) r[i_re] = val.x;
-                        if (i_re + 1 < limit) r[i_re + 1] = val.y;
-                    });
+                    const int c = tid % CT;
+                    const int n2 = c0 + c;
+                    if (n2 >= M2) return;
+                    for (int bf = tid / CT; bf < nbf; bf += TR) {
+                        C v[R];
+                        const unsigned i_first = butterfly(bf, c, n2, v);
+                        static_for<0, R>([&](auto K) {
+                            constexpr int k = decltype(K)::value;
+                            const unsigned i_re = i_first + 2u * (unsigned)k * Wt * (unsigned)M2;
+                            if (i_re < limit) r[i_re] = v[k].x;
+                            if (i_re + 1u < limit) r[i_re + 1u] = v[k].y;
+                        });
+                    }
                 });
             }
         });

@@ -20,45 +20,49 @@ namespace asc {
 constexpr size_t GEN_SMEM_MAX = 220 * 1024;
 constexpr int GEN_RADICES[] = {16, 15, 12, 10, 9, 8, 6, 5, 4, 3, 2};
 
-// Fewest-pass factorisation of n into supported radices (0 passes: impossible).
-inline int gen_min_passes(int n, std::map<int, int>& memo) {
-    if (n == 1) return 0;
+// Relative cost of one in-place pass per point: a fixed part (shared-memory round trip, index
+// arithmetic, barrier) plus the butterfly's share -- measured on B200, a radix-5 pass costs about
+// 1.6 x a radix-16 pass.
+inline double gen_pass_cost(int r) { return 1.0 + 6.0 / (double)r; }
+
+// Cheapest factorisation of n into supported radices: (cost, passes); cost < 0: impossible.
+struct GenAxisCost { double cost; int passes; int first; };
+inline GenAxisCost gen_axis_cost(int n, std::map<int, GenAxisCost>& memo) {
+    if (n == 1) return GenAxisCost{0.0, 0, 1};
     auto it = memo.find(n);
     if (it != memo.end()) return it->second;
-    int best = 1 << 20;
+    GenAxisCost best{-1.0, 0, 0};
     for (int r : GEN_RADICES)
         if (n % r == 0) {
-            const int sub = gen_min_passes(n / r, memo);
-            if (sub + 1 < best) best = sub + 1;
+            const GenAxisCost sub = gen_axis_cost(n / r, memo);
+            if (sub.cost < 0.0) continue;
+            const double c = sub.cost + gen_pass_cost(r);
+            if (best.cost < 0.0 || c < best.cost - 1e-12) best = GenAxisCost{c, sub.passes + 1, r};
         }
     memo[n] = best;
     return best;
 }
 
 inline bool gen_make_axis(int n, GenAxis* ax) {
-    std::map<int, int> memo;
-    const int np = gen_min_passes(n, memo);
-    if (n < 2 || np > GEN_MAX_PASSES) return false;
+    std::map<int, GenAxisCost> memo;
+    const GenAxisCost top = gen_axis_cost(n, memo);
+    if (n < 2 || top.cost < 0.0 || top.passes > GEN_MAX_PASSES) return false;
     ax->n = n;
     ax->npass = 0;
-    int rest = n;
-    // largest radix first among the choices that keep the pass count minimal: the stride-1 pass
-    // ends up with the smallest radix
-    while (rest > 1) {
-        bool found = false;
-        for (int r : GEN_RADICES)
-            if (rest % r == 0 && gen_min_passes(rest / r, memo) == gen_min_passes(rest, memo) - 1) {
-                ax->radix[ax->npass++] = r;
-                rest /= r;
-                found = true;
-                break;
-            }
-        if (!found) return false;
+    std::vector<int> rs;
+    for (int rest = n; rest > 1;) {
+        const int r = gen_axis_cost(rest, memo).first;
+        rs.push_back(r);
+        rest /= r;
     }
+    std::sort(rs.begin(), rs.end(), [](int a, int b) { return a > b; });   // the stride-1 pass gets the smallest radix
+    for (int r : rs) ax->radix[ax->npass++] = r;
     long long prod = 1;
     for (int p = 0; p < ax->npass; p++) {
         prod *= ax->radix[p];
         ax->stride[p] = (int)(n / prod);
+        ax->div_stride[p] = make_fastdiv((unsigned)ax->stride[p]);
+        ax->div_items[p] = make_fastdiv((unsigned)(n / ax->radix[p]));
     }
     return true;
 }
@@ -84,36 +88,42 @@ inline std::vector<int> gen_freq2pos(const GenAxis& ax) {
     return t;
 }
 
-// Relative cost of a split (lower is better), 0 = unusable.  elem = bytes per complex point.
+// Relative cost of a split (lower is better), 0 = unusable.  elem = bytes per complex point,
+// ct = columns per tile.
 inline double gen_split_cost(long long M, int M1, int elem, int ct) {
     const long long M2 = M / M1;
     if (M1 < 2 || M2 < 2 || M2 > (1 << 20)) return 0.0;
     const size_t tile = (size_t)M1 * ct * elem, rows = (size_t)4 * (M2 + M2 / 8 + 1) * elem;
     if (tile > GEN_SMEM_MAX || rows > GEN_SMEM_MAX) return 0.0;
-    std::map<int, int> memo;
-    const int pc = gen_min_passes(M1, memo), pr = gen_min_passes((int)M2, memo);
-    if (pc > GEN_MAX_PASSES || pr > GEN_MAX_PASSES) return 0.0;
-    // column passes: forward on 1.5 signals + inverse on 1; row passes: forward on 2, inverse on 1
+    std::map<int, GenAxisCost> memo;
+    const GenAxisCost pc = gen_axis_cost(M1, memo), pr = gen_axis_cost((int)M2, memo);
+    if (pc.cost < 0.0 || pr.cost < 0.0 || pc.passes > GEN_MAX_PASSES || pr.passes > GEN_MAX_PASSES) return 0.0;
     // a pass keeps GEN_THREADS threads busy only if the CTA has that many butterflies (radix ~10)
     auto util = [](double butterflies) { const double u = butterflies / GEN_THREADS; return u > 1.0 ? 1.0 : (u < 0.25 ? 0.25 : u); };
-    double cost = 2.5 * pc / util((double)M1 * ct / 10.0) + 3.0 * pr / util(4.0 * (double)M2 / 10.0);
-    // fewer resident CTAs per SM when a CTA's buffer exceeds a third / half of the SM
-    auto occupancy_penalty = [](size_t bytes) { return bytes > 110 * 1024 ? 1.3 : (bytes > 74 * 1024 ? 1.12 : 1.0); };
-    cost *= occupancy_penalty(tile) * occupancy_penalty(rows);
-    if (M2 % ct != 0) cost *= 1.25;            // ragged last tile, rows not 128-byte aligned
-    return cost;
+    // resident CTAs per SM by shared memory (the kernels are compiled for three)
+    auto occupancy_penalty = [](size_t bytes) { return bytes > 112 * 1024 ? 1.8 : (bytes > 74 * 1024 ? 1.25 : 1.0); };
+    // column passes: forward on 1.5 signals + inverse on 1; row passes: forward on 2, inverse on 1
+    double col = 2.5 * pc.cost / util((double)M1 * ct / 10.0) * occupancy_penalty(tile);
+    if (ct * elem < 128) col *= 1.1;            // half cache lines per tile row
+    if (M2 % ct != 0) col *= 1.25;              // ragged last tile, rows not line-aligned
+    const double row = 3.0 * pr.cost / util(4.0 * (double)M2 / 10.0) * occupancy_penalty(rows);
+    return col + row;
 }
 
-inline bool gen_choose_split(long long M, int elem, int ct, int* M1_out, double* cost_out) {
+inline bool gen_choose_split(long long M, int elem, bool is_double, int* M1_out, int* ct_out, double* cost_out) {
     double best = 0.0;
-    int best_m1 = 0;
-    for (long long d = 2; d <= 2048 && d <= M; d++) {
+    int best_m1 = 0, best_ct = 0;
+    for (long long d = 2; d <= 4096 && d <= M; d++) {
         if (M % d != 0) continue;
-        const double c = gen_split_cost(M, (int)d, elem, ct);
-        if (c > 0.0 && (best == 0.0 || c < best)) { best = c; best_m1 = (int)d; }
+        for (int ct : {16, 8}) {
+            if (is_double && ct != 8) continue;
+            const double c = gen_split_cost(M, (int)d, elem, ct);
+            if (c > 0.0 && (best == 0.0 || c < best)) { best = c; best_m1 = (int)d; best_ct = ct; }
+        }
     }
     if (best == 0.0) return false;
     *M1_out = best_m1;
+    *ct_out = best_ct;
     if (cost_out) *cost_out = best;
     return true;
 }
@@ -122,13 +132,13 @@ inline bool gen_choose_split(long long M, int elem, int ct, int* M1_out, double*
 // cheapest embedding length M >= ceil(3L / 2) among the smooth numbers up to 15 % above the
 // smallest one.  is_double: fp64 arithmetic (16-byte points, 8-column tiles).
 inline bool gen_make_shape(long long L, bool is_double, GenShape* out) {
-    const int elem = is_double ? 16 : 8, ct = is_double ? 8 : 16;
+    const int elem = is_double ? 16 : 8;
     if (L < 1) return false;
     GenShape sh{};
     sh.L = L;
-    int m1 = 0;
+    int m1 = 0, ct = 0;
     double cost = 0.0;
-    if (is_235_smooth(L) && gen_choose_split(L, elem, ct, &m1, &cost)) {
+    if (is_235_smooth(L) && gen_choose_split(L, elem, is_double, &m1, &ct, &cost)) {
         sh.M = L;
         sh.src_ext = 2 * L;
     } else {
@@ -141,23 +151,25 @@ inline bool gen_make_shape(long long L, bool is_double, GenShape* out) {
         std::sort(cand.begin(), cand.end());
         double best = 0.0;
         long long best_m = 0;
-        int best_m1 = 0;
+        int best_m1 = 0, best_ct = 0;
         long long first_ok = 0;
         for (long long m : cand) {
             if (first_ok && (double)m > 1.15 * (double)first_ok) break;
-            int mm1;
+            int mm1, mct;
             double c;
-            if (!gen_choose_split(m, elem, ct, &mm1, &c)) continue;
+            if (!gen_choose_split(m, elem, is_double, &mm1, &mct, &c)) continue;
             if (!first_ok) first_ok = m;
             const double total = c * (double)m;
-            if (best == 0.0 || total < best) { best = total; best_m = m; best_m1 = mm1; }
+            if (best == 0.0 || total < best) { best = total; best_m = m; best_m1 = mm1; best_ct = mct; }
         }
         if (best_m == 0) return false;
         sh.M = best_m;
         sh.src_ext = 3 * L;
         m1 = best_m1;
+        ct = best_ct;
     }
     sh.M1 = m1;
+    sh.ct = ct;
     sh.M2 = (int)(sh.M / m1);
     if (!gen_make_axis(sh.M1, &sh.col) || !gen_make_axis(sh.M2, &sh.row)) return false;
     *out = sh;
@@ -170,7 +182,7 @@ inline double gen_peak_scale(const GenShape& sh) { return 0.5 * (double)sh.L / (
 
 template <class C>
 struct GenTables {
-    std::vector<C> wcol, wrow, m_lo, m_hi;
+    std::vector<C> wcol, wrow, wpos, m_lo, m_hi;
     std::vector<int> p2f_col, p2f_row, f2p_row;
 };
 
@@ -189,6 +201,8 @@ inline GenTables<C> gen_build_tables(const GenShape& sh) {
     t.p2f_col = gen_pos2freq(sh.col);
     t.p2f_row = gen_pos2freq(sh.row);
     t.f2p_row = gen_freq2pos(sh.row);
+    t.wpos.resize(sh.M2);
+    for (int e = 0; e < sh.M2; e++) t.wpos[e] = t.wrow[t.p2f_row[e]];
     return t;
 }
 
@@ -198,6 +212,7 @@ inline std::string gen_describe(const GenShape& sh, bool is_double) {
     for (int i = 0; i < sh.col.npass; i++) d += (i ? "x" : "") + std::to_string(sh.col.radix[i]);
     d += " row=";
     for (int i = 0; i < sh.row.npass; i++) d += (i ? "x" : "") + std::to_string(sh.row.radix[i]);
+    d += " tile=" + std::to_string(sh.ct);
     d += sh.M == sh.L ? " generic four-step" : " generic four-step, embedded (N'=2M>=3L)";
     d += is_double ? " fp64" : " fp32";
     return d;

@@ -41,7 +41,7 @@ synth_kernel(T* __restrict__ sources, T* __restrict__ samples, uint64_t seed,
 }
 
 // f64le frames -> fp32 slot of a session pool (the wire-format conversion, on arrival).
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 convert_f64_to_f32_kernel(const double* __restrict__ in, float* __restrict__ out, long long n)
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -113,7 +113,7 @@ __device__ __forceinline__ KeyF64 key_shfl_xor(KeyF64 k, int o) {
 }
 
 // `pitch`: doubles between consecutive pairs' arrays (N when packed).
-__global__ void __launch_bounds__(1024)
+static __global__ void __launch_bounds__(1024)
 argmax_f64_kernel(const double* __restrict__ r, long long N, long long pitch, PairPeak* __restrict__ peaks)
 {
     __shared__ KeyF64 s_k[32];

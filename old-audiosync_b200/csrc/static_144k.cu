@@ -1,0 +1,3 @@
+// Static four-step kernels of the L = 144k plan (see static_plan_impl.cuh).
+#include "static_plan_impl.cuh"
+template int asc::build_static_plan<asc::Plan144k>(asc::FftPlan*);

@@ -129,20 +129,21 @@ static int run_generic(const InT* source, const InT* sample, long long L, long l
     PairPeak pk;
     memset(&pk, 0, sizeof(pk));
     pk.key = 12345ull; pk.second_bits = 777u;   // garbage: G_A must clear both
-    {
-        using K = GenColFwdKernel<T, InT>;
+    auto col_fwd = [&](auto KK) {
+        using K = decltype(KK);
         typename K::Params p{source, sample, planes.data(), &pk, tb.wcol.data(), tb.m_lo.data(), tb.m_hi.data(),
-                             tb.p2f_col.data(), sh, 2 * L, L};
+                             tb.p2f_col.data(), sh, 2 * L, L, 1, 1};
         std::vector<C> smem(K::smem_bytes(sh) / sizeof(C) + 1);
         for (int sig = 0; sig < 2; sig++)
             for (int tile = 0; tile < (sh.M2 + K::CT - 1) / K::CT; tile++) {
                 HostExec ex{tile, sig, 0, K::THREADS};
                 K::run(ex, p, smem.data());
             }
-    }
+    };
+    if (sh.ct == 16) col_fwd(GenColFwdKernel<T, InT, 16>{}); else col_fwd(GenColFwdKernel<T, InT, 8>{});
     {
         using K = GenRowFusedKernel<T>;
-        typename K::Params p{planes.data(), tb.wrow.data(), tb.m_lo.data(), tb.m_hi.data(), tb.p2f_row.data(),
+        typename K::Params p{planes.data(), tb.wrow.data(), tb.wpos.data(), tb.m_lo.data(), tb.m_hi.data(),
                              tb.f2p_row.data(), sh};
         std::vector<C> smem(K::smem_bytes(sh) / sizeof(C) + 1);
         for (int r = 0; r <= sh.M1 / 2; r++) {
@@ -150,15 +151,16 @@ static int run_generic(const InT* source, const InT* sample, long long L, long l
             K::run(ex, p, smem.data());
         }
     }
-    {
-        using K = GenColInvKernel<T>;
+    auto col_inv = [&](auto KK) {
+        using K = decltype(KK);
         typename K::Params p{planes.data(), &pk, tb.wcol.data(), tb.p2f_col.data(), sh, reinterpret_cast<T*>(planes.data())};
         std::vector<C> smem(K::smem_bytes(sh) / sizeof(C) + 1);
         for (int tile = 0; tile < (sh.M2 + K::CT - 1) / K::CT; tile++) {
             HostExec ex{0, tile, 0, K::THREADS};
             K::run(ex, p, smem.data());
         }
-    }
+    };
+    if (sh.ct == 16) col_inv(GenColInvKernel<T, 16>{}); else col_inv(GenColInvKernel<T, 8>{});
     const double scale = gen_peak_scale(sh);
     if (sizeof(T) == 4) {
         *raw_index = (long long)argmax_key_index(pk.key);

@@ -251,13 +251,14 @@ def test_generic_plan_shapes():
                 assert L > 3 * 10 ** 6, (L, precise)       # only very long inputs may lack a plan
                 continue
             d = buf.value.decode()
-            m = re.search(r"M=(\d+) M1=(\d+) M2=(\d+) col=([0-9x]+) row=([0-9x]+)", d)
-            M, M1, M2 = int(m.group(1)), int(m.group(2)), int(m.group(3))
+            m = re.search(r"M=(\d+) M1=(\d+) M2=(\d+) col=([0-9x]+) row=([0-9x]+) tile=(\d+)", d)
+            M, M1, M2, ct = int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(6))
             col = [int(x) for x in m.group(4).split("x")]; row = [int(x) for x in m.group(5).split("x")]
             assert M1 * M2 == M and np.prod(col) == M1 and np.prod(row) == M2
             assert all(r in (2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16) for r in col + row)
             assert (M == L) or (2 * M >= 3 * L and M <= 1.2 * 1.5 * L + 64)
-            elem, ct = (16, 8) if precise else (8, 16)
+            elem = 16 if precise else 8
+            assert ct in ((8,) if precise else (8, 16))
             assert M1 * ct * elem <= 220 * 1024 and 4 * (M2 + M2 // 8 + 1) * elem <= 220 * 1024
             assert len(col) <= 6 and len(row) <= 6, d
 
