@@ -13,11 +13,24 @@ used for device buffers, the barrier and the max-over-ranks only.
 
 The printed JSON line carries, besides the base contract:
   roofline      -- dominant kernel: algorithmic bytes per launch / its average
-                   launch duration (CUDA events around every launch, on its own
-                   stream, inside the timed region) vs MEASURED_PEAKS.json;
-  path_roofline -- the whole path: SURVEY 8(d)'s 21*L*4 bytes/pair * pairs/s;
+                   launch duration vs MEASURED_PEAKS.json.  `value` is timed with
+                   no per-launch events (the shipped configuration: the stages
+                   are chained with programmatic dependent launch); the per-kernel
+                   durations come from a second, identical pass of K steps with
+                   CUDA events around every launch on its own stream;
+                   `kernels` lists all four with their own fractions;
+  path_roofline -- the whole path three ways: `frac` with SURVEY 8(d)'s 21*L*4
+                   bytes/pair (the survey's accounting), `frac_moved` with the
+                   17*L*4 this design moves, `frac_dram` with the DRAM bytes ncu
+                   measured (profiles/traffic.json);
   e2e           -- the same metric through the host-facing C-ABI batch call with
-                   pinned HOST buffers (uploads and result download timed);
+                   pinned HOST buffers of the reference ABI's dtype, double (uploads
+                   and result download timed); `e2e_variants` adds fp32-pinned and
+                   f64-pageable host buffers;
+  in_library    -- (N > 1, rank 0) ONE context / one process driving all N devices
+                   through audiosync_cuda_xcorr_batch(HOST) and through
+                   ..._batch_device per device: north_star's dispatcher, beside the
+                   process-per-GPU figure;
   cpu_baseline  -- the reference's CPU path (oracle/_ref, FFT shim) on this box.
 """
 from __future__ import annotations
@@ -67,7 +80,8 @@ UNIT = "pairs/s"
 #   col_inv   reads 2U                                                             = 2 U
 #   pearson   reads 2U (the two windows)                                           = 2 U
 KERNEL_U = {"col_fwd": 7, "row_fused": 6, "col_inv_argmax": 2, "pearson": 2}
-PATH_U = 21
+PATH_U = 21          # SURVEY 8(d)'s minimal-pass schedule
+MOVED_U = 17         # what this design moves (K_B fuses forward pass 2 with inverse pass 1)
 
 
 # stdout carries exactly ONE line, the JSON result: everything libraries print to fd 1 (NCCL's
@@ -105,6 +119,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-inlib", action="store_true", help="skip the in-library multi-GPU leg (N > 1)")
+    ap.add_argument("--inlib-pairs", type=int, default=1024, help="device-resident pairs per GPU in the in-library leg")
     return ap.parse_args()
 
 
@@ -332,8 +348,8 @@ def measure_latency(ctx, ac, torch, dev, local, stream, d_src, d_smp, d_res, n, 
                     prev = 0
                     for Li in ac.INTERV_SAMPLE:
                         for slot in range(ns):
-                            lib.audiosync_cuda_pool_append(pool._h, slot, ps + 16 * prev, 2 * (Li - prev),
-                                                           pm + 8 * prev, Li - prev)
+                            lib.audiosync_cuda_pool_append_async(pool._h, slot, ps + 16 * prev, 2 * (Li - prev),
+                                                                 pm + 8 * prev, Li - prev)
                         rec = pool.run(0, ns, Li)
                         prev = Li
                     for slot in range(ns):
@@ -351,6 +367,90 @@ def measure_latency(ctx, ac, torch, dev, local, stream, d_src, d_smp, d_res, n, 
         except Exception as e:          # never let the extra measurement take the bench line down
             out["session_pool_schedule"] = {"error": str(e)[:200]}
     lib.fftw_free(ps); lib.fftw_free(pm)
+    return out
+
+
+# ------------------------------------------------------------------ in-library multi-GPU dispatcher
+
+def measure_in_library(ac, torch, n_dev, L, args, per_gpu_process_value):
+    """north_star (3) / SURVEY 8(e): ONE process and ONE context drive all `n_dev` devices.
+
+    (a) device-resident: `inlib_pairs` fp32 pairs per device, generated on each device; every step
+        enqueues the whole path on every device through audiosync_cuda_xcorr_batch_device (one
+        stream per device, no host synchronisation between devices); time = max over devices of the
+        CUDA-event span on that device's stream.  (b) host-facing: one pinned fp32 batch through
+        audiosync_cuda_xcorr_batch(memspace=HOST), which shards contiguous pair blocks over the
+        devices (one host thread + stream per device) and gathers the records.
+    """
+    out = {"devices": n_dev}
+    npd = args.inlib_pairs
+    with ac.Context(list(range(n_dev))) as ctx:
+        bufs = []
+        for g in range(n_dev):
+            dev = torch.device("cuda", g)
+            with torch.cuda.device(dev):
+                st = torch.cuda.Stream(dev)
+                src = torch.empty(npd * 2 * L, dtype=torch.float32, device=dev)
+                smp = torch.empty(npd * L, dtype=torch.float32, device=dev)
+                res = torch.zeros(npd * ac.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+                ctx.synth_pairs(g, SEED, g * npd, npd, L, ac.F32, src.data_ptr(), smp.data_ptr(), st.cuda_stream)
+                bufs.append((dev, st, src, smp, res))
+
+        # one host thread + one stream per device, as north_star (3) describes (ctypes releases the GIL)
+        def drive(g, nsteps, timed):
+            dev, st, src, smp, res = bufs[g]
+            torch.cuda.set_device(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if timed:
+                gate.wait()
+            a.record(st)
+            for _ in range(nsteps):
+                ctx.xcorr_batch_device(g, src.data_ptr(), smp.data_ptr(), npd, L, ac.F32, res.data_ptr(), st.cuda_stream)
+            b.record(st)
+            torch.cuda.synchronize(dev)
+            return a.elapsed_time(b)
+
+        from concurrent.futures import ThreadPoolExecutor
+        gate = threading.Barrier(n_dev)
+        steps = max(args.steps, 8)
+        with ThreadPoolExecutor(n_dev) as pool:
+            list(pool.map(lambda g: drive(g, max(2, args.warmup), False), range(n_dev)))
+            t0 = time.perf_counter()
+            spans = list(pool.map(lambda g: drive(g, steps, True), range(n_dev)))
+            wall = time.perf_counter() - t0
+        ms = max(spans)
+        from oracle import capi
+        bad = 0
+        for g, (dev, st, src, smp, res) in enumerate(bufs):
+            r = res.cpu().numpy().view(ac.RESULT_DTYPE)
+            bad += sum(1 for i in range(0, npd, max(1, npd // 32))
+                       if int(r["lag"][i]) != capi.synth_true_lag(SEED, g * npd + i, L))
+        v = n_dev * npd * steps / (ms * 1e-3)
+        out["device_resident"] = {"value": v, "unit": UNIT, "pairs_per_gpu": npd, "steps": steps, "ms_max_over_devices": ms,
+                                  "wall_ms": wall * 1e3, "lag_mismatches": bad,
+                                  "vs_process_per_gpu": v / (n_dev * per_gpu_process_value),
+                                  "api": "audiosync_cuda_xcorr_batch_device on every device of one context"}
+        # (b) host-facing call, pinned fp32 batch sharded by the library
+        ne = min(args.e2e_pairs, npd) * n_dev
+        h_src = torch.empty(ne * 2 * L, dtype=torch.float32, pin_memory=True)
+        h_smp = torch.empty(ne * L, dtype=torch.float32, pin_memory=True)
+        per = ne // n_dev
+        for g, (dev, st, src, smp, res) in enumerate(bufs):
+            h_src[g * per * 2 * L:(g + 1) * per * 2 * L].copy_(src[: per * 2 * L])
+            h_smp[g * per * L:(g + 1) * per * L].copy_(smp[: per * L])
+        for dev, *_ in bufs:
+            torch.cuda.synchronize(dev)
+        o = ctx.xcorr_batch_ptr(h_src.data_ptr(), h_smp.data_ptr(), ne, L, ac.F32, ac.HOST)
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            o = ctx.xcorr_batch_ptr(h_src.data_ptr(), h_smp.data_ptr(), ne, L, ac.F32, ac.HOST)
+        dt = time.perf_counter() - t0
+        badh = sum(1 for g in range(n_dev) for i in range(0, per, max(1, per // 16))
+                   if int(o["lags"][g * per + i]) != capi.synth_true_lag(SEED, g * npd + i, L))
+        out["host_batch"] = {"value": ne * reps / dt, "unit": UNIT, "pairs_per_call": ne, "host_dtype": "f32",
+                             "host_memory": "pinned", "h2d_gbs_total": ne * 3 * L * 4 * reps / dt / 1e9,
+                             "lag_mismatches": badh, "api": "audiosync_cuda_xcorr_batch(memspace=HOST), devices = all"}
     return out
 
 
@@ -420,8 +520,6 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
-    ctx.profile_enable(True)
-    ctx.profile_reset()
     launches0 = ctx.launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -436,6 +534,18 @@ def main():
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count() - launches0
+    # per-kernel durations: the same K steps again, every launch bracketed by CUDA events on its
+    # own stream (kept out of the timed region above: the event records sit between the
+    # PDL-chained stage launches)
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for _ in range(args.steps):
+        step()
+    p1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms_profiled = p0.elapsed_time(p1)
     prof = ctx.profile_read()
     ctx.profile_enable(False)
 
@@ -453,39 +563,67 @@ def main():
         ms, launches, bad = float(tmax[0]), int(tsum[1]), int(tsum[2])
     value = world * n * args.steps / (ms * 1e-3)
 
-    # ---- end to end: host-facing C-ABI batch call, pinned host buffers -----------------------
+    # ---- end to end: host-facing C-ABI batch call on HOST buffers -----------------------------
+    # headline: pinned doubles, the dtype the reference ABI's callers hold (f64le from ffmpeg);
+    # variants: fp32 pinned (half the bytes) and pageable doubles (staged through the library's
+    # pinned ring).  Uploads and the result download are inside the timed region.
     e2e = None
+    e2e_variants = {}
     if not args.no_e2e:
+        def e2e_leg(tdt, acdt, pinned, ne, reps):
+            esz = 4 if acdt == ac.F32 else 8
+            h_src = torch.empty(ne * 2 * L, dtype=tdt, pin_memory=pinned)
+            h_smp = torch.empty(ne * L, dtype=tdt, pin_memory=pinned)
+            h_src.copy_(d_src[: ne * 2 * L]); h_smp.copy_(d_smp[: ne * L])     # exact in both dtypes
+            torch.cuda.synchronize(dev)
+            out = None
+            for _ in range(2):
+                out = ctx.xcorr_batch_ptr(h_src.data_ptr(), h_smp.data_ptr(), ne, L, acdt, ac.HOST)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                out = ctx.xcorr_batch_ptr(h_src.data_ptr(), h_smp.data_ptr(), ne, L, acdt, ac.HOST)
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            assert all(int(out["lags"][i]) == int(res["lag"][i]) for i in range(ne))
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            del h_src, h_smp
+            return {"value": world * ne * reps / float(tt[0]), "unit": UNIT,
+                    "h2d_bytes_per_step": ne * 3 * L * esz, "d2h_bytes_per_step": ne * ac.RESULT_DTYPE.itemsize,
+                    "pairs_per_step": ne, "host_dtype": "f32" if esz == 4 else "f64",
+                    "host_memory": "pinned" if pinned else "pageable", "host_binding": numa,
+                    "h2d_gbs_per_gpu": ne * 3 * L * esz * reps / float(tt[0]) / 1e9,
+                    "bound": "pcie (host->device copy of %.2f MB per pair)" % (3 * L * esz / 1e6),
+                    "api": "audiosync_cuda_xcorr_batch(memspace=HOST)"}
         ne = min(args.e2e_pairs, n)
-        h_src = torch.empty(ne * 2 * L, dtype=torch.float32, pin_memory=True)
-        h_smp = torch.empty(ne * L, dtype=torch.float32, pin_memory=True)
-        h_src.copy_(d_src[: ne * 2 * L]); h_smp.copy_(d_smp[: ne * L])
-        torch.cuda.synchronize(dev)
-        out = None
-        for _ in range(2):
-            out = ctx.xcorr_batch_ptr(h_src.data_ptr(), h_smp.data_ptr(), ne, L, ac.F32, ac.HOST)
-        barrier()
-        t0 = time.perf_counter()
         reps = max(2, args.steps)
-        for _ in range(reps):
-            out = ctx.xcorr_batch_ptr(h_src.data_ptr(), h_smp.data_ptr(), ne, L, ac.F32, ac.HOST)
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        assert all(int(out["lags"][i]) == int(res["lag"][i]) for i in range(ne))
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * ne * reps / float(tt[0]), "unit": UNIT,
-               "h2d_bytes_per_step": ne * 3 * L * 4, "d2h_bytes_per_step": ne * ac.RESULT_DTYPE.itemsize,
-               "pairs_per_step": ne, "host_dtype": "f32", "host_memory": "pinned", "host_binding": numa,
-               "h2d_gbs_per_gpu": ne * 3 * L * 4 * reps / float(tt[0]) / 1e9, "bound": "pcie (host->device copy of 17.28 MB per pair)",
-               "api": "audiosync_cuda_xcorr_batch(memspace=HOST)"}
-        del h_src, h_smp
+        e2e = e2e_leg(torch.float64, ac.F64, True, max(1, ne // 2), reps)
+        e2e_variants["f32_pinned"] = e2e_leg(torch.float32, ac.F32, True, ne, reps)
+        e2e_variants["f64_pageable"] = e2e_leg(torch.float64, ac.F64, False, max(1, ne // 4), 2)
 
     # ---- config 3: single-pair latency at this length (rank 0 only) --------------------------
     latency = None
     if rank == 0 and not args.no_latency:
         latency = measure_latency(ctx, ac, torch, dev, local, stream, d_src, d_smp, d_res, n, L)
+
+    # ---- north_star (3): the in-library dispatcher -- one process, one context, all N devices --
+    in_library = None
+    if world > 1 and not args.no_inlib:
+        # the other ranks must wait on the HOST: an NCCL barrier is a kernel spinning on their GPUs,
+        # which rank 0 is about to drive -- a gloo group keeps the devices free
+        host_group = dist.new_group(backend="gloo")
+        barrier()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=host_group)
+        if rank == 0:
+            try:
+                in_library = measure_in_library(ac, torch, world, L, args, value / world)
+            except Exception as e:                  # never let the extra leg take the bench line down
+                in_library = {"error": str(e)[:300]}
+        dist.barrier(group=host_group)
+        barrier()
 
     if rank == 0:
         peak, peak_kind = measured_peaks()
@@ -507,7 +645,25 @@ def main():
                 traffic = None
         total_kernel_ms = sum(v[1] for v in prof.values())
         shares = {k: round(v[1] / total_kernel_ms, 4) for k, v in prof.items() if v[1] > 0}
-        path_achieved = PATH_U * U * value / world / 1e9
+        tj = {}
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+            except Exception:
+                tj = {}
+        kernels = {}
+        for k, u in KERNEL_U.items():
+            nl, tm = prof.get(k, (0, 0.0))
+            if nl == 0 or tm <= 0:
+                continue
+            us_pair = 1e3 * tm / (n * args.steps)
+            ach = u * U / (us_pair * 1e-6) / 1e9
+            kernels[k] = {"us_per_pair": round(us_pair, 3), "alg_bytes_per_pair": u * U, "achieved_gbs": round(ach, 1),
+                          "frac": round(ach / peak, 4),
+                          "dram_bytes_per_pair_ncu": tj.get(k, {}).get("bytes_per_pair")}
+        dram_pair = sum(v.get("bytes_per_pair", 0) for k, v in tj.items() if k in KERNEL_U) or None
+        pairs_s_gpu = value / world
+        path_achieved = PATH_U * U * pairs_s_gpu / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -522,14 +678,26 @@ def main():
                          "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                          "alg_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
                          "launches": n_launch, "bytes_per_pair": KERNEL_U[dom] * U,
-                         "kernel_time_shares": shares},
+                         "kernel_time_shares": shares,
+                         "traffic_source": "constant from profiles/traffic.json (one ncu --set full capture), not measured in this run",
+                         "measured_in": "second pass of the same %d steps with CUDA events around every launch "
+                                        "(%.1f ms vs %.1f ms for the timed, event-free pass)" % (args.steps, ms_profiled, ms),
+                         "kernels": kernels},
             "path_roofline": {"bytes_per_pair": PATH_U * U, "achieved": path_achieved, "peak": peak,
-                              "unit": "GB/s", "frac": path_achieved / peak, "per_gpu": True},
-            "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                              "unit": "GB/s", "frac": path_achieved / peak, "per_gpu": True,
+                              "accounting": "frac: SURVEY 8(d)'s 21*U schedule (the survey's accounting); frac_moved: the "
+                                            "17*U this design moves; frac_dram: DRAM bytes per pair measured by ncu",
+                              "bytes_moved_per_pair": MOVED_U * U,
+                              "frac_moved": MOVED_U * U * pairs_s_gpu / 1e9 / peak,
+                              "dram_bytes_per_pair_ncu": dram_pair,
+                              "frac_dram": (dram_pair * pairs_s_gpu / 1e9 / peak) if dram_pair else None},
+            "e2e": e2e, "e2e_variants": e2e_variants, "gpu_launches": launches, "clocks": clocks,
             "check": {"lag_mismatches": bad, "success_flags": ok_flags, "pairs_checked_per_rank": min(n, 256)},
         }
         if latency is not None:
             line["latency"] = latency
+        if in_library is not None:
+            line["in_library"] = in_library
         if world == 1 and not args.no_cpu_baseline:
             os.sched_setaffinity(0, all_cpus)      # the CPU leg gets every host core back
             line["cpu_baseline"] = cpu_baseline_sample(L, SEED)

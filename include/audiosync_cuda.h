@@ -203,6 +203,16 @@ int  audiosync_cuda_pool_reset(audiosync_cuda_pool *pool, size_t slot);
 int  audiosync_cuda_pool_append(audiosync_cuda_pool *pool, size_t slot,
                                 const double *source_frames, size_t n_source,
                                 const double *sample_frames, size_t n_sample);
+/* The same, stream-ordered: returns as soon as the copies are enqueued (arriving doubles cross
+ * PCIe in 8 MB pieces; for F32 slots the conversion of one piece overlaps the copy of the next).
+ * Page-locked host buffers must stay unchanged until audiosync_cuda_pool_flush() or the next
+ * audiosync_cuda_pool_run() returns (pageable ones are copied out before the call returns).
+ * pool_run orders itself behind every earlier append. */
+int  audiosync_cuda_pool_append_async(audiosync_cuda_pool *pool, size_t slot,
+                                      const double *source_frames, size_t n_source,
+                                      const double *sample_frames, size_t n_sample);
+/* Blocks until every appended frame is in its slot. */
+int  audiosync_cuda_pool_flush(audiosync_cuda_pool *pool);
 /* Frames a slot holds so far. */
 int  audiosync_cuda_pool_fill(const audiosync_cuda_pool *pool, size_t slot,
                               size_t *source_frames, size_t *sample_frames);

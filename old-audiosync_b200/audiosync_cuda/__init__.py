@@ -51,7 +51,8 @@ EXPORTED_SYMBOLS = [
     "audiosync_cuda_set_path", "audiosync_cuda_set_wave_pairs", "audiosync_cuda_set_debug", "audiosync_cuda_set_precise",
     "audiosync_cuda_set_residency", "audiosync_cuda_dropin_stats",
     "audiosync_cuda_pool_create", "audiosync_cuda_pool_destroy", "audiosync_cuda_pool_reset",
-    "audiosync_cuda_pool_append", "audiosync_cuda_pool_fill", "audiosync_cuda_pool_run",
+    "audiosync_cuda_pool_append", "audiosync_cuda_pool_append_async", "audiosync_cuda_pool_flush",
+    "audiosync_cuda_pool_fill", "audiosync_cuda_pool_run",
     "audiosync_cuda_describe_plan", "audiosync_cuda_launch_count",
     "audiosync_cuda_profile_enable", "audiosync_cuda_profile_reset",
     "audiosync_cuda_profile_read", "audiosync_cuda_last_error", "audiosync_cuda_version",
@@ -128,6 +129,10 @@ def lib() -> C.CDLL:
     L.audiosync_cuda_pool_reset.argtypes = [vp, sz]
     L.audiosync_cuda_pool_append.restype = i32
     L.audiosync_cuda_pool_append.argtypes = [vp, sz, vp, sz, vp, sz]
+    L.audiosync_cuda_pool_append_async.restype = i32
+    L.audiosync_cuda_pool_append_async.argtypes = [vp, sz, vp, sz, vp, sz]
+    L.audiosync_cuda_pool_flush.restype = i32
+    L.audiosync_cuda_pool_flush.argtypes = [vp]
     L.audiosync_cuda_pool_fill.restype = i32
     L.audiosync_cuda_pool_fill.argtypes = [vp, sz, C.POINTER(sz), C.POINTER(sz)]
     L.audiosync_cuda_pool_run.restype = i32
@@ -566,6 +571,17 @@ class SessionPool:
                                               m.ctypes.data if m.size else None, m.size)
         if rc != 0:
             raise AudiosyncCudaError("pool_append failed: " + last_error())
+
+    def append_ptr(self, slot: int, source_ptr: int, n_source: int, sample_ptr: int, n_sample: int, sync: bool = False):
+        """Stream-ordered append from raw host addresses (e.g. ``RealBuffer``): returns once the copies
+        are enqueued unless ``sync``; ``run`` / ``flush`` order themselves behind it."""
+        fn = lib().audiosync_cuda_pool_append if sync else lib().audiosync_cuda_pool_append_async
+        if fn(self._h, slot, source_ptr or None, n_source, sample_ptr or None, n_sample) != 0:
+            raise AudiosyncCudaError("pool_append failed: " + last_error())
+
+    def flush(self):
+        if lib().audiosync_cuda_pool_flush(self._h) != 0:
+            raise AudiosyncCudaError("pool_flush failed: " + last_error())
 
     def fill(self, slot: int):
         a, b = C.c_size_t(), C.c_size_t()

@@ -324,6 +324,62 @@ static void destroy_device_state(DeviceState& d) {
     d.device = -1;
 }
 
+// A few persistent helper threads that split one large host memcpy (pageable input -> pinned
+// bounce buffer) into slices: a single core copies ~10 GB/s, PCIe takes 55.  One copy at a time
+// (callers would only fight over the same memory bandwidth); never torn down.
+class CopyPool {
+    struct Slice { char* dst; const char* src; size_t n; };
+    std::vector<std::thread> workers_;
+    std::mutex m_, run_mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<Slice> slices_;
+    size_t next_ = 0, pending_ = 0;
+    void loop() {
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            cv_.wait(lk, [&] { return next_ < slices_.size(); });
+            const Slice s = slices_[next_++];
+            lk.unlock();
+            memcpy(s.dst, s.src, s.n);
+            lk.lock();
+            if (--pending_ == 0) done_cv_.notify_all();
+        }
+    }
+public:
+    explicit CopyPool(unsigned n) {
+        for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { loop(); });
+        for (auto& t : workers_) t.detach();
+    }
+    size_t threads() const { return workers_.size() + 1; }
+    void copy(void* dst, const void* src, size_t bytes) {
+        const size_t parts = threads();
+        if (bytes < ((size_t)1 << 20) || parts == 1) { memcpy(dst, src, bytes); return; }
+        std::lock_guard<std::mutex> run(run_mu_);
+        const size_t per = ((bytes + parts - 1) / parts + 63) & ~(size_t)63;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            slices_.clear(); next_ = 0; pending_ = 0;
+            for (size_t o = per; o < bytes; o += per) {       // slice 0 is the caller's own
+                slices_.push_back(Slice{static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, std::min(per, bytes - o)});
+                pending_++;
+            }
+        }
+        cv_.notify_all();
+        memcpy(dst, src, std::min(per, bytes));
+        std::unique_lock<std::mutex> lk(m_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+    }
+};
+static CopyPool& copy_pool() {
+    static CopyPool* pool = [] {
+        unsigned hw = std::thread::hardware_concurrency();
+        const char* e = getenv("AUDIOSYNC_CUDA_COPY_THREADS");
+        unsigned n = e ? (unsigned)std::max(1, atoi(e)) : std::min(4u, std::max(1u, hw / 2));
+        return new CopyPool(n - 1);
+    }();
+    return *pool;
+}
+
 // Host -> device copy of `bytes` on `st` from ANY host memory.  Page-locked (cudaMallocHost /
 // cudaHostRegister'ed, e.g. this library's fftw_alloc_real) and managed sources go straight to
 // the copy engine; pageable ones are staged through the pinned ring.
@@ -346,7 +402,7 @@ static int upload_from_host(void* dst, const void* src, size_t bytes, cudaStream
         if (ring.buf[i].ensure(StageRing::PIECE) != 0) return -1;
         if (!ring.ev[i]) ASC_CUDA_OK(cudaEventCreateWithFlags(&ring.ev[i], cudaEventDisableTiming));
         if (ring.pending[i]) ASC_CUDA_OK(cudaEventSynchronize(ring.ev[i]));   // its last DMA has drained
-        memcpy(ring.buf[i].p, static_cast<const char*>(src) + o, m);
+        copy_pool().copy(ring.buf[i].p, static_cast<const char*>(src) + o, m);
         ASC_CUDA_OK(cudaMemcpyAsync(static_cast<char*>(dst) + o, ring.buf[i].p, m, cudaMemcpyHostToDevice, st));
         ASC_CUDA_OK(cudaEventRecord(ring.ev[i], st));
         ring.pending[i] = true;
@@ -359,6 +415,7 @@ static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* s
                           const char* samples, size_t p0, size_t p1, long long L, int dtype,
                           audiosync_cuda_result* out) {
     if (p1 <= p0) return 0;
+    std::lock_guard<std::mutex> dlk(d.mu);
     ASC_CUDA_OK(cudaSetDevice(d.device));
     const size_t esz = dtype == AUDIOSYNC_CUDA_F32 ? 4 : 8;
     const size_t src_bytes = (size_t)(2 * L) * esz, smp_bytes = (size_t)L * esz;
@@ -614,7 +671,7 @@ int audiosync_cuda_synth_pairs(audiosync_cuda_ctx* ctx, int device, uint64_t see
     DeviceState* d = ctx->find(device);
     if (!d) { set_last_error("device %d is not part of this context", device); return -1; }
     if (n_pairs == 0) return 0;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::mutex> lk(d->mu);
     ASC_CUDA_OK(cudaSetDevice(d->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
     const long long L = (long long)sample_len;
@@ -648,7 +705,7 @@ int audiosync_cuda_xcorr_batch_device(audiosync_cuda_ctx* ctx, int device, const
     if (dtype != AUDIOSYNC_CUDA_F32 && dtype != AUDIOSYNC_CUDA_F64) { set_last_error("bad dtype"); return -1; }
     DeviceState* d = ctx->find(device);
     if (!d) { set_last_error("device %d is not part of this context", device); return -1; }
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    std::lock_guard<std::mutex> lk(d->mu);      // per device: threads driving different devices do not serialise
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : d->stream;
     return enqueue_batch(ctx, *d, d->work, d_sources, d_samples, n_pairs, (long long)sample_len, dtype, d_results, st);
 }
@@ -671,6 +728,7 @@ int audiosync_cuda_xcorr_batch_results(audiosync_cuda_ctx* ctx, const void* sour
             set_last_error("device-memspace pointers must live on a device of the context");
             return -1;
         }
+        std::lock_guard<std::mutex> dlk(d->mu);
         ASC_CUDA_OK(cudaSetDevice(d->device));
         if (d->results.ensure(sizeof(audiosync_cuda_result) * n_pairs) != 0) return -1;
         auto* d_res = static_cast<audiosync_cuda_result*>(d->results.p);
@@ -736,7 +794,17 @@ struct audiosync_cuda_pool {
     size_t n_slots = 0, max_len = 0;
     long long src_pitch = 0, smp_pitch = 0;      // elements; multiples of 4 (16-byte rows for cp.async)
     int dtype = AUDIOSYNC_CUDA_F64;
-    asc::DevBuf src, smp, stage;
+    asc::DevBuf src, smp;
+    // fp32 slots: arriving doubles land in one of two staging buffers (copy stream) and are
+    // converted into the slot by a kernel on the pool's own stream, so the H2D copy of piece k + 1
+    // overlaps the conversion of piece k
+    asc::DevBuf stage[2];
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_converted[2] = {nullptr, nullptr};
+    bool conv_pending[2] = {false, false};
+    int next_stage = 0;
+    cudaStream_t conv_stream = nullptr;
+    cudaEvent_t ev_arrived = nullptr;            // everything appended so far is in the slots
+    bool dirty = false;                          // appends enqueued since the last flush / run
     std::vector<size_t> have_src, have_smp;
 };
 
@@ -744,22 +812,39 @@ namespace asc {
 static int pool_upload(audiosync_cuda_pool* pool, DevBuf& slab, size_t elem_off, const double* host, size_t n) {
     DeviceState& d = *pool->dev;
     if (n == 0) return 0;
-    if (pool->dtype == AUDIOSYNC_CUDA_F64) {
-        ASC_CUDA_OK(cudaMemcpyAsync(static_cast<double*>(slab.p) + elem_off, host, sizeof(double) * n,
-                                    cudaMemcpyHostToDevice, d.copy_stream));
-        return 0;
-    }
-    // fp32 slots: stage the doubles, convert on the device, in pieces
-    const size_t piece = 1u << 20;
-    if (pool->stage.ensure(sizeof(double) * std::min(piece, n)) != 0) return -1;
+    const bool pageable = host_pointer_is_pageable(host);
+    pool->dirty = true;
+    if (pool->dtype == AUDIOSYNC_CUDA_F64)
+        return upload_from_host(static_cast<double*>(slab.p) + elem_off, host, sizeof(double) * n, d.copy_stream, d.stage, pageable);
+    const size_t piece = 1u << 20;               // doubles per piece: 8 MB
     for (size_t o = 0; o < n; o += piece) {
         const size_t m = std::min(piece, n - o);
-        ASC_CUDA_OK(cudaMemcpyAsync(pool->stage.p, host + o, sizeof(double) * m, cudaMemcpyHostToDevice, d.copy_stream));
+        const int k = pool->next_stage;
+        pool->next_stage ^= 1;
+        if (pool->stage[k].ensure(sizeof(double) * piece) != 0) return -1;
+        if (pool->conv_pending[k]) ASC_CUDA_OK(cudaStreamWaitEvent(d.copy_stream, pool->ev_converted[k], 0));
+        if (upload_from_host(pool->stage[k].p, host + o, sizeof(double) * m, d.copy_stream, d.stage, pageable) != 0) return -1;
+        ASC_CUDA_OK(cudaEventRecord(pool->ev_copied[k], d.copy_stream));
+        ASC_CUDA_OK(cudaStreamWaitEvent(pool->conv_stream, pool->ev_copied[k], 0));
         const unsigned blocks = (unsigned)std::min<size_t>((m + 255) / 256, 2048);
-        if (launch(pool->ctx, d, KC_SYNTH, d.copy_stream, [&] {
-                convert_f64_to_f32_kernel<<<blocks, 256, 0, d.copy_stream>>>(
-                    static_cast<const double*>(pool->stage.p), static_cast<float*>(slab.p) + elem_off + o, (long long)m);
+        if (launch(pool->ctx, d, KC_SYNTH, pool->conv_stream, [&] {
+                convert_f64_to_f32_kernel<<<blocks, 256, 0, pool->conv_stream>>>(
+                    static_cast<const double*>(pool->stage[k].p), static_cast<float*>(slab.p) + elem_off + o, (long long)m);
             }) != 0) return -1;
+        ASC_CUDA_OK(cudaEventRecord(pool->ev_converted[k], pool->conv_stream));
+        pool->conv_pending[k] = true;
+    }
+    return 0;
+}
+// `st` waits until every frame appended so far is in its slot
+static int pool_order_after_appends(audiosync_cuda_pool* pool, cudaStream_t st) {
+    DeviceState& d = *pool->dev;
+    if (!pool->dirty) return 0;
+    ASC_CUDA_OK(cudaEventRecord(pool->ev_arrived, d.copy_stream));
+    ASC_CUDA_OK(cudaStreamWaitEvent(st, pool->ev_arrived, 0));
+    if (pool->dtype == AUDIOSYNC_CUDA_F32) {
+        ASC_CUDA_OK(cudaEventRecord(pool->ev_arrived, pool->conv_stream));
+        ASC_CUDA_OK(cudaStreamWaitEvent(st, pool->ev_arrived, 0));
     }
     return 0;
 }
@@ -788,6 +873,16 @@ int audiosync_cuda_pool_create(audiosync_cuda_ctx* ctx, int device, size_t n_slo
     }
     pool->have_src.assign(n_slots, 0);
     pool->have_smp.assign(n_slots, 0);
+    bool ok = cudaStreamCreateWithFlags(&pool->conv_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&pool->ev_arrived, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; k++)
+        ok = cudaEventCreateWithFlags(&pool->ev_copied[k], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&pool->ev_converted[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        set_last_error("pool_create: cannot create streams / events");
+        audiosync_cuda_pool_destroy(pool);
+        return -1;
+    }
     *out = pool;
     return 0;
 }
@@ -795,7 +890,13 @@ int audiosync_cuda_pool_create(audiosync_cuda_ctx* ctx, int device, size_t n_slo
 void audiosync_cuda_pool_destroy(audiosync_cuda_pool* pool) {
     if (!pool) return;
     if (pool->dev && pool->dev->device >= 0) { cudaSetDevice(pool->dev->device); cudaDeviceSynchronize(); }
-    pool->src.release(); pool->smp.release(); pool->stage.release();
+    pool->src.release(); pool->smp.release(); pool->stage[0].release(); pool->stage[1].release();
+    for (int k = 0; k < 2; k++) {
+        if (pool->ev_copied[k]) cudaEventDestroy(pool->ev_copied[k]);
+        if (pool->ev_converted[k]) cudaEventDestroy(pool->ev_converted[k]);
+    }
+    if (pool->ev_arrived) cudaEventDestroy(pool->ev_arrived);
+    if (pool->conv_stream) cudaStreamDestroy(pool->conv_stream);
     delete pool;
 }
 
@@ -814,8 +915,8 @@ int audiosync_cuda_pool_fill(const audiosync_cuda_pool* pool, size_t slot, size_
     return 0;
 }
 
-int audiosync_cuda_pool_append(audiosync_cuda_pool* pool, size_t slot, const double* source_frames, size_t n_source,
-                               const double* sample_frames, size_t n_sample) {
+int audiosync_cuda_pool_append_async(audiosync_cuda_pool* pool, size_t slot, const double* source_frames, size_t n_source,
+                                     const double* sample_frames, size_t n_sample) {
     if (!pool || slot >= pool->n_slots || (n_source && !source_frames) || (n_sample && !sample_frames)) {
         set_last_error("pool_append: invalid argument");
         return -1;
@@ -827,14 +928,32 @@ int audiosync_cuda_pool_append(audiosync_cuda_pool* pool, size_t slot, const dou
         return -1;
     }
     DeviceState& d = *pool->dev;
+    std::lock_guard<std::mutex> dlk(d.mu);
     ASC_CUDA_OK(cudaSetDevice(d.device));
     if (pool_upload(pool, pool->src, slot * (size_t)pool->src_pitch + pool->have_src[slot], source_frames, n_source) != 0 ||
         pool_upload(pool, pool->smp, slot * (size_t)pool->smp_pitch + pool->have_smp[slot], sample_frames, n_sample) != 0)
         return -1;
-    ASC_CUDA_OK(cudaStreamSynchronize(d.copy_stream));      // the frames are resident when this returns
     pool->have_src[slot] += n_source;
     pool->have_smp[slot] += n_sample;
     return 0;
+}
+
+int audiosync_cuda_pool_flush(audiosync_cuda_pool* pool) {
+    if (!pool) return -1;
+    std::lock_guard<std::mutex> lk(pool->ctx->mu);
+    DeviceState& d = *pool->dev;
+    std::lock_guard<std::mutex> dlk(d.mu);
+    ASC_CUDA_OK(cudaSetDevice(d.device));
+    ASC_CUDA_OK(cudaStreamSynchronize(d.copy_stream));
+    ASC_CUDA_OK(cudaStreamSynchronize(pool->conv_stream));
+    pool->dirty = false;
+    return 0;
+}
+
+int audiosync_cuda_pool_append(audiosync_cuda_pool* pool, size_t slot, const double* source_frames, size_t n_source,
+                               const double* sample_frames, size_t n_sample) {
+    if (audiosync_cuda_pool_append_async(pool, slot, source_frames, n_source, sample_frames, n_sample) != 0) return -1;
+    return audiosync_cuda_pool_flush(pool);       // the frames are resident when this returns
 }
 
 int audiosync_cuda_pool_run(audiosync_cuda_pool* pool, size_t first_slot, size_t n_slots, size_t sample_len,
@@ -853,6 +972,7 @@ int audiosync_cuda_pool_run(audiosync_cuda_pool* pool, size_t first_slot, size_t
         }
     }
     DeviceState& d = *pool->dev;
+    std::lock_guard<std::mutex> dlk(d.mu);
     ASC_CUDA_OK(cudaSetDevice(d.device));
     if (d.results.ensure(sizeof(audiosync_cuda_result) * n_slots) != 0 ||
         d.h_results.ensure(sizeof(audiosync_cuda_result) * n_slots) != 0)
@@ -861,12 +981,14 @@ int audiosync_cuda_pool_run(audiosync_cuda_pool* pool, size_t first_slot, size_t
     const char* s0 = static_cast<const char*>(pool->src.p) + first_slot * (size_t)pool->src_pitch * esz;
     const char* m0 = static_cast<const char*>(pool->smp.p) + first_slot * (size_t)pool->smp_pitch * esz;
     auto* d_res = static_cast<audiosync_cuda_result*>(d.results.p);
+    if (pool_order_after_appends(pool, d.stream) != 0) return -1;
     if (enqueue_batch(pool->ctx, d, d.work, s0, m0, n_slots, (long long)sample_len, pool->dtype, d_res, d.stream,
                       pool->src_pitch, pool->smp_pitch) != 0)
         return -1;
     ASC_CUDA_OK(cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result) * n_slots,
                                 cudaMemcpyDeviceToHost, d.stream));
     ASC_CUDA_OK(cudaStreamSynchronize(d.stream));
+    pool->dirty = false;                          // d.stream waited for every append
     memcpy(results, d.h_results.p, sizeof(audiosync_cuda_result) * n_slots);
     return 0;
 }
@@ -954,6 +1076,7 @@ static int cross_correlation_resident(audiosync_cuda_ctx* ctx, size_t block, dou
                                       long long L, audiosync_cuda_result* out) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceState& d = ctx->devs[0];
+    std::lock_guard<std::mutex> dlk(d.mu);
     ASC_CUDA_OK(cudaSetDevice(d.device));
     if (d.results.ensure(sizeof(audiosync_cuda_result)) != 0 ||
         d.h_results.ensure(sizeof(audiosync_cuda_result)) != 0)
@@ -1063,6 +1186,7 @@ double pearson_coefficient(double* source_start, const double* source_end, doubl
     if (!ctx) return nan;
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceState& d = ctx->devs[0];
+    std::lock_guard<std::mutex> dlk(d.mu);
     auto fail = [&]() { return nan; };
     if (cudaSetDevice(d.device) != cudaSuccess) return fail();
     const int n_chunks = (int)((n + PEARSON_CHUNK - 1) / PEARSON_CHUNK);

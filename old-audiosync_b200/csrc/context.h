@@ -65,7 +65,7 @@ struct PinnedBuf {
 // memory is staged by the driver and blocks the calling thread for the whole transfer).
 struct StageRing {
     static constexpr int N = 4;
-    static constexpr size_t PIECE = (size_t)4 << 20;
+    static constexpr size_t PIECE = (size_t)8 << 20;
     PinnedBuf buf[N];
     cudaEvent_t ev[N] = {nullptr, nullptr, nullptr, nullptr};
     bool pending[N] = {false, false, false, false};
@@ -116,6 +116,7 @@ struct DeviceState {
     cudaEvent_t ev_up[2] = {nullptr, nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr};
     std::map<size_t, std::shared_ptr<FftPlan>> plans;   // by sample_len
+    std::mutex mu;        // serialises users of `work`, `results`, the input mirrors and the staging ring
     std::mutex plan_mu;   // plans are built once and shared by concurrent callers
     // profiling (prof_mu: launches may come from concurrent drop-in callers)
     std::mutex prof_mu;

@@ -629,6 +629,31 @@ def test_session_pool_matches_dropin_over_the_schedule(ac, capi):
         assert pool.fill(1) == (0, 0)
 
 
+def test_session_pool_async_append_is_ordered(ac, capi):
+    """Stream-ordered appends (pinned source buffers, no host synchronisation between them) followed
+    directly by run(): the batch call orders itself behind every pending copy / conversion, for F64
+    and F32 slots, and returns what the synchronous path returns."""
+    L, n = 288000, 4
+    data = [capi.synth_pair(SEED + 33, pid, L) for pid in range(n)]
+    for dt in (ac.F64, ac.F32):
+        with ac.Context([0]) as c, ac.SessionPool(c, 0, n, L, dt) as pa, ac.SessionPool(c, 0, n, L, dt) as ps, \
+                ac.RealBuffer(2 * L) as sb, ac.RealBuffer(L) as mb:
+            for slot, (src, smp) in enumerate(data):
+                ps.append(slot, src, smp)                                   # synchronous reference
+            ref = ps.run(0, n, L)
+            for slot, (src, smp) in enumerate(data):
+                pa.flush()                                                  # the pinned buffers are about to be rewritten
+                sb.array[:] = src; mb.array[:] = smp
+                half = L // 2
+                pa.append_ptr(slot, sb.ptr, 2 * half, mb.ptr, half)         # two pieces, ragged, back to back
+                pa.append_ptr(slot, sb.ptr + 16 * half, 2 * (L - half), mb.ptr + 8 * half, L - half)
+            rec = pa.run(0, n, L)                                           # no flush: run orders itself
+            for name in ("lag", "ret", "raw_index", "coef", "peak"):
+                assert np.array_equal(rec[name], ref[name], equal_nan=True), name
+            for slot in range(n):
+                assert int(rec["lag"][slot]) == capi.synth_true_lag(SEED + 33, slot, L)
+
+
 def test_session_pool_fp32_slots(ac, capi):
     """F32 slots convert the f64le frames on arrival: same lag, coefficient within tolerance."""
     L, n = 144000, 3
