@@ -2,12 +2,14 @@
 """Builds the committed profile summary of one GPU visit from gpurun_out/:
    profiles/<tag>_ncu.md   -- launch list (gpu__time_duration), per-kernel ncu metrics, instruction mix / phases
    profiles/traffic.json   -- ncu DRAM bytes per pair for each kernel class (bench.py reads it for roofline.traffic)
-usage: make_profile_summary.py TAG PAIRS_PER_LAUNCH_IN_FULL_CAPTURE   (e.g. v6 64)"""
+usage: make_profile_summary.py TAG PAIRS_PER_LAUNCH_IN_FULL_CAPTURE [PAIRS_IN_LAUNCH_LIST] [ROUND]   (e.g. v6 64 128 r02)"""
 import collections, csv, io, json, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, ppl = sys.argv[1], int(sys.argv[2])
+ppl_list = int(sys.argv[3]) if len(sys.argv) > 3 else 128
+rnd = sys.argv[4] if len(sys.argv) > 4 else "r02"
 G = os.path.join(ROOT, "gpurun_out")
-out = ["# Round 1, %s kernels: ncu evidence" % tag, ""]
+out = ["# Round %d, %s kernels: ncu evidence" % (int(rnd[1:]), tag), ""]
 
 def cls(name):
     for k, c in (("ColFwd", "col_fwd"), ("RowFused", "row_fused"), ("ColInv", "col_inv_argmax"), ("pearson", "pearson"),
@@ -25,8 +27,8 @@ if os.path.exists(lp):
         k = (cls(r[ki]), r[gi], r[bi]); agg.setdefault(k, []).append(float(r[vi].replace(",", "")))
     ours = ("col_fwd", "row_fused", "col_inv_argmax", "pearson")
     tot = sum(sum(v) for k, v in agg.items() if k[0] in ours)
-    out += ["## Launch list", "", "`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --pairs 64 --steps 1 --warmup 1` "
-            "(cold-cache, serialised: compare SHARES).", "", "| kernel | grid | block | launches | avg us | share of path |", "|---|---|---|---|---|---|"]
+    out += ["## Launch list", "", ("`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --pairs %d --steps 1 --warmup 1` "
+             "(cold-cache, serialised: compare SHARES).") % ppl_list, "", "| kernel | grid | block | launches | avg us | share of path |", "|---|---|---|---|---|---|"]
     for (k, g, b), v in agg.items():
         out.append("| %s | %s | %s | %d | %.1f | %s |" % (k, g, b, len(v), sum(v) / len(v) / 1e3,
                                                        "%.3f" % (sum(v) / tot) if k in ours else "- (setup)"))
@@ -65,12 +67,12 @@ if os.path.exists(rep):
     algU = {"col_fwd": 7, "row_fused": 6, "col_inv_argmax": 2, "pearson": 2}
     for n, d in zip(names, data):
         b = (tobytes(d[ir], units[ir]) + tobytes(d[iw], units[iw])) / ppl
-        traffic[n] = {"bytes_per_pair": b, "source": "profiles/r01_%s_ncu.md" % tag}
+        traffic[n] = {"bytes_per_pair": b, "source": "profiles/%s_%s_ncu.md" % (rnd, tag)}
         out.append("- %s: %.2f MB / pair measured, %.2f MB algorithmic (%d U)" % (n, b / 1e6, algU.get(n, 0) * 5.76, algU.get(n, 0)))
     tot = sum(v["bytes_per_pair"] for v in traffic.values())
     out += ["- whole path: %.2f MB / pair measured; 97.92 MB moved by design (17 U); 120.96 MB in the prescribed accounting (21 U)" % (tot / 1e6), ""]
     json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     src = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_source_summary.py"), rep, "12"], capture_output=True, text=True).stdout
     out += ["## Instruction mix, stall reasons and phase shares (source page)", "", "```", src.rstrip(), "```", ""]
-open(os.path.join(ROOT, "profiles", "r01_%s_ncu.md" % tag), "w").write("\n".join(out))
+open(os.path.join(ROOT, "profiles", "%s_%s_ncu.md" % (rnd, tag)), "w").write("\n".join(out))
 print("\n".join(out[:60]))
