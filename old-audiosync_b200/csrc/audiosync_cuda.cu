@@ -124,6 +124,32 @@ static int build_small_plan(FftPlan* plan, long long L) {
     return 0;
 }
 
+template <typename T>
+static int build_generic_plan_t(FftPlan* plan) {
+    typedef typename GenTraits<T>::C C;
+    const GenShape& sh = plan->gen;
+    const GenTables<C> tb = gen_build_tables<C>(sh);
+    if (upload(plan->g_wcol, tb.wcol) != 0 || upload(plan->g_wrow, tb.wrow) != 0 || upload(plan->g_lo, tb.m_lo) != 0 ||
+        upload(plan->g_hi, tb.m_hi) != 0 || upload(plan->g_p2f_col, tb.p2f_col) != 0 ||
+        upload(plan->g_wpos, tb.wpos) != 0 || upload(plan->g_f2p_row, tb.f2p_row) != 0)
+        return -1;
+    const bool small_col = sh.nt_col == GEN_THREADS_SMALL, small_row = sh.nt_row == GEN_THREADS_SMALL;
+    if ((small_col ? GenStage<T, GEN_THREADS_SMALL>::prepare_cols(sh) : GenStage<T, GEN_THREADS>::prepare_cols(sh)) != 0 ||
+        (small_row ? GenStage<T, GEN_THREADS_SMALL>::prepare_rows(sh) : GenStage<T, GEN_THREADS>::prepare_rows(sh)) != 0)
+        return -1;
+    plan->run_wave = [plan, small_col, small_row](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
+                                                  int dtype, long long sp, long long mp, void* ws, PairPeak* peaks, int pairs,
+                                                  cudaStream_t st) {
+        using Big = GenStage<T, GEN_THREADS>;
+        using Small = GenStage<T, GEN_THREADS_SMALL>;
+        if ((small_col ? Small::col_fwd(plan, ctx, d, src, smp, dtype, sp, mp, ws, peaks, pairs, st)
+                       : Big::col_fwd(plan, ctx, d, src, smp, dtype, sp, mp, ws, peaks, pairs, st)) != 0) return -1;
+        if ((small_row ? Small::rows(plan, ctx, d, ws, pairs, st) : Big::rows(plan, ctx, d, ws, pairs, st)) != 0) return -1;
+        return small_col ? Small::col_inv(plan, ctx, d, ws, peaks, pairs, st) : Big::col_inv(plan, ctx, d, ws, peaks, pairs, st);
+    };
+    return 0;
+}
+
 static int build_generic_plan(FftPlan* plan, long long L, bool precise) {
     plan->kind = PATH_GENERIC_FFT;
     plan->L = L;

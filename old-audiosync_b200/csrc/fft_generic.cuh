@@ -32,7 +32,10 @@ namespace asc {
 #define ASC_GEN_MIN_CTAS 3       // resident CTAs per SM the fp32 runtime-radix kernels are compiled for (85 registers)
 #endif
 constexpr int GEN_MAX_PASSES = 8;
-constexpr int GEN_THREADS = 256;
+constexpr int GEN_THREADS = 256;       // CTA size of the large shapes
+constexpr int GEN_THREADS_SMALL = 64;  // ... and of shapes whose passes have fewer than ~128 butterflies per CTA
+// resident CTAs per SM a runtime-radix kernel is compiled for: 85 registers per thread (fp32)
+constexpr int gen_min_ctas(int nt, bool is_double) { return is_double ? (nt >= 256 ? 1 : 4) : (ASC_GEN_MIN_CTAS * 256) / nt; }
 
 // Division of a small unsigned number by a runtime constant without a divide: q = n / d for
 // n < 2^31 (Granlund-Montgomery: m = ceil(2^(31 + ceil(log2 d)) / d)); powers of two shift.
@@ -82,6 +85,7 @@ struct GenShape {
     long long src_ext;  // real points of the (periodically extended) source: 2L exact, 3L embedded
     int M1, M2;
     int ct;             // columns per tile of the column kernels (fp32: 16 or 8, fp64: 8)
+    int nt_col, nt_row; // threads per CTA of the column / row kernels (GEN_THREADS or GEN_THREADS_SMALL)
     GenAxis col, row;
 };
 
@@ -192,13 +196,13 @@ constexpr bool gen_radix_supported(int r) {
 // --------------------------------------------------------------------- G_A
 // Forward column pass of both signals: grid = (ceil(M2 / CT), 2, pairs).  A thread keeps its
 // column (THREADS is a multiple of CT) and walks the butterflies of that column.
-template <typename T, typename InT, int CT_ = GenTraits<T>::CT>
+template <typename T, typename InT, int CT_ = GenTraits<T>::CT, int NT_ = GEN_THREADS>
 struct GenColFwdKernel {
     typedef typename GenTraits<T>::C C;
     static constexpr int CT = CT_;
-    static constexpr int THREADS = GEN_THREADS;
+    static constexpr int THREADS = NT_;
     static constexpr int TR = THREADS / CT;          // butterflies of one column handled per sweep
-    static constexpr int MIN_CTAS = sizeof(T) == 4 ? ASC_GEN_MIN_CTAS : 1;
+    static constexpr int MIN_CTAS = gen_min_ctas(NT_, sizeof(T) == 8);
     static_assert(THREADS % CT == 0, "a thread must keep its column");
 
     struct Params {
@@ -302,12 +306,12 @@ struct GenColFwdKernel {
 // Forward rows of both planes, split / conj-multiply / merge, inverse rows: grid = (M1/2 + 1, 1, pairs).
 // Rows are padded by one point per 128 bytes (phys), which keeps every pass -- also the stride-1
 // pass of an even radix, e.g. power-of-two lengths -- free of bank conflicts.
-template <typename T>
+template <typename T, int NT_ = GEN_THREADS>
 struct GenRowFusedKernel {
     typedef typename GenTraits<T>::C C;
     static constexpr int PADSH = GenTraits<T>::PADSH;
-    static constexpr int THREADS = GEN_THREADS;
-    static constexpr int MIN_CTAS = sizeof(T) == 4 ? ASC_GEN_MIN_CTAS : 1;
+    static constexpr int THREADS = NT_;
+    static constexpr int MIN_CTAS = gen_min_ctas(NT_, sizeof(T) == 8);
 
     struct Params {
         C* planes;
@@ -491,13 +495,13 @@ struct GenRowFusedKernel {
 // Inverse column pass.  fp32: |r| argmax epilogue over the indices < limit (= 2L), the correlation
 // is never written.  fp64: r[0 .. limit) is written to `r_out` (the dead sample plane) and resolved
 // by argmax_f64_kernel, which keeps full double keys.  grid = (pairs, ceil(M2 / CT)).
-template <typename T, int CT_ = GenTraits<T>::CT>
+template <typename T, int CT_ = GenTraits<T>::CT, int NT_ = GEN_THREADS>
 struct GenColInvKernel {
     typedef typename GenTraits<T>::C C;
     static constexpr int CT = CT_;
-    static constexpr int THREADS = GEN_THREADS;
+    static constexpr int THREADS = NT_;
     static constexpr int TR = THREADS / CT;
-    static constexpr int MIN_CTAS = sizeof(T) == 4 ? ASC_GEN_MIN_CTAS : 1;
+    static constexpr int MIN_CTAS = gen_min_ctas(NT_, sizeof(T) == 8);
 
     struct Params {
         const C* planes;

@@ -1,0 +1,3 @@
+// Runtime-radix four-step kernels, float arithmetic, 256 threads per CTA (see gen_impl.cuh).
+#include "gen_impl.cuh"
+template struct asc::GenStage<float, 256>;

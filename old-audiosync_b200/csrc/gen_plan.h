@@ -98,13 +98,14 @@ inline double gen_split_cost(long long M, int M1, int elem, int ct) {
     std::map<int, GenAxisCost> memo;
     const GenAxisCost pc = gen_axis_cost(M1, memo), pr = gen_axis_cost((int)M2, memo);
     if (pc.cost < 0.0 || pr.cost < 0.0 || pc.passes > GEN_MAX_PASSES || pr.passes > GEN_MAX_PASSES) return 0.0;
-    // a pass keeps GEN_THREADS threads busy only if the CTA has that many butterflies (radix ~10)
-    auto util = [](double butterflies) { const double u = butterflies / GEN_THREADS; return u > 1.0 ? 1.0 : (u < 0.25 ? 0.25 : u); };
+    // a pass keeps a CTA's threads busy only if it has that many butterflies (radix ~10); the kernels
+    // exist with 256 and with 64 threads per CTA
+    auto util = [](double butterflies) { const double u = butterflies / GEN_THREADS_SMALL; return u > 1.0 ? 1.0 : (u < 0.25 ? 0.25 : u); };
     // resident CTAs per SM by shared memory (the kernels are compiled for three)
     auto occupancy_penalty = [](size_t bytes) { return bytes > 112 * 1024 ? 1.8 : (bytes > 74 * 1024 ? 1.25 : 1.0); };
     // column passes: forward on 1.5 signals + inverse on 1; row passes: forward on 2, inverse on 1
     double col = 2.5 * pc.cost / util((double)M1 * ct / 10.0) * occupancy_penalty(tile);
-    if (ct * elem < 128) col *= 1.1;            // half cache lines per tile row
+    if (ct * elem < 128) col *= 1.3;            // half cache lines per tile row (measured: K_A +27 % at M1 = 250)
     if (M2 % ct != 0) col *= 1.25;              // ragged last tile, rows not line-aligned
     const double row = 3.0 * pr.cost / util(4.0 * (double)M2 / 10.0) * occupancy_penalty(rows);
     return col + row;
@@ -172,6 +173,11 @@ inline bool gen_make_shape(long long L, bool is_double, GenShape* out) {
     sh.ct = ct;
     sh.M2 = (int)(sh.M / m1);
     if (!gen_make_axis(sh.M1, &sh.col) || !gen_make_axis(sh.M2, &sh.row)) return false;
+    // CTA size: the pass with the largest radix has the fewest butterflies per CTA (column tile:
+    // M1 / R per column; rows: the inverse passes work on two rows)
+    auto max_radix = [](const GenAxis& ax) { int m = 0; for (int p = 0; p < ax.npass; p++) m = std::max(m, ax.radix[p]); return m; };
+    sh.nt_col = (sh.M1 / max_radix(sh.col)) * sh.ct >= 2 * GEN_THREADS_SMALL ? GEN_THREADS : GEN_THREADS_SMALL;
+    sh.nt_row = (sh.M2 / max_radix(sh.row)) * 2 >= 2 * GEN_THREADS_SMALL ? GEN_THREADS : GEN_THREADS_SMALL;
     *out = sh;
     return true;
 }
@@ -212,7 +218,7 @@ inline std::string gen_describe(const GenShape& sh, bool is_double) {
     for (int i = 0; i < sh.col.npass; i++) d += (i ? "x" : "") + std::to_string(sh.col.radix[i]);
     d += " row=";
     for (int i = 0; i < sh.row.npass; i++) d += (i ? "x" : "") + std::to_string(sh.row.radix[i]);
-    d += " tile=" + std::to_string(sh.ct);
+    d += " tile=" + std::to_string(sh.ct) + " threads=" + std::to_string(sh.nt_col) + "/" + std::to_string(sh.nt_row);
     d += sh.M == sh.L ? " generic four-step" : " generic four-step, embedded (N'=2M>=3L)";
     d += is_double ? " fp64" : " fp32";
     return d;

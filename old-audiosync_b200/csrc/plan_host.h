@@ -143,6 +143,16 @@ static int prepare_kernel(size_t smem) {
 
 // Builders instantiated in their own translation units.
 template <class P> int build_static_plan(FftPlan* plan);     // static_plan_impl.cuh: one per interval length
-template <typename T> int build_generic_plan_t(FftPlan* plan);   // gen_impl.cuh: float, double
+// gen_impl.cuh: launchers of the runtime-radix kernels per (arithmetic type, CTA size)
+template <typename T, int NT>
+struct GenStage {
+    static int prepare_cols(const GenShape& sh);
+    static int prepare_rows(const GenShape& sh);
+    static int col_fwd(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp, int dtype,
+                       long long sp, long long mp, void* ws, PairPeak* peaks, int pairs, cudaStream_t st);
+    static int rows(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d, void* ws, int pairs, cudaStream_t st);
+    static int col_inv(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d, void* ws, PairPeak* peaks, int pairs,
+                       cudaStream_t st);
+};
 
 }  // namespace asc

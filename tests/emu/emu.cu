@@ -140,9 +140,10 @@ static int run_generic(const InT* source, const InT* sample, long long L, long l
                 K::run(ex, p, smem.data());
             }
     };
-    if (sh.ct == 16) col_fwd(GenColFwdKernel<T, InT, 16>{}); else col_fwd(GenColFwdKernel<T, InT, 8>{});
-    {
-        using K = GenRowFusedKernel<T>;
+    if (sh.nt_col == GEN_THREADS) { if (sh.ct == 16) col_fwd(GenColFwdKernel<T, InT, 16, GEN_THREADS>{}); else col_fwd(GenColFwdKernel<T, InT, 8, GEN_THREADS>{}); }
+    else { if (sh.ct == 16) col_fwd(GenColFwdKernel<T, InT, 16, GEN_THREADS_SMALL>{}); else col_fwd(GenColFwdKernel<T, InT, 8, GEN_THREADS_SMALL>{}); }
+    auto rows = [&](auto KK) {
+        using K = decltype(KK);
         typename K::Params p{planes.data(), tb.wrow.data(), tb.wpos.data(), tb.m_lo.data(), tb.m_hi.data(),
                              tb.f2p_row.data(), sh};
         std::vector<C> smem(K::smem_bytes(sh) / sizeof(C) + 1);
@@ -150,7 +151,8 @@ static int run_generic(const InT* source, const InT* sample, long long L, long l
             HostExec ex{r, 0, 0, K::THREADS};
             K::run(ex, p, smem.data());
         }
-    }
+    };
+    if (sh.nt_row == GEN_THREADS) rows(GenRowFusedKernel<T, GEN_THREADS>{}); else rows(GenRowFusedKernel<T, GEN_THREADS_SMALL>{});
     auto col_inv = [&](auto KK) {
         using K = decltype(KK);
         typename K::Params p{planes.data(), &pk, tb.wcol.data(), tb.p2f_col.data(), sh, reinterpret_cast<T*>(planes.data())};
@@ -160,7 +162,8 @@ static int run_generic(const InT* source, const InT* sample, long long L, long l
             K::run(ex, p, smem.data());
         }
     };
-    if (sh.ct == 16) col_inv(GenColInvKernel<T, 16>{}); else col_inv(GenColInvKernel<T, 8>{});
+    if (sh.nt_col == GEN_THREADS) { if (sh.ct == 16) col_inv(GenColInvKernel<T, 16, GEN_THREADS>{}); else col_inv(GenColInvKernel<T, 8, GEN_THREADS>{}); }
+    else { if (sh.ct == 16) col_inv(GenColInvKernel<T, 16, GEN_THREADS_SMALL>{}); else col_inv(GenColInvKernel<T, 8, GEN_THREADS_SMALL>{}); }
     const double scale = gen_peak_scale(sh);
     if (sizeof(T) == 4) {
         *raw_index = (long long)argmax_key_index(pk.key);
