@@ -176,8 +176,8 @@ inline bool gen_make_shape(long long L, bool is_double, GenShape* out) {
     // CTA size: the pass with the largest radix has the fewest butterflies per CTA (column tile:
     // M1 / R per column; rows: the inverse passes work on two rows)
     auto max_radix = [](const GenAxis& ax) { int m = 0; for (int p = 0; p < ax.npass; p++) m = std::max(m, ax.radix[p]); return m; };
-    sh.nt_col = (sh.M1 / max_radix(sh.col)) * sh.ct >= 2 * GEN_THREADS_SMALL ? GEN_THREADS : GEN_THREADS_SMALL;
-    sh.nt_row = (sh.M2 / max_radix(sh.row)) * 2 >= 2 * GEN_THREADS_SMALL ? GEN_THREADS : GEN_THREADS_SMALL;
+    sh.nt_col = (sh.M1 / max_radix(sh.col)) * sh.ct >= GEN_THREADS ? GEN_THREADS : GEN_THREADS_SMALL;
+    sh.nt_row = (sh.M2 / max_radix(sh.row)) * 2 >= GEN_THREADS ? GEN_THREADS : GEN_THREADS_SMALL;
     *out = sh;
     return true;
 }
