@@ -233,6 +233,17 @@ int emu_generic_f64(const double* source, const double* sample, long long L, int
     return precise ? run_generic<double, double>(source, sample, L, raw_index, peak_value, second_value, desc, desc_len)
                    : run_generic<float, double>(source, sample, L, raw_index, peak_value, second_value, desc, desc_len);
 }
+// multiply-shift division of the runtime-radix kernels: first (n, d) with fast_div(n, d) != n / d, or 0
+long long emu_fastdiv_first_error(unsigned d_max, unsigned n_max) {
+    for (unsigned d = 1; d <= d_max; d++) {
+        const FastDiv f = make_fastdiv(d);
+        for (unsigned n = 0; n <= n_max; n = n < 70000 ? n + 1 : n + 997)
+            if (fast_div(n, f) != n / d) return ((long long)d << 32) | n;
+        for (unsigned n : {0x7fffffffu, 0x7ffffffeu, 0x40000000u})
+            if (fast_div(n, f) != n / d) return ((long long)d << 32) | n;
+    }
+    return 0;
+}
 int emu_generic_describe(long long L, int precise, char* desc, size_t desc_len) {
     GenShape sh;
     if (!gen_make_shape(L, precise != 0, &sh)) return -1;

@@ -276,3 +276,11 @@ def test_fp64_arithmetic_mode_on_hard_goldens(emu, case):
     assert abs(sec - case["second"]) <= 1e-9 * abs(case["peak"]) + 1e-300
     idx32, _, _, _ = run_generic(emu, src, smp)
     assert idx32 == case["raw_index"]
+
+
+def test_fast_division_is_exact(emu):
+    """FastDiv (fft_generic.cuh): n / d by multiply-high + shift for every divisor a plan can produce
+    (strides and butterflies per row, < 2^20) and every n a kernel forms (< 2^31)."""
+    emu.emu_fastdiv_first_error.restype = C.c_longlong
+    emu.emu_fastdiv_first_error.argtypes = [C.c_uint, C.c_uint]
+    assert emu.emu_fastdiv_first_error(4100, 3000000) == 0
