@@ -210,7 +210,7 @@ def run_generic(E, src, smp, f64=False, precise=False):
     return idx.value, pk.value, sec.value, desc.value.decode()
 
 
-GENERIC_LENGTHS = [256, 257, 1001, 2187, 4099, 6561, 8749, 10007, 24000, 39366, 65536, 100000, 250000]
+GENERIC_LENGTHS = [256, 257, 1001, 2187, 4099, 6561, 8749, 10007, 24000, 39366, 65536, 98415, 100000, 250000]
 
 
 @pytest.mark.parametrize("L", GENERIC_LENGTHS)

@@ -201,7 +201,7 @@ def test_hard_goldens_dropin_and_batch(ac, ctx, case):
 
 
 # ------------------------------------------------------------------ any length: runtime-radix plans
-GEN_LENGTHS = [4099, 8749, 10007, 24000, 100000, 250000, 1000000, 1048576, 1440002]
+GEN_LENGTHS = [4099, 8749, 10007, 24000, 98415, 100000, 250000, 1000000, 1048576, 1440002]
 
 
 @pytest.mark.parametrize("L", GEN_LENGTHS)
