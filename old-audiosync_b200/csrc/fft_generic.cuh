@@ -86,6 +86,7 @@ struct GenShape {
     int M1, M2;
     int ct;             // columns per tile of the column kernels (fp32: 16 or 8, fp64: 8)
     int nt_col, nt_row; // threads per CTA of the column / row kernels (GEN_THREADS or GEN_THREADS_SMALL)
+    int row_pad;        // rows of the row kernel padded by one point per 128 bytes (1) or plain (0)
     GenAxis col, row;
 };
 
@@ -322,7 +323,6 @@ struct GenRowFusedKernel {
         const int* f2p_row;      // position of frequency
         GenShape sh;
     };
-    static ASC_HD int phys(int p) { return p + (p >> PADSH); }
     static ASC_HD int row_pitch(int M2) { return M2 + (M2 >> PADSH) + 1; }
     static size_t smem_bytes(const GenShape& sh) { return (size_t)4 * row_pitch(sh.M2) * sizeof(C) + 16; }
 
@@ -331,6 +331,10 @@ struct GenRowFusedKernel {
         const GenShape& sh = p.sh;
         const int M1 = sh.M1, M2 = sh.M2;
         const int RP = row_pitch(M2);
+        // padded rows (one point per 128 bytes) where the planner found bank conflicts without them:
+        // power-of-two-rich row lengths; plain rows otherwise (cheaper addressing)
+        const bool padded = sh.row_pad != 0;
+        auto phys = [padded](int p) -> int { return padded ? p + (p >> PADSH) : p; };
         const int r = ex.bx();
         const long long pair = ex.bz();
         const bool two = (r != 0) && (2 * r != M1);
@@ -366,8 +370,8 @@ struct GenRowFusedKernel {
                 const int items = per_row * 2 * nrows;
                 const int tstep = M2 / (S * R);
                 const FastDiv dS = sh.row.div_stride[ps], dI = sh.row.div_items[ps];
-                const bool regular = (S & ((1 << PADSH) - 1)) == 0;
-                const int SP = S + (S >> PADSH);
+                const bool regular = !padded || (S & ((1 << PADSH) - 1)) == 0;
+                const int SP = padded ? S + (S >> PADSH) : S;
                 ex.phase([&](int tid) {
                     for (int w = tid; w < items; w += THREADS) {
                         const int bw = (int)fast_div((unsigned)w, dI), bf = w - bw * per_row;
@@ -446,8 +450,8 @@ struct GenRowFusedKernel {
                 const int items = per_row * nrows;
                 const int tstep = M2 / (S * R);
                 const FastDiv dS = sh.row.div_stride[ps], dI = sh.row.div_items[ps];
-                const bool regular = (S & ((1 << PADSH) - 1)) == 0;
-                const int SP = S + (S >> PADSH);
+                const bool regular = !padded || (S & ((1 << PADSH) - 1)) == 0;
+                const int SP = padded ? S + (S >> PADSH) : S;
                 ex.phase([&](int tid) {
                     for (int w = tid; w < items; w += THREADS) {
                         const int rw = (int)fast_div((unsigned)w, dI), bf = w - rw * per_row;

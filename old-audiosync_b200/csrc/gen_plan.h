@@ -129,6 +129,34 @@ inline bool gen_choose_split(long long M, int elem, bool is_double, int* M1_out,
     return true;
 }
 
+// Shared-memory bank conflicts of the row kernel's passes for a row layout: per pass the worst
+// number of lanes of one wavefront (128 bytes of lanes: 16 fp32 points, 8 fp64 points) that fall
+// into the same bank group, averaged over the first butterflies and inputs; 1.0 = conflict-free.
+inline double gen_row_conflicts(const GenAxis& row, int elem, bool padded) {
+    const int lanes = 128 / elem, padsh = elem == 8 ? 4 : 3;
+    auto phys = [&](int p) { return padded ? p + (p >> padsh) : p; };
+    double total = 0.0;
+    for (int ps = 0; ps < row.npass; ps++) {
+        const int R = row.radix[ps], S = row.stride[ps], per_row = row.n / R;
+        double worst_sum = 0.0;
+        int cases = 0;
+        for (int w0 = 0; w0 + lanes <= per_row && cases < 8; w0 += lanes)
+            for (int q = 0; q < R && q < 4; q++) {
+                int count[32] = {0};
+                int worst = 0;
+                for (int l = 0; l < lanes; l++) {
+                    const int bf = w0 + l, blk = bf / S, j = bf - blk * S;
+                    const int bank = phys(blk * S * R + j + q * S) % lanes;
+                    worst = std::max(worst, ++count[bank]);
+                }
+                worst_sum += worst;
+                cases++;
+            }
+        total += cases ? worst_sum / cases : 1.0;
+    }
+    return total / row.npass;
+}
+
 // The plan for a sample_len: the exact length when it is 2/3/5-smooth and splits, otherwise the
 // cheapest embedding length M >= ceil(3L / 2) among the smooth numbers up to 15 % above the
 // smallest one.  is_double: fp64 arithmetic (16-byte points, 8-column tiles).
@@ -176,8 +204,12 @@ inline bool gen_make_shape(long long L, bool is_double, GenShape* out) {
     // CTA size: the pass with the largest radix has the fewest butterflies per CTA (column tile:
     // M1 / R per column; rows: the inverse passes work on two rows)
     auto max_radix = [](const GenAxis& ax) { int m = 0; for (int p = 0; p < ax.npass; p++) m = std::max(m, ax.radix[p]); return m; };
-    sh.nt_col = (sh.M1 / max_radix(sh.col)) * sh.ct >= GEN_THREADS ? GEN_THREADS : GEN_THREADS_SMALL;
-    sh.nt_row = (sh.M2 / max_radix(sh.row)) * 2 >= GEN_THREADS ? GEN_THREADS : GEN_THREADS_SMALL;
+    // rows: padded only where padding removes bank conflicts worth more than its address arithmetic
+    sh.row_pad = gen_row_conflicts(sh.row, elem, true) < 0.8 * gen_row_conflicts(sh.row, elem, false) ? 1 : 0;
+    // ... and only where the CTA's buffer is small enough that twelve 64-thread CTAs fit an SM
+    const size_t tile_bytes = (size_t)sh.M1 * sh.ct * elem, rows_bytes = (size_t)4 * (sh.M2 + sh.M2 / 8 + 1) * elem;
+    sh.nt_col = ((sh.M1 / max_radix(sh.col)) * sh.ct >= GEN_THREADS || tile_bytes > 18 * 1024) ? GEN_THREADS : GEN_THREADS_SMALL;
+    sh.nt_row = ((sh.M2 / max_radix(sh.row)) * 2 >= GEN_THREADS || rows_bytes > 18 * 1024) ? GEN_THREADS : GEN_THREADS_SMALL;
     *out = sh;
     return true;
 }
@@ -218,7 +250,7 @@ inline std::string gen_describe(const GenShape& sh, bool is_double) {
     for (int i = 0; i < sh.col.npass; i++) d += (i ? "x" : "") + std::to_string(sh.col.radix[i]);
     d += " row=";
     for (int i = 0; i < sh.row.npass; i++) d += (i ? "x" : "") + std::to_string(sh.row.radix[i]);
-    d += " tile=" + std::to_string(sh.ct) + " threads=" + std::to_string(sh.nt_col) + "/" + std::to_string(sh.nt_row);
+    d += std::string(sh.row_pad ? " padded" : " plain") + " tile=" + std::to_string(sh.ct) + " threads=" + std::to_string(sh.nt_col) + "/" + std::to_string(sh.nt_row);
     d += sh.M == sh.L ? " generic four-step" : " generic four-step, embedded (N'=2M>=3L)";
     d += is_double ? " fp64" : " fp32";
     return d;

@@ -251,7 +251,7 @@ def test_generic_plan_shapes():
                 assert L > 3 * 10 ** 6, (L, precise)       # only very long inputs may lack a plan
                 continue
             d = buf.value.decode()
-            m = re.search(r"M=(\d+) M1=(\d+) M2=(\d+) col=([0-9x]+) row=([0-9x]+) tile=(\d+)", d)
+            m = re.search(r"M=(\d+) M1=(\d+) M2=(\d+) col=([0-9x]+) row=([0-9x]+) (?:padded|plain) tile=(\d+)", d)
             M, M1, M2, ct = int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(6))
             col = [int(x) for x in m.group(4).split("x")]; row = [int(x) for x in m.group(5).split("x")]
             assert M1 * M2 == M and np.prod(col) == M1 and np.prod(row) == M2
