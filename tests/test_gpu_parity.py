@@ -742,6 +742,26 @@ def test_full_size_batch_recovers_injected_lags(ac, ctx, capi):
         assert (0.994 < c < 0.996) if pid % 4 != 3 else (0.79 < c < 0.81)
 
 
+def test_full_size_shift_property(ac, ctx):
+    """L = 1,440,000, independent of the oracle: r[j] = N * sum_n source[(n + j) mod N] * sample[n], so
+    rotating the source by d rotates r by d -- the raw index must move by exactly d (mod 2L), the
+    peak and the second peak must stay (to fp32 rounding), for shifts that cross the fold boundary
+    idx = L in both directions."""
+    import torch
+    L, n = 1440000, 6
+    res0, d_src, d_smp = _batch_on_device(ac, ctx, SEED + 60, 0, n, L)
+    src = d_src.view(n, 2 * L)
+    shifts = [1, -1, 12345, L, L + 7, -(L // 3)]
+    rolled = torch.stack([torch.roll(src[i], shifts[i]) for i in range(n)]).contiguous()
+    rec = ctx.xcorr_batch_torch(rolled, d_smp.view(n, L))
+    for i in range(n):
+        want = (int(res0["raw_index"][i]) + shifts[i]) % (2 * L)
+        assert int(rec["raw_index"][i]) == want
+        assert int(rec["lag"][i]) == (want if want < L else want - 2 * L)
+        assert close(float(rec["peak"][i]), float(res0["peak"][i]), 1e-5)
+        assert abs(float(rec["second"][i]) - float(res0["second"][i])) <= 1e-5 * abs(float(res0["peak"][i]))
+
+
 def test_scaling_and_negation_properties(ac, ctx, capi):
     """r is bilinear: scaling the sample by a power of two scales the peak exactly and leaves
     lag and coefficient unchanged; negating it flips the peak sign and the coefficient."""
