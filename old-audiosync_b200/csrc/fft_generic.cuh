@@ -323,7 +323,7 @@ struct GenRowFusedKernel {
         const int* f2p_row;      // position of frequency
         GenShape sh;
     };
-    static ASC_HD int row_pitch(int M2) { return M2 + (M2 >> PADSH) + 1; }
+    static ASC_HD int row_pitch(int M2) { return (M2 + (M2 >> PADSH) + 2) & ~1; }     // even: 16-byte rows for bulk copies
     static size_t smem_bytes(const GenShape& sh) { return (size_t)4 * row_pitch(sh.M2) * sizeof(C) + 16; }
 
     template <class Ex>
@@ -344,8 +344,30 @@ struct GenRowFusedKernel {
         C* __restrict__ plane_p = plane_s + sh.M;
         const int P = sh.row.npass;
 
-        // stage: slots 0,1 source rows (k1a, k1b); 2,3 sample rows.  Asynchronous copies, one element
-        // each (the padded rows are element-aligned only), all in flight before the first wait.
+        // stage: slots 0,1 source rows (k1a, k1b); 2,3 sample rows.  Plain rows of whole 16-byte units
+        // arrive as bulk copies of the TMA unit (one instruction per row, completion on an mbarrier
+        // behind the last row); padded rows as asynchronous copies of one element each (they are
+        // element-aligned only), all in flight before the first wait.
+        const bool bulk = !padded && ((size_t)M2 * sizeof(C)) % 16 == 0 && (size_t)M2 * sizeof(C) >= 4096;   // short rows: cp.async has the lower latency
+        void* mbar = buf + 4 * RP;
+        if (bulk) {
+            ex.phase([&](int tid) {
+                if (tid == 0) mbar_init(mbar, 1);
+            });
+            ex.phase([&](int tid) {
+                if (tid == 0) {
+                    const unsigned full = (unsigned)(M2 * sizeof(C));
+                    mbar_expect_tx(mbar, (unsigned)(2 * nrows) * full);
+                    bulk_load(buf, plane_s + (long long)k1a * M2, full, mbar);
+                    bulk_load(buf + 2 * RP, plane_p + (long long)k1a * M2, full, mbar);
+                    if (two) {
+                        bulk_load(buf + RP, plane_s + (long long)k1b * M2, full, mbar);
+                        bulk_load(buf + 3 * RP, plane_p + (long long)k1b * M2, full, mbar);
+                    }
+                }
+                mbar_wait(mbar, 0);
+            });
+        } else
         ex.phase([&](int tid) {
             for (int slot = 0; slot < 4; slot++) {
                 const int rr = slot & 1;
@@ -441,8 +463,8 @@ struct GenRowFusedKernel {
                 }
             }
         });
-        // inverse DIT on nrows rows (slots 0,1), passes P-1 .. 0
-        for (int ps = P - 1; ps >= 0; ps--) {
+        // inverse DIT on nrows rows (slots 0,1), passes P-1 .. 1 in place
+        for (int ps = P - 1; ps >= 1; ps--) {
             const int S = sh.row.stride[ps];
             gen_dispatch_radix(sh.row.radix[ps], [&](auto RR) {
                 constexpr int R = decltype(RR)::value;
@@ -483,15 +505,60 @@ struct GenRowFusedKernel {
                 });
             });
         }
-        // natural order now: times conj W_M^(n2 * k1), back in place (row k1 of plane 0)
-        ex.phase([&](int tid) {
-            for (int rw = 0; rw < nrows; rw++) {
-                const unsigned k1 = (unsigned)(rw ? k1b : k1a);
-                C* __restrict__ o = plane_s + (size_t)k1 * (unsigned)M2;
-                for (int e = tid; e < M2; e += THREADS)
-                    o[e] = cmulc(buf[rw * RP + phys(e)], gen_tw2<C>(p.m_lo, p.m_hi, (unsigned)e * k1));
-            }
-        });
+        // last inverse pass (pass 0: one block per row, butterfly j yields the natural-order points
+        // n2 = j + k * S): times conj W_M^(n2 * k1) = conj(W_M^(j * k1) * (W_M^(S * k1))^k), straight
+        // to row k1 of plane 0 -- consecutive threads, consecutive points
+        {
+            const int S = sh.row.stride[0];
+            gen_dispatch_radix(sh.row.radix[0], [&](auto RR) {
+                constexpr int R = decltype(RR)::value;
+                const int tstep = M2 / (S * R);           // == 1
+                const bool regular = !padded || (S & ((1 << PADSH) - 1)) == 0;
+                const int SP = padded ? S + (S >> PADSH) : S;
+                ex.phase([&](int tid) {
+                    for (int w = tid; w < nrows * S; w += THREADS) {
+                        const int rw = w >= S ? 1 : 0, j = w - rw * S;
+                        const unsigned k1 = (unsigned)(rw ? k1b : k1a);
+                        C* __restrict__ row = buf + rw * RP;
+                        C* __restrict__ o = plane_s + (size_t)k1 * (unsigned)M2;
+                        {
+                            C v[R];
+                            {
+                                // twiddles from their four power-of-two entries as they are used (a full
+                                // t[R] beside v[R] would not fit the 85-register budget in this pass)
+                                C t[9];
+                                static_for<0, 4>([&](auto I) {
+                                    constexpr int k = 1 << decltype(I)::value;
+                                    if constexpr (k < R) t[k] = ldg(p.wrow + j * (k * tstep));
+                                });
+                                if (regular) {
+                                    C* __restrict__ b0 = row + phys(j);
+                                    v[0] = b0[0];
+                                    static_for<1, R>([&](auto Q) { v[decltype(Q)::value] = cmulc(b0[decltype(Q)::value * SP], gen_pow_from_pow2<decltype(Q)::value, C>(t)); });
+                                } else {
+                                    v[0] = row[phys(j)];
+                                    static_for<1, R>([&](auto Q) { v[decltype(Q)::value] = cmulc(row[phys(j + decltype(Q)::value * S)], gen_pow_from_pow2<decltype(Q)::value, C>(t)); });
+                                }
+                            }
+                            dft_reg<R, +1, C>(v);
+                            // the row's constants are formed here, after the butterfly (a thread runs this
+                            // loop once or twice: keeping them live across it only costs registers)
+                            C g[9];
+                            static_for<0, 4>([&](auto I) {
+                                constexpr int k = 1 << decltype(I)::value;
+                                if constexpr (k < R) g[k] = gen_tw2<C>(p.m_lo, p.m_hi, (unsigned)(S * k) * k1);
+                            });
+                            const C t0 = gen_tw2<C>(p.m_lo, p.m_hi, (unsigned)j * k1);
+                            o[j] = cmulc(v[0], t0);
+                            static_for<1, R>([&](auto K) {
+                                constexpr int k = decltype(K)::value;
+                                o[j + k * S] = cmulc(v[k], cmul(t0, gen_pow_from_pow2<k, C>(g)));
+                            });
+                        }
+                    }
+                });
+            });
+        }
     }
 };
 
