@@ -249,10 +249,30 @@ struct GenColFwdKernel {
                     if ((int)n2 >= M2) return;
                     auto load = [&](int i0, C (&v)[R]) {
                         if (first) {
-                            static_for<0, R>([&](auto Q) {
-                                constexpr int q = decltype(Q)::value;
-                                v[q] = gen_load_point<C, InT>(x, (unsigned)(i0 + q * S) * (unsigned)M2 + n2, sig, sh.L, sh.src_ext, fast_pts, vec);
-                            });
+                            // packed points n0 + q * dn; when the last one still lies inside the array
+                            // proper the whole butterfly is R vector loads at a constant stride
+                            typedef typename scalar_of<C>::type real;
+                            const unsigned nfirst = (unsigned)i0 * (unsigned)M2 + n2, dn = (unsigned)S * (unsigned)M2;
+                            if (vec && nfirst + (unsigned)(R - 1) * dn < fast_pts) {
+                                if constexpr (sizeof(InT) == 4) {
+                                    const float2* __restrict__ px = reinterpret_cast<const float2*>(x) + nfirst;
+                                    static_for<0, R>([&](auto Q) {
+                                        const float2 d2 = ldg(px + (size_t)decltype(Q)::value * dn);
+                                        v[decltype(Q)::value] = cmake((real)d2.x, (real)d2.y);
+                                    });
+                                } else {
+                                    const double2* __restrict__ px = reinterpret_cast<const double2*>(x) + nfirst;
+                                    static_for<0, R>([&](auto Q) {
+                                        const double2 d2 = ldg(px + (size_t)decltype(Q)::value * dn);
+                                        v[decltype(Q)::value] = cmake((real)d2.x, (real)d2.y);
+                                    });
+                                }
+                            } else {
+                                static_for<0, R>([&](auto Q) {
+                                    constexpr int q = decltype(Q)::value;
+                                    v[q] = gen_load_point<C, InT>(x, nfirst + (unsigned)q * dn, sig, sh.L, sh.src_ext, fast_pts, vec);
+                                });
+                            }
                         } else {
                             static_for<0, R>([&](auto Q) { v[decltype(Q)::value] = buf[(i0 + decltype(Q)::value * S) * CT + c]; });
                         }
