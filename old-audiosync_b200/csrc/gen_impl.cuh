@@ -7,10 +7,18 @@
 
 namespace asc {
 
+// The runtime-radix kernels serve plans of many shapes: each is allowed the device's whole opt-in
+// shared memory (a per-plan limit would be lowered again by the next, smaller plan of the same kernel).
 template <class K>
 static int prepare_gen_kernel(size_t smem) {
-    if (smem > 48 * 1024)
-        ASC_CUDA_OK(cudaFuncSetAttribute(gen_kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, optin = 0;
+    ASC_CUDA_OK(cudaGetDevice(&dev));
+    ASC_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (smem > (size_t)optin) {
+        set_last_error("plan needs %zu bytes of shared memory per CTA, the device allows %d", smem, optin);
+        return -1;
+    }
+    ASC_CUDA_OK(cudaFuncSetAttribute(gen_kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     return 0;
 }
 

@@ -230,6 +230,15 @@ def test_generic_plan_any_length_vs_oracle(ac, ctx, capi, L):
             assert (ret, lag) == (o["ret"], o["lag"]) and close(coef, o["coef"])
 
 
+def test_generic_plans_of_different_sizes_in_one_context(ac, ctx, capi):
+    """A large plan, a small one, the large one again, all on the same kernels of one context: the
+    shared-memory limit of a kernel must not shrink with the last plan built."""
+    for L in (1000000, 4099, 1000000, 24000, 250000, 1000000):
+        res, _, _ = _batch_on_device(ac, ctx, SEED + 70, 0, 2, L)
+        for i in range(2):
+            assert int(res["lag"][i]) == capi.synth_true_lag(SEED + 70, i, L) and int(res["ret"][i]) == 0
+
+
 def test_generic_plan_edges_off_schedule(ac, ctx, capi):
     """idx == L, idx == L + 1, all-zero sample and a NaN input on an embedded (odd) length."""
     import hard_cases as hc
