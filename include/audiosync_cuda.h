@@ -96,6 +96,11 @@ void audiosync_cuda_set_residency(int on);
  * calls that reused a resident session.  Any pointer may be NULL. */
 void audiosync_cuda_dropin_stats(uint64_t *calls, uint64_t *h2d_bytes, uint64_t *resident_hits);
 
+/* Largest number of drop-in cross_correlation() calls that were in flight on the GPU(s) at the
+ * same time since load (or since the last call with reset != 0): > 1 means concurrent callers
+ * really overlapped instead of queueing on a lock. */
+int audiosync_cuda_dropin_max_inflight(int reset);
+
 /* ------------------------------------------------------------------------
  * Part 3 -- batched / multi-GPU surface (new; not in the reference)
  * ------------------------------------------------------------------------ */

@@ -24,7 +24,7 @@ __all__ = [
     "interval_loop", "Context", "RESULT_DTYPE", "MIN_CONFIDENCE", "SAMPLE_RATE",
     "INTERV_SAMPLE", "frames_to_ms", "F32", "F64", "HOST", "DEVICE",
     "PATH_AUTO", "PATH_FFT", "PATH_DIRECT", "EXPORTED_SYMBOLS", "shard_pairs", "gather_results",
-    "cross_correlation_ptr", "RealBuffer", "set_residency", "dropin_stats", "SessionPool",
+    "cross_correlation_ptr", "RealBuffer", "set_residency", "dropin_stats", "dropin_max_inflight", "SessionPool",
 ]
 
 F32, F64 = 0, 1
@@ -49,7 +49,7 @@ EXPORTED_SYMBOLS = [
     "audiosync_cuda_xcorr_batch", "audiosync_cuda_xcorr_batch_results", "audiosync_cuda_xcorr_batch_device",
     "audiosync_cuda_synth_pairs", "audiosync_cuda_synchronize",
     "audiosync_cuda_set_path", "audiosync_cuda_set_wave_pairs", "audiosync_cuda_set_debug", "audiosync_cuda_set_precise",
-    "audiosync_cuda_set_residency", "audiosync_cuda_dropin_stats",
+    "audiosync_cuda_set_residency", "audiosync_cuda_dropin_stats", "audiosync_cuda_dropin_max_inflight",
     "audiosync_cuda_pool_create", "audiosync_cuda_pool_destroy", "audiosync_cuda_pool_reset",
     "audiosync_cuda_pool_append", "audiosync_cuda_pool_append_async", "audiosync_cuda_pool_flush",
     "audiosync_cuda_pool_fill", "audiosync_cuda_pool_run",
@@ -121,6 +121,8 @@ def lib() -> C.CDLL:
     L.audiosync_cuda_set_residency.argtypes = [i32]
     L.audiosync_cuda_dropin_stats.restype = None
     L.audiosync_cuda_dropin_stats.argtypes = [C.POINTER(C.c_uint64)] * 3
+    L.audiosync_cuda_dropin_max_inflight.restype = i32
+    L.audiosync_cuda_dropin_max_inflight.argtypes = [i32]
     L.audiosync_cuda_pool_create.restype = i32
     L.audiosync_cuda_pool_create.argtypes = [vp, i32, sz, sz, i32, C.POINTER(vp)]
     L.audiosync_cuda_pool_destroy.restype = None
@@ -295,6 +297,11 @@ def dropin_stats():
     a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
     lib().audiosync_cuda_dropin_stats(C.byref(a), C.byref(b), C.byref(c))
     return int(a.value), int(b.value), int(c.value)
+
+
+def dropin_max_inflight(reset: bool = False) -> int:
+    """Largest number of drop-in calls in flight at the same time (see include/audiosync_cuda.h)."""
+    return int(lib().audiosync_cuda_dropin_max_inflight(1 if reset else 0))
 
 
 def pearson_coefficient(x: np.ndarray, y: np.ndarray) -> float:

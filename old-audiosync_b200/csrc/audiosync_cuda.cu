@@ -499,6 +499,7 @@ static std::map<const char*, size_t> g_allocs;          // user pointer -> bytes
 static std::atomic<uint64_t> g_alloc_gen{1};
 static std::atomic<int> g_residency{-1};                // -1: read AUDIOSYNC_CUDA_RESIDENT on first use
 static std::atomic<uint64_t> g_dropin_calls{0}, g_dropin_h2d_bytes{0}, g_dropin_resident_hits{0};
+static std::atomic<int> g_dropin_inflight{0}, g_dropin_inflight_max{0};
 
 static bool residency_enabled() {
     int v = g_residency.load();
@@ -550,6 +551,10 @@ void audiosync_cuda_dropin_stats(uint64_t* calls, uint64_t* h2d_bytes, uint64_t*
     if (calls) *calls = g_dropin_calls.load();
     if (h2d_bytes) *h2d_bytes = g_dropin_h2d_bytes.load();
     if (resident_hits) *resident_hits = g_dropin_resident_hits.load();
+}
+
+int audiosync_cuda_dropin_max_inflight(int reset) {
+    return reset ? g_dropin_inflight_max.exchange(0) : g_dropin_inflight_max.load();
 }
 
 int audiosync_cuda_create(audiosync_cuda_ctx** out, const int* devices, int n_devices) {
@@ -1083,6 +1088,9 @@ struct SlotLease {
                     s->busy = true;
                     ctx->slot_next = (ctx->slot_next + k + 1) % n;
                     slot = s;
+                    const int now = g_dropin_inflight.fetch_add(1) + 1;
+                    int seen = g_dropin_inflight_max.load();
+                    while (now > seen && !g_dropin_inflight_max.compare_exchange_weak(seen, now)) {}
                     return;
                 }
             }
@@ -1090,6 +1098,7 @@ struct SlotLease {
         }
     }
     ~SlotLease() {
+        g_dropin_inflight.fetch_sub(1);
         { std::lock_guard<std::mutex> lk(ctx->slot_mu); slot->busy = false; }
         ctx->slot_cv.notify_one();
     }

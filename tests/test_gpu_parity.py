@@ -822,9 +822,11 @@ def test_concurrent_callers(ac, capi):
         for k in range(3):
             out[t][k] = ac.cross_correlation(*pairs[(t + k) % 4])
 
+    ac.dropin_max_inflight(reset=True)
     th = [threading.Thread(target=work, args=(t,)) for t in range(8)]
     [t.start() for t in th]
     [t.join() for t in th]
+    assert ac.dropin_max_inflight() >= 2            # callers overlapped on the GPU, no global lock
     for t in range(8):
         for k in range(3):
             i = (t + k) % 4
