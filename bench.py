@@ -564,44 +564,58 @@ def main():
     value = world * n * args.steps / (ms * 1e-3)
 
     # ---- end to end: host-facing C-ABI batch call on HOST buffers -----------------------------
-    # headline: pinned doubles, the dtype the reference ABI's callers hold (f64le from ffmpeg);
-    # variants: fp32 pinned (half the bytes) and pageable doubles (staged through the library's
-    # pinned ring).  Uploads and the result download are inside the timed region.
+    # headline: pinned doubles, the dtype the reference ABI's callers hold (f64le from ffmpeg), in
+    # the library's default configuration -- LOSSLESS host narrowing: pairs whose doubles are exact
+    # images of floats (decoded audio always is; so is the seeded generator's) are converted to fp32
+    # by the library's copy threads while others go up as doubles on the copy engine, both at once;
+    # every result bit equals the un-narrowed call's (tests/test_gpu_parity.py).  Variants: the same
+    # with narrowing off (the doubles cross the link as they are), fp32 pinned, pageable doubles.
+    # Uploads, the host-side conversion and the result download are inside the timed region.
     e2e = None
     e2e_variants = {}
     if not args.no_e2e:
-        def e2e_leg(tdt, acdt, pinned, ne, reps):
+        def e2e_leg(tdt, acdt, pinned, ne, reps, narrow=ac.NARROW_LOSSLESS):
             esz = 4 if acdt == ac.F32 else 8
             h_src = torch.empty(ne * 2 * L, dtype=tdt, pin_memory=pinned)
             h_smp = torch.empty(ne * L, dtype=tdt, pin_memory=pinned)
             h_src.copy_(d_src[: ne * 2 * L]); h_smp.copy_(d_smp[: ne * L])     # exact in both dtypes
             torch.cuda.synchronize(dev)
+            ctx.set_host_narrowing(narrow)
             out = None
             for _ in range(2):
                 out = ctx.xcorr_batch_ptr(h_src.data_ptr(), h_smp.data_ptr(), ne, L, acdt, ac.HOST)
             barrier()
+            ctx.host_feed_stats(reset=True)
             t0 = time.perf_counter()
             for _ in range(reps):
                 out = ctx.xcorr_batch_ptr(h_src.data_ptr(), h_smp.data_ptr(), ne, L, acdt, ac.HOST)
             torch.cuda.synchronize(dev)
             dt = time.perf_counter() - t0
+            fed_direct, fed_narrowed = ctx.host_feed_stats(reset=True)
+            ctx.set_host_narrowing(ac.NARROW_LOSSLESS)
             assert all(int(out["lags"][i]) == int(res["lag"][i]) for i in range(ne))
             tt = torch.tensor([dt], dtype=torch.float64, device=dev)
             if world > 1:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             del h_src, h_smp
+            link_bytes = (ne * reps * 3 * L * esz) if esz == 4 else (fed_direct * 3 * L * 8 + fed_narrowed * 3 * L * 4)
             return {"value": world * ne * reps / float(tt[0]), "unit": UNIT,
                     "h2d_bytes_per_step": ne * 3 * L * esz, "d2h_bytes_per_step": ne * ac.RESULT_DTYPE.itemsize,
                     "pairs_per_step": ne, "host_dtype": "f32" if esz == 4 else "f64",
                     "host_memory": "pinned" if pinned else "pageable", "host_binding": numa,
-                    "h2d_gbs_per_gpu": ne * 3 * L * esz * reps / float(tt[0]) / 1e9,
-                    "bound": "pcie (host->device copy of %.2f MB per pair)" % (3 * L * esz / 1e6),
+                    "host_narrowing": (None if esz == 4 else ["off", "lossless", "always"][narrow]),
+                    "pairs_fed_as_doubles": fed_direct, "pairs_narrowed_on_host": fed_narrowed,
+                    "host_gbs_per_gpu": ne * 3 * L * esz * reps / float(tt[0]) / 1e9,
+                    "link_gbs_per_gpu": link_bytes / float(tt[0]) / 1e9,
+                    "bound": "pcie + host copy threads (%.2f MB of host input per pair)" % (3 * L * esz / 1e6),
                     "api": "audiosync_cuda_xcorr_batch(memspace=HOST)"}
         ne = min(args.e2e_pairs, n)
         reps = max(2, args.steps)
         e2e = e2e_leg(torch.float64, ac.F64, True, max(1, ne // 2), reps)
+        e2e_variants["f64_pinned_narrowing_off"] = e2e_leg(torch.float64, ac.F64, True, max(1, ne // 2), reps, narrow=ac.NARROW_OFF)
         e2e_variants["f32_pinned"] = e2e_leg(torch.float32, ac.F32, True, ne, reps)
         e2e_variants["f64_pageable"] = e2e_leg(torch.float64, ac.F64, False, max(1, ne // 4), 2)
+        e2e_variants["f64_pageable_narrowing_off"] = e2e_leg(torch.float64, ac.F64, False, max(1, ne // 4), 2, narrow=ac.NARROW_OFF)
 
     # ---- config 3: single-pair latency at this length (rank 0 only) --------------------------
     latency = None

@@ -240,6 +240,26 @@ int audiosync_cuda_synchronize(audiosync_cuda_ctx *ctx, int device);
 /* Tuning / test knobs (default behaviour matches the reference's). */
 int  audiosync_cuda_set_path(audiosync_cuda_ctx *ctx, int path);          /* AUTO / FFT / DIRECT */
 int  audiosync_cuda_set_wave_pairs(audiosync_cuda_ctx *ctx, int pairs);   /* pairs per kernel wave, 0 = auto */
+/* Host narrowing for the HOST-memspace batch calls with dtype F64.  The link, not the GPU, bounds
+ * host-fed batches (34.56 MB per 1.44M-frame pair at ~55 GB/s), and the transform is fp32 anyway:
+ * the library can convert the doubles to fp32 ON THE HOST while it stages them (copy threads,
+ * AUDIOSYNC_CUDA_COPY_THREADS), so that half the bytes cross PCIe.
+ *   LOSSLESS (default): only where the conversion is exact -- every double of the chunk the image
+ *     of its float, which audio decoded from 16/24-bit PCM or float samples always is.  The Pearson
+ *     step then widens the floats back and runs its fp64 arithmetic, so every result bit equals the
+ *     un-narrowed call's; the first inexact value (NaN included) ends narrowing for the rest of the
+ *     call and that chunk is uploaded as doubles.  Page-locked inputs are fed both ways at once:
+ *     whole pairs by the copy engine straight from the caller's memory while the copy threads narrow
+ *     others, each taking the next pair when it is free.
+ *   ALWAYS: every chunk, exact or not; the call then answers for the fp32 batch of the rounded
+ *     values (coefficient ~1e-7 relative from the f64 call's; identical windows still give 1.0).
+ *   OFF: the doubles cross the link as they are.
+ * Env AUDIOSYNC_CUDA_HOST_NARROWING=0/1/2 sets the mode of new contexts.  Ignored in precise mode. */
+enum { AUDIOSYNC_CUDA_NARROW_OFF = 0, AUDIOSYNC_CUDA_NARROW_LOSSLESS = 1, AUDIOSYNC_CUDA_NARROW_ALWAYS = 2 };
+int  audiosync_cuda_set_host_narrowing(audiosync_cuda_ctx *ctx, int mode);
+/* The host-side conversion itself (copy threads, SIMD): dst[i] = (float)src[i], round to nearest
+ * even; returns 1 when every value survived unchanged, 0 otherwise.  Needs no GPU. */
+int  audiosync_cuda_host_narrow(float *dst, const double *src, size_t n);
 /* fp64-ARITHMETIC validation mode: every transform runs on the double-precision instantiation
  * of the runtime-radix kernels (the reference computes in double complex throughout,
  * src/cross_correlation.c:187-239) and the argmax on full double keys -- several times slower
@@ -255,6 +275,9 @@ int audiosync_cuda_describe_plan(audiosync_cuda_ctx *ctx, size_t sample_len,
 
 /* Launch accounting: number of kernels this context has launched so far. */
 uint64_t audiosync_cuda_launch_count(const audiosync_cuda_ctx *ctx);
+/* Host-fed F64 batches since the context was created (or the last call with reset != 0): pairs that
+ * crossed the link as doubles -> out[0], pairs narrowed to fp32 on the host -> out[1]. */
+int audiosync_cuda_host_feed_stats(audiosync_cuda_ctx *ctx, uint64_t out[2], int reset);
 
 /* Per-kernel device timing.  When enabled every launch is bracketed by CUDA
  * events on its own stream; audiosync_cuda_profile_read() synchronises and

@@ -23,13 +23,14 @@ __all__ = [
     "AudiosyncCudaError", "lib", "lib_path", "cross_correlation", "pearson_coefficient",
     "interval_loop", "Context", "RESULT_DTYPE", "MIN_CONFIDENCE", "SAMPLE_RATE",
     "INTERV_SAMPLE", "frames_to_ms", "F32", "F64", "HOST", "DEVICE",
-    "PATH_AUTO", "PATH_FFT", "PATH_DIRECT", "EXPORTED_SYMBOLS", "shard_pairs", "gather_results",
+    "PATH_AUTO", "PATH_FFT", "PATH_DIRECT", "NARROW_OFF", "NARROW_LOSSLESS", "NARROW_ALWAYS", "EXPORTED_SYMBOLS", "shard_pairs", "gather_results", "host_narrow",
     "cross_correlation_ptr", "RealBuffer", "set_residency", "dropin_stats", "dropin_max_inflight", "SessionPool",
 ]
 
 F32, F64 = 0, 1
 HOST, DEVICE = 0, 1
 PATH_AUTO, PATH_FFT, PATH_DIRECT = 0, 1, 2
+NARROW_OFF, NARROW_LOSSLESS, NARROW_ALWAYS = 0, 1, 2
 
 MIN_CONFIDENCE = 0.95                                             # audiosync.h:24
 SAMPLE_RATE = 48000                                               # audiosync.h:14
@@ -49,11 +50,12 @@ EXPORTED_SYMBOLS = [
     "audiosync_cuda_xcorr_batch", "audiosync_cuda_xcorr_batch_results", "audiosync_cuda_xcorr_batch_device",
     "audiosync_cuda_synth_pairs", "audiosync_cuda_synchronize",
     "audiosync_cuda_set_path", "audiosync_cuda_set_wave_pairs", "audiosync_cuda_set_debug", "audiosync_cuda_set_precise",
+    "audiosync_cuda_set_host_narrowing", "audiosync_cuda_host_narrow",
     "audiosync_cuda_set_residency", "audiosync_cuda_dropin_stats", "audiosync_cuda_dropin_max_inflight",
     "audiosync_cuda_pool_create", "audiosync_cuda_pool_destroy", "audiosync_cuda_pool_reset",
     "audiosync_cuda_pool_append", "audiosync_cuda_pool_append_async", "audiosync_cuda_pool_flush",
     "audiosync_cuda_pool_fill", "audiosync_cuda_pool_run",
-    "audiosync_cuda_describe_plan", "audiosync_cuda_launch_count",
+    "audiosync_cuda_describe_plan", "audiosync_cuda_launch_count", "audiosync_cuda_host_feed_stats",
     "audiosync_cuda_profile_enable", "audiosync_cuda_profile_reset",
     "audiosync_cuda_profile_read", "audiosync_cuda_last_error", "audiosync_cuda_version",
 ]
@@ -113,6 +115,10 @@ def lib() -> C.CDLL:
     L.audiosync_cuda_synchronize.argtypes = [vp, i32]
     L.audiosync_cuda_set_path.restype = i32
     L.audiosync_cuda_set_path.argtypes = [vp, i32]
+    L.audiosync_cuda_set_host_narrowing.restype = i32
+    L.audiosync_cuda_set_host_narrowing.argtypes = [vp, i32]
+    L.audiosync_cuda_host_narrow.restype = i32
+    L.audiosync_cuda_host_narrow.argtypes = [vp, vp, C.c_size_t]
     L.audiosync_cuda_set_precise.restype = i32
     L.audiosync_cuda_set_precise.argtypes = [vp, i32]
     L.audiosync_cuda_set_wave_pairs.restype = i32
@@ -143,6 +149,8 @@ def lib() -> C.CDLL:
     L.audiosync_cuda_set_debug.argtypes = [i32]
     L.audiosync_cuda_describe_plan.restype = i32
     L.audiosync_cuda_describe_plan.argtypes = [vp, sz, C.c_char_p, sz]
+    L.audiosync_cuda_host_feed_stats.restype = i32
+    L.audiosync_cuda_host_feed_stats.argtypes = [vp, C.POINTER(u64), i32]
     L.audiosync_cuda_launch_count.restype = u64
     L.audiosync_cuda_launch_count.argtypes = [vp]
     L.audiosync_cuda_profile_enable.restype = i32
@@ -287,6 +295,14 @@ class RealBuffer:
         self.free()
 
 
+def host_narrow(x: np.ndarray):
+    """(float32 copy of x, exact) through the library's host-side conversion (no GPU needed)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty(x.shape, np.float32)
+    exact = lib().audiosync_cuda_host_narrow(out.ctypes.data, x.ctypes.data, x.size)
+    return out, bool(exact)
+
+
 def set_residency(on: bool) -> None:
     """Interval-schedule residency of the drop-in ``cross_correlation`` (opt-in, default off)."""
     lib().audiosync_cuda_set_residency(1 if on else 0)
@@ -399,6 +415,11 @@ class Context:
         """fp64 arithmetic in the transforms (validation mode; see include/audiosync_cuda.h)."""
         self._check(lib().audiosync_cuda_set_precise(self._h, 1 if on else 0), "set_precise")
 
+    def set_host_narrowing(self, mode: int):
+        """f64 HOST batches converted to fp32 on the host while staged (half the PCIe bytes):
+        NARROW_OFF, NARROW_LOSSLESS (default: only where exact, results bit-identical) or NARROW_ALWAYS."""
+        self._check(lib().audiosync_cuda_set_host_narrowing(self._h, int(mode)), "set_host_narrowing")
+
     def set_wave_pairs(self, pairs: int):
         self._check(lib().audiosync_cuda_set_wave_pairs(self._h, pairs), "set_wave_pairs")
 
@@ -408,6 +429,12 @@ class Context:
         if n < 0:
             raise AudiosyncCudaError("describe_plan failed: " + last_error())
         return buf.value.decode()
+
+    def host_feed_stats(self, reset: bool = False):
+        """(pairs that crossed the link as doubles, pairs narrowed to fp32 on the host) of F64 host batches."""
+        out = (C.c_uint64 * 2)()
+        self._check(lib().audiosync_cuda_host_feed_stats(self._h, out, 1 if reset else 0), "host_feed_stats")
+        return int(out[0]), int(out[1])
 
     def launch_count(self) -> int:
         return int(lib().audiosync_cuda_launch_count(self._h))

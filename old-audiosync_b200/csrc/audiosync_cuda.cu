@@ -270,7 +270,8 @@ static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, WorkSet& work,
     ASC_CUDA_OK(cudaSetDevice(d.device));
     FftPlan* plan = get_plan(ctx, d, L);
     if (!plan) return -1;
-    const size_t esz = dtype == AUDIOSYNC_CUDA_F32 ? 4 : 8;
+    const size_t esz = dtype == AUDIOSYNC_CUDA_F64 ? 8 : 4;
+    const int in_dtype = dtype == AUDIOSYNC_CUDA_F64 ? AUDIOSYNC_CUDA_F64 : AUDIOSYNC_CUDA_F32;   // what the transform loads
     int wave = ctx->wave_pairs > 0 ? ctx->wave_pairs : default_wave_pairs(plan, n_pairs);
     wave = (int)std::min<size_t>((size_t)wave, n_pairs);
     wave = std::min(wave, 65535);
@@ -290,18 +291,24 @@ static int enqueue_batch(audiosync_cuda_ctx* ctx, DeviceState& d, WorkSet& work,
         const int pairs = (int)std::min<size_t>((size_t)wave, n_pairs - p0);
         const char* s = static_cast<const char*>(src) + p0 * (size_t)src_pitch * esz;
         const char* m = static_cast<const char*>(smp) + p0 * (size_t)smp_pitch * esz;
-        if (plan->run_wave(ctx, d, s, m, dtype, src_pitch, smp_pitch, work.ws.p, peaks, pairs, st) != 0) return -1;
+        if (plan->run_wave(ctx, d, s, m, in_dtype, src_pitch, smp_pitch, work.ws.p, peaks, pairs, st) != 0) return -1;
         const dim3 grid(n_chunks, pairs);
         int rc;
         if (dtype == AUDIOSYNC_CUDA_F32) {
             rc = launch(ctx, d, KC_PEARSON, st, [&] {
-                launch_stage(pearson_kernel<float>, grid, dim3(PEARSON_THREADS), 0, st,
+                launch_stage(pearson_kernel<float, false>, grid, dim3(PEARSON_THREADS), 0, st,
+                    reinterpret_cast<const float*>(s), reinterpret_cast<const float*>(m), src_pitch, smp_pitch, L,
+                    (const PairPeak*)peaks, 0LL, plan->peak_scale, partials, tickets, n_chunks, d_results + p0);
+            });
+        } else if (dtype == ASC_DTYPE_F32_EXACT) {
+            rc = launch(ctx, d, KC_PEARSON, st, [&] {
+                launch_stage(pearson_kernel<float, true>, grid, dim3(PEARSON_THREADS), 0, st,
                     reinterpret_cast<const float*>(s), reinterpret_cast<const float*>(m), src_pitch, smp_pitch, L,
                     (const PairPeak*)peaks, 0LL, plan->peak_scale, partials, tickets, n_chunks, d_results + p0);
             });
         } else {
             rc = launch(ctx, d, KC_PEARSON, st, [&] {
-                launch_stage(pearson_kernel<double>, grid, dim3(PEARSON_THREADS), 0, st,
+                launch_stage(pearson_kernel<double, true>, grid, dim3(PEARSON_THREADS), 0, st,
                     reinterpret_cast<const double*>(s), reinterpret_cast<const double*>(m), src_pitch, smp_pitch, L,
                     (const PairPeak*)peaks, 0LL, plan->peak_scale, partials, tickets, n_chunks, d_results + p0);
             });
@@ -338,6 +345,8 @@ static void destroy_device_state(DeviceState& d) {
     d.work.release(); d.results.release();
     for (int i = 0; i < 2; i++) {
         d.in_src[i].release(); d.in_smp[i].release();
+        d.in_src32[i].release(); d.in_smp32[i].release();
+        if (d.ev_up32[i]) cudaEventDestroy(d.ev_up32[i]);
         if (d.ev_up[i]) cudaEventDestroy(d.ev_up[i]);
         if (d.ev_done[i]) cudaEventDestroy(d.ev_done[i]);
     }
@@ -347,61 +356,98 @@ static void destroy_device_state(DeviceState& d) {
     for (auto e : d.event_pool) cudaEventDestroy(e);
     if (d.stream) cudaStreamDestroy(d.stream);
     if (d.copy_stream) cudaStreamDestroy(d.copy_stream);
+    if (d.narrow_stream) cudaStreamDestroy(d.narrow_stream);
+    for (int k = 0; k < DeviceState::DIRECT_DEPTH; k++)
+        if (d.direct_ev[k]) cudaEventDestroy(d.direct_ev[k]);
     d.device = -1;
 }
 
+bool narrow_f64_to_f32(float* dst, const double* src, size_t n, bool stream);      // host_simd.cpp
+
 // A few persistent helper threads that split one large host memcpy (pageable input -> pinned
-// bounce buffer) into slices: a single core copies ~10 GB/s, PCIe takes 55.  One copy at a time
-// (callers would only fight over the same memory bandwidth); never torn down.
+// bounce buffer) or one double -> float narrowing pass into slices: a single core copies ~10 GB/s,
+// PCIe takes 55.  One pass at a time (callers would only fight over the same memory bandwidth);
+// never torn down.
 class CopyPool {
-    struct Slice { char* dst; const char* src; size_t n; };
+    struct Slice { char* dst; const char* src; size_t n; bool narrow; };   // n: bytes (copy) or elements (narrow)
+    void run_slice(const Slice& s) {
+        if (!s.narrow) { memcpy(s.dst, s.src, s.n); return; }
+        if (!narrow_f64_to_f32(reinterpret_cast<float*>(s.dst), reinterpret_cast<const double*>(s.src), s.n, nt_stores_))
+            inexact_.store(true, std::memory_order_relaxed);
+    }
     std::vector<std::thread> workers_;
     std::mutex m_, run_mu_;
     std::condition_variable cv_, done_cv_;
     std::vector<Slice> slices_;
     size_t next_ = 0, pending_ = 0;
+    std::atomic<bool> inexact_{false};
+    bool nt_stores_ = true;
+    size_t copy_parts_ = 8;
     void loop() {
         std::unique_lock<std::mutex> lk(m_);
         for (;;) {
             cv_.wait(lk, [&] { return next_ < slices_.size(); });
             const Slice s = slices_[next_++];
             lk.unlock();
-            memcpy(s.dst, s.src, s.n);
+            run_slice(s);
             lk.lock();
             if (--pending_ == 0) done_cv_.notify_all();
         }
     }
+    // n units of `in_unit` source bytes each become `out_unit` destination bytes (copy: 1 -> 1 with
+    // n bytes; narrow: 8 -> 4 with n doubles), split over the workers and the calling thread
+    void run(void* dst, const void* src, size_t n, size_t in_unit, size_t out_unit, bool narrow, size_t parts) {
+        parts = std::max<size_t>(1, std::min(parts, threads()));
+        if (n * in_unit < ((size_t)1 << 20) || parts == 1) {
+            run_slice(Slice{static_cast<char*>(dst), static_cast<const char*>(src), n, narrow});
+            return;
+        }
+        const size_t per = ((n + parts - 1) / parts + 63) & ~(size_t)63;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            slices_.clear(); next_ = 0; pending_ = 0;
+            for (size_t o = per; o < n; o += per) {       // slice 0 is the caller's own
+                slices_.push_back(Slice{static_cast<char*>(dst) + o * out_unit, static_cast<const char*>(src) + o * in_unit,
+                                        std::min(per, n - o), narrow});
+                pending_++;
+            }
+        }
+        cv_.notify_all();
+        run_slice(Slice{static_cast<char*>(dst), static_cast<const char*>(src), std::min(per, n), narrow});
+        std::unique_lock<std::mutex> lk(m_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+    }
 public:
-    explicit CopyPool(unsigned n) {
+    CopyPool(unsigned n, unsigned copy_parts, bool nt) : nt_stores_(nt), copy_parts_(copy_parts) {
         for (unsigned i = 0; i < n; i++) workers_.emplace_back([this] { loop(); });
         for (auto& t : workers_) t.detach();
     }
     size_t threads() const { return workers_.size() + 1; }
     void copy(void* dst, const void* src, size_t bytes) {
-        const size_t parts = threads();
-        if (bytes < ((size_t)1 << 20) || parts == 1) { memcpy(dst, src, bytes); return; }
-        std::lock_guard<std::mutex> run(run_mu_);
-        const size_t per = ((bytes + parts - 1) / parts + 63) & ~(size_t)63;
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            slices_.clear(); next_ = 0; pending_ = 0;
-            for (size_t o = per; o < bytes; o += per) {       // slice 0 is the caller's own
-                slices_.push_back(Slice{static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, std::min(per, bytes - o)});
-                pending_++;
-            }
-        }
-        cv_.notify_all();
-        memcpy(dst, src, std::min(per, bytes));
-        std::unique_lock<std::mutex> lk(m_);
-        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        std::lock_guard<std::mutex> run_lk(run_mu_);
+        run(dst, src, bytes, 1, 1, false, copy_parts_);
+    }
+    // dst[i] = (float)src[i]; true when every conversion was exact
+    bool narrow(float* dst, const double* src, size_t n) {
+        std::lock_guard<std::mutex> run_lk(run_mu_);
+        inexact_.store(false, std::memory_order_relaxed);
+        run(dst, src, n, sizeof(double), sizeof(float), true, threads());
+        return !inexact_.load(std::memory_order_relaxed);
     }
 };
+// Plain copies stop scaling at ~8 threads (measured on the 16-core B200 host: 4 / 8 / 12 threads
+// stage pageable doubles at 38 / 52 / 50 GB/s); narrowing keeps gaining up to 12 (45 / 68 / 77 GB/s
+// of doubles read).  Default: three quarters of this process's share of the cores, at most 12.
 static CopyPool& copy_pool() {
     static CopyPool* pool = [] {
-        unsigned hw = std::thread::hardware_concurrency();
+        unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        int gpus = 1;
+        if (cudaGetDeviceCount(&gpus) != cudaSuccess || gpus < 1) { cudaGetLastError(); gpus = 1; }
         const char* e = getenv("AUDIOSYNC_CUDA_COPY_THREADS");
-        unsigned n = e ? (unsigned)std::max(1, atoi(e)) : std::min(4u, std::max(1u, hw / 2));
-        return new CopyPool(n - 1);
+        const unsigned share = std::max(1u, hw * 3 / 4 / (unsigned)gpus);
+        unsigned n = e ? (unsigned)std::max(1, atoi(e)) : std::min(12u, share);
+        const char* nt = getenv("AUDIOSYNC_CUDA_NT_STORES");
+        return new CopyPool(n - 1, std::min(8u, n), !(nt && atoi(nt) == 0));
     }();
     return *pool;
 }
@@ -436,25 +482,83 @@ static int upload_from_host(void* dst, const void* src, size_t bytes, cudaStream
     return 0;
 }
 
+// Host doubles -> device floats: converted on the host into the pinned ring (copy threads), so that
+// half the bytes cross PCIe.  Any host memory.  *exact is cleared when a value did not survive the
+// conversion unchanged; with stop_on_inexact the upload ends at that piece (the caller redoes it).
+static int upload_narrowed(float* dst, const double* src, size_t n, cudaStream_t st, StageRing& ring,
+                           bool* exact, bool stop_on_inexact) {
+    const size_t piece = StageRing::PIECE / sizeof(float);        // elements per ring buffer
+    for (size_t o = 0; o < n; o += piece) {
+        const size_t m = std::min(piece, n - o);
+        const int i = ring.next;
+        ring.next = (ring.next + 1) % StageRing::N;
+        if (ring.buf[i].ensure(StageRing::PIECE) != 0) return -1;
+        if (!ring.ev[i]) ASC_CUDA_OK(cudaEventCreateWithFlags(&ring.ev[i], cudaEventDisableTiming));
+        if (ring.pending[i]) ASC_CUDA_OK(cudaEventSynchronize(ring.ev[i]));
+        ring.pending[i] = false;
+        if (!copy_pool().narrow(static_cast<float*>(ring.buf[i].p), src + o, m)) {
+            *exact = false;
+            if (stop_on_inexact) return 0;
+        }
+        ASC_CUDA_OK(cudaMemcpyAsync(dst + o, ring.buf[i].p, m * sizeof(float), cudaMemcpyHostToDevice, st));
+        ASC_CUDA_OK(cudaEventRecord(ring.ev[i], st));
+        ring.pending[i] = true;
+    }
+    return 0;
+}
+
+// Direct (un-narrowed) uploads of whole pairs that run beside the narrowing threads: how many
+// are still in flight.
+static int direct_in_flight(DeviceState& d) {
+    int n = 0;
+    for (int k = 0; k < DeviceState::DIRECT_DEPTH; k++) {
+        if (!d.direct_pending[k]) continue;
+        if (cudaEventQuery(d.direct_ev[k]) == cudaSuccess) d.direct_pending[k] = false;
+        else { cudaGetLastError(); n++; }
+    }
+    return n;
+}
+
 // Host-memory pairs [p0, p1) on one device: chunked, double buffered.
+//
+// F64 batches with host narrowing on (see include/audiosync_cuda.h): a chunk's pairs are taken from
+// both ends.  From the back, the copy threads convert a pair to fp32 into the pinned ring and its
+// half-size pieces go up on `narrow_stream`; from the front -- page-locked inputs only -- the copy
+// engine takes whole pairs of doubles straight from the caller's memory on `copy_stream`, at most
+// DIRECT_DEPTH in flight, so that link time the conversion leaves idle is used and neither side
+// waits for the other.  The two sub-batches [0, k) (doubles) and [k, n) (exact fp32 images) are
+// enqueued separately.  solo: this call drives a single device (several devices of one context
+// share the copy threads; each then feeds its device with direct uploads only).
 static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* sources,
                           const char* samples, size_t p0, size_t p1, long long L, int dtype,
-                          audiosync_cuda_result* out) {
+                          audiosync_cuda_result* out, bool solo) {
     if (p1 <= p0) return 0;
     std::lock_guard<std::mutex> dlk(d.mu);
     ASC_CUDA_OK(cudaSetDevice(d.device));
     const size_t esz = dtype == AUDIOSYNC_CUDA_F32 ? 4 : 8;
-    const size_t src_bytes = (size_t)(2 * L) * esz, smp_bytes = (size_t)L * esz;
-    // chunk: about 192 MB of input per buffer, at least one pair
-    size_t chunk = std::max<size_t>(1, (192u << 20) / (src_bytes + smp_bytes));
+    const size_t src_n = (size_t)(2 * L), smp_n = (size_t)L;
+    const size_t src_bytes = src_n * esz, smp_bytes = smp_n * esz;
+    const bool pageable = host_pointer_is_pageable(sources) || host_pointer_is_pageable(samples);
+    int mode = (dtype == AUDIOSYNC_CUDA_F64 && !ctx->precise) ? ctx->narrow_host : AUDIOSYNC_CUDA_NARROW_OFF;
+    if (mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS && !solo && !pageable) mode = AUDIOSYNC_CUDA_NARROW_OFF;
+    const bool hybrid = mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS && !pageable;
+    // chunk: about 192 MB of input per buffer (twice that when pairs are fed both ways), at least one pair
+    size_t chunk = std::max<size_t>(1, ((size_t)(hybrid ? 384u : 192u) << 20) / (src_bytes + smp_bytes));
     chunk = std::min(chunk, p1 - p0);
     for (int b = 0; b < 2; b++) {
         if (d.in_src[b].ensure(src_bytes * chunk) != 0 || d.in_smp[b].ensure(smp_bytes * chunk) != 0) return -1;
+        if (mode != AUDIOSYNC_CUDA_NARROW_OFF &&
+            (d.in_src32[b].ensure(sizeof(float) * src_n * chunk) != 0 || d.in_smp32[b].ensure(sizeof(float) * smp_n * chunk) != 0))
+            return -1;
         if (!d.ev_up[b]) ASC_CUDA_OK(cudaEventCreateWithFlags(&d.ev_up[b], cudaEventDisableTiming));
+        if (!d.ev_up32[b]) ASC_CUDA_OK(cudaEventCreateWithFlags(&d.ev_up32[b], cudaEventDisableTiming));
         if (!d.ev_done[b]) ASC_CUDA_OK(cudaEventCreateWithFlags(&d.ev_done[b], cudaEventDisableTiming));
     }
+    for (int k = 0; k < DeviceState::DIRECT_DEPTH; k++)
+        if (!d.direct_ev[k]) ASC_CUDA_OK(cudaEventCreateWithFlags(&d.direct_ev[k], cudaEventDisableTiming));
+    if (mode != AUDIOSYNC_CUDA_NARROW_OFF && !d.narrow_stream)
+        ASC_CUDA_OK(cudaStreamCreateWithFlags(&d.narrow_stream, cudaStreamNonBlocking));
     const size_t total = p1 - p0;
-    const bool pageable = host_pointer_is_pageable(sources) || host_pointer_is_pageable(samples);
     if (d.results.ensure(sizeof(audiosync_cuda_result) * total) != 0) return -1;
     if (d.h_results.ensure(sizeof(audiosync_cuda_result) * total) != 0) return -1;
     audiosync_cuda_result* d_res = static_cast<audiosync_cuda_result*>(d.results.p);
@@ -462,15 +566,73 @@ static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* s
     for (size_t c0 = 0; c0 < total; c0 += chunk, it++) {
         const size_t n = std::min(chunk, total - c0);
         const int b = it & 1;
-        if (it >= 2) ASC_CUDA_OK(cudaStreamWaitEvent(d.copy_stream, d.ev_done[b], 0));
-        if (upload_from_host(d.in_src[b].p, sources + (p0 + c0) * src_bytes, src_bytes * n, d.copy_stream, d.stage, pageable) != 0 ||
-            upload_from_host(d.in_smp[b].p, samples + (p0 + c0) * smp_bytes, smp_bytes * n, d.copy_stream, d.stage, pageable) != 0)
-            return -1;
-        ASC_CUDA_OK(cudaEventRecord(d.ev_up[b], d.copy_stream));
-        ASC_CUDA_OK(cudaStreamWaitEvent(d.stream, d.ev_up[b], 0));
-        if (enqueue_batch(ctx, d, d.work, d.in_src[b].p, d.in_smp[b].p, n, L, dtype, d_res + c0, d.stream) != 0)
-            return -1;
+        const char* hs = sources + (p0 + c0) * src_bytes;
+        const char* hm = samples + (p0 + c0) * smp_bytes;
+        if (it >= 2) {
+            ASC_CUDA_OK(cudaStreamWaitEvent(d.copy_stream, d.ev_done[b], 0));
+            if (mode != AUDIOSYNC_CUDA_NARROW_OFF) ASC_CUDA_OK(cudaStreamWaitEvent(d.narrow_stream, d.ev_done[b], 0));
+        }
+        size_t lo = 0, hi = n;          // pairs [0, lo) go up as they are, pairs [hi, n) narrowed
+        if (mode == AUDIOSYNC_CUDA_NARROW_OFF) {
+            if (upload_from_host(d.in_src[b].p, hs, src_bytes * n, d.copy_stream, d.stage, pageable) != 0 ||
+                upload_from_host(d.in_smp[b].p, hm, smp_bytes * n, d.copy_stream, d.stage, pageable) != 0)
+                return -1;
+            lo = n;
+        }
+        while (lo < hi) {
+            if (mode == AUDIOSYNC_CUDA_NARROW_OFF || (hybrid && direct_in_flight(d) < DeviceState::DIRECT_DEPTH)) {
+                // the next pair from the front, as doubles (after narrowing was given up: all that is left)
+                if (mode != AUDIOSYNC_CUDA_NARROW_OFF || !pageable) {
+                    int k = 0;
+                    while (k < DeviceState::DIRECT_DEPTH - 1 && d.direct_pending[k]) k++;
+                    if (d.direct_pending[k]) ASC_CUDA_OK(cudaEventSynchronize(d.direct_ev[k]));
+                    ASC_CUDA_OK(cudaMemcpyAsync(static_cast<char*>(d.in_src[b].p) + lo * src_bytes, hs + lo * src_bytes, src_bytes,
+                                                cudaMemcpyHostToDevice, d.copy_stream));
+                    ASC_CUDA_OK(cudaMemcpyAsync(static_cast<char*>(d.in_smp[b].p) + lo * smp_bytes, hm + lo * smp_bytes, smp_bytes,
+                                                cudaMemcpyHostToDevice, d.copy_stream));
+                    ASC_CUDA_OK(cudaEventRecord(d.direct_ev[k], d.copy_stream));
+                    d.direct_pending[k] = true;
+                    lo++;
+                } else {                // pageable inputs whose narrowing was given up: the rest through the ring
+                    if (upload_from_host(static_cast<char*>(d.in_src[b].p) + lo * src_bytes, hs + lo * src_bytes, src_bytes * (hi - lo),
+                                         d.copy_stream, d.stage, true) != 0 ||
+                        upload_from_host(static_cast<char*>(d.in_smp[b].p) + lo * smp_bytes, hm + lo * smp_bytes, smp_bytes * (hi - lo),
+                                         d.copy_stream, d.stage, true) != 0)
+                        return -1;
+                    lo = hi;
+                }
+                continue;
+            }
+            // the next pair from the back, narrowed
+            const size_t j = hi - 1;
+            bool exact = true;
+            const bool stop = mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS;
+            if (upload_narrowed(static_cast<float*>(d.in_src32[b].p) + j * src_n, reinterpret_cast<const double*>(hs) + j * src_n, src_n,
+                                d.narrow_stream, d.stage, &exact, stop) != 0)
+                return -1;
+            if ((exact || !stop) &&
+                upload_narrowed(static_cast<float*>(d.in_smp32[b].p) + j * smp_n, reinterpret_cast<const double*>(hm) + j * smp_n, smp_n,
+                                d.narrow_stream, d.stage, &exact, stop) != 0)
+                return -1;
+            if (!exact && stop) mode = AUDIOSYNC_CUDA_NARROW_OFF;     // this pair and all later ones go up as doubles
+            else hi = j;
+        }
+        // pairs [0, lo): doubles (or the caller's fp32); pairs [hi, n): narrowed
+        if (lo > 0) {
+            ASC_CUDA_OK(cudaEventRecord(d.ev_up[b], d.copy_stream));
+            ASC_CUDA_OK(cudaStreamWaitEvent(d.stream, d.ev_up[b], 0));
+            if (enqueue_batch(ctx, d, d.work, d.in_src[b].p, d.in_smp[b].p, lo, L, dtype, d_res + c0, d.stream) != 0) return -1;
+        }
+        if (hi < n) {
+            ASC_CUDA_OK(cudaEventRecord(d.ev_up32[b], d.narrow_stream));
+            ASC_CUDA_OK(cudaStreamWaitEvent(d.stream, d.ev_up32[b], 0));
+            const int dt = ctx->narrow_host == AUDIOSYNC_CUDA_NARROW_ALWAYS ? AUDIOSYNC_CUDA_F32 : ASC_DTYPE_F32_EXACT;
+            if (enqueue_batch(ctx, d, d.work, static_cast<float*>(d.in_src32[b].p) + hi * src_n,
+                              static_cast<float*>(d.in_smp32[b].p) + hi * smp_n, n - hi, L, dt, d_res + c0 + hi, d.stream) != 0)
+                return -1;
+        }
         ASC_CUDA_OK(cudaEventRecord(d.ev_done[b], d.stream));
+        if (dtype == AUDIOSYNC_CUDA_F64) { ctx->fed_direct += lo; ctx->fed_narrowed += n - hi; }
     }
     ASC_CUDA_OK(cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result) * total,
                                 cudaMemcpyDeviceToHost, d.stream));
@@ -601,6 +763,8 @@ int audiosync_cuda_create(audiosync_cuda_ctx** out, const int* devices, int n_de
     }
     const char* w = getenv("AUDIOSYNC_CUDA_WAVE_PAIRS");
     if (w) ctx->wave_pairs = atoi(w);
+    const char* nh = getenv("AUDIOSYNC_CUDA_HOST_NARROWING");
+    if (nh && atoi(nh) >= AUDIOSYNC_CUDA_NARROW_OFF && atoi(nh) <= AUDIOSYNC_CUDA_NARROW_ALWAYS) ctx->narrow_host = atoi(nh);
     *out = ctx;
     return 0;
 }
@@ -633,6 +797,18 @@ int audiosync_cuda_set_precise(audiosync_cuda_ctx* ctx, int on) {
     return 0;
 }
 
+int audiosync_cuda_set_host_narrowing(audiosync_cuda_ctx* ctx, int mode) {
+    if (!ctx || mode < AUDIOSYNC_CUDA_NARROW_OFF || mode > AUDIOSYNC_CUDA_NARROW_ALWAYS) return -1;
+    ctx->narrow_host = mode;
+    return 0;
+}
+
+int audiosync_cuda_host_narrow(float* dst, const double* src, size_t n) {
+    if (n == 0) return 1;
+    if (!dst || !src) return 0;
+    return copy_pool().narrow(dst, src, n) ? 1 : 0;
+}
+
 int audiosync_cuda_set_wave_pairs(audiosync_cuda_ctx* ctx, int pairs) {
     if (!ctx || pairs < 0) return -1;
     ctx->wave_pairs = pairs;
@@ -641,6 +817,13 @@ int audiosync_cuda_set_wave_pairs(audiosync_cuda_ctx* ctx, int pairs) {
 
 uint64_t audiosync_cuda_launch_count(const audiosync_cuda_ctx* ctx) {
     return ctx ? ctx->launches.load() : 0;
+}
+
+int audiosync_cuda_host_feed_stats(audiosync_cuda_ctx* ctx, uint64_t out[2], int reset) {
+    if (!ctx || !out) return -1;
+    out[0] = reset ? ctx->fed_direct.exchange(0) : ctx->fed_direct.load();
+    out[1] = reset ? ctx->fed_narrowed.exchange(0) : ctx->fed_narrowed.load();
+    return 0;
 }
 
 int audiosync_cuda_describe_plan(audiosync_cuda_ctx* ctx, size_t sample_len, char* buf, size_t buf_len) {
@@ -774,6 +957,7 @@ int audiosync_cuda_xcorr_batch_results(audiosync_cuda_ctx* ctx, const void* sour
         std::vector<std::string> errs(G);
         std::vector<std::thread> th;
         const size_t base = n_pairs / G, rem = n_pairs % G;
+        const bool solo = G == 1 || n_pairs == 1;      // one device fed by this call: the copy threads are its own
         size_t p0 = 0;
         for (size_t g = 0; g < G; g++) {
             const size_t cnt = base + (g < rem ? 1 : 0);
@@ -782,7 +966,7 @@ int audiosync_cuda_xcorr_batch_results(audiosync_cuda_ctx* ctx, const void* sour
             if (cnt == 0) continue;
             auto work = [&, g, a, b] {
                 rcs[g] = run_host_range(ctx, ctx->devs[g], static_cast<const char*>(sources),
-                                        static_cast<const char*>(samples), a, b, L, dtype, results);
+                                        static_cast<const char*>(samples), a, b, L, dtype, results, solo);
                 if (rcs[g] != 0) errs[g] = take_last_error();   // the worker's thread-local message
             };
             if (G == 1) work(); else th.emplace_back(work);
@@ -1240,7 +1424,7 @@ double pearson_coefficient(double* source_start, const double* source_end, doubl
     }
     if (ensure_tickets(d.work, 1) != 0) return fail();
     if (launch(ctx, d, KC_PEARSON, st, [&] {
-            pearson_kernel<double><<<dim3(n_chunks, 1), PEARSON_THREADS, 0, st>>>(
+            pearson_kernel<double, true><<<dim3(n_chunks, 1), PEARSON_THREADS, 0, st>>>(
                 static_cast<const double*>(d.in_src[0].p), static_cast<const double*>(d.in_smp[0].p), 0, 0,
                 n, nullptr, n, 1.0, partials, static_cast<unsigned int*>(d.work.tickets.p), n_chunks, d_res);
         }) != 0) return fail();

@@ -63,6 +63,12 @@ struct PinnedBuf {
 // Pinned bounce buffers for PAGEABLE host inputs: the host memcpy of piece k + 1 overlaps the
 // DMA of piece k and the stream stays asynchronous (a cudaMemcpyAsync straight from pageable
 // memory is staged by the driver and blocks the calling thread for the whole transfer).
+// Internal input type of enqueue_batch beside the public F32 / F64: fp32 values that are the EXACT
+// images of the caller's doubles (lossless host narrowing).  The transform reads them as any fp32
+// batch; the Pearson step widens them and runs the f64 path's arithmetic, so the result record is
+// the f64 call's bit for bit.
+constexpr int ASC_DTYPE_F32_EXACT = 100;
+
 struct StageRing {
     static constexpr int N = 4;
     static constexpr size_t PIECE = (size_t)8 << 20;
@@ -108,13 +114,20 @@ struct DeviceState {
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;        // compute
     cudaStream_t copy_stream = nullptr;   // uploads for the host-facing batch call
+    cudaStream_t narrow_stream = nullptr; // uploads of host-narrowed (f64 -> fp32) pairs, beside the direct ones
     WorkSet work;         // scratch of the batch entry points (serialised by the context mutex)
     DevBuf results;       // audiosync_cuda_result for host-facing calls
     DevBuf in_src[2], in_smp[2];          // device copies of host inputs (double buffered)
+    DevBuf in_src32[2], in_smp32[2];      // the host-narrowed pairs of a chunk (fp32 images of f64 inputs)
     PinnedBuf h_results;
     StageRing stage;                      // bounce buffers for pageable host inputs
     cudaEvent_t ev_up[2] = {nullptr, nullptr};
+    cudaEvent_t ev_up32[2] = {nullptr, nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr};
+    // direct (un-narrowed) pair uploads in flight beside the narrowing threads: at most DIRECT_DEPTH
+    static constexpr int DIRECT_DEPTH = 2;
+    cudaEvent_t direct_ev[DIRECT_DEPTH] = {nullptr, nullptr};
+    bool direct_pending[DIRECT_DEPTH] = {false, false};
     std::map<size_t, std::shared_ptr<FftPlan>> plans;   // by sample_len
     std::mutex mu;        // serialises users of `work`, `results`, the input mirrors and the staging ring
     std::mutex plan_mu;   // plans are built once and shared by concurrent callers
@@ -170,8 +183,10 @@ struct audiosync_cuda_ctx {
     int path = AUDIOSYNC_CUDA_PATH_AUTO;
     int wave_pairs = 0;
     bool precise = false;     // fp64 ARITHMETIC in the transforms (validation mode)
+    int narrow_host = 1;      // AUDIOSYNC_CUDA_NARROW_*: f64 HOST batches converted to fp32 on the host while staged
     bool profile = false;
     std::atomic<uint64_t> launches{0};
+    std::atomic<uint64_t> fed_direct{0}, fed_narrowed{0};   // F64 host-fed pairs: as doubles / narrowed on the host
     asc::ResidentSession resident;           // drop-in cross_correlation() only (default context)
 
     asc::DeviceState* find(int device);

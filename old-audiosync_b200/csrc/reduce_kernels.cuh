@@ -215,7 +215,10 @@ __device__ __forceinline__ void pearson_finish(const PearsonPartial& s, const Wi
 // CTA of a pair to finish (ticket counter, self-resetting) sums the chunk partials in a fixed
 // order and writes the result record, so the whole Pearson step needs no second launch.
 // Every thread of the CTA must call it (barriers inside).
-template <typename T, int NTP>
+// WIDE: fp64 arithmetic on the widened inputs whatever T is.  T = float with WIDE is the path of
+// host-narrowed batches whose floats are the exact images of the caller's doubles: element for
+// element the same operations as T = double, so the record is the f64 call's bit for bit.
+template <typename T, int NTP, bool WIDE = (sizeof(T) == 8)>
 __device__ __forceinline__ void pearson_block(
     const T* __restrict__ sources, const T* __restrict__ samples,
     long long src_pitch, long long smp_pitch, long long L,
@@ -259,7 +262,7 @@ __device__ __forceinline__ void pearson_block(
         const double px = sh.piv[0], py = sh.piv[1];
         long long hi = lo + (NTP * PEARSON_PER_THREAD);
         if (hi > w.n) hi = w.n;
-        if constexpr (sizeof(T) == 4) {
+        if constexpr (!WIDE) {
             // fp32 inputs: shifted values and products in fp32, 16 elements per thread and
             // iteration summed in fp32 (every term is < 4, so the partial is good to ~1e-7
             // relative), then folded into the fp64 accumulators -- 5 conversions per 16
@@ -375,7 +378,7 @@ __device__ __forceinline__ void pearson_block(
                 py += __shfl_xor_sync(0xffffffffu, py, o);
             }
             px *= (1.0 / 32.0); py *= (1.0 / 32.0);
-            if constexpr (sizeof(T) == 4) { px = (double)(float)px; py = (double)(float)py; }
+            if constexpr (!WIDE) { px = (double)(float)px; py = (double)(float)py; }
         }
         if (t == 0) {
             pearson_finish(s, w, raw, peak, second, px, py, L, results + pair);
@@ -385,7 +388,7 @@ __device__ __forceinline__ void pearson_block(
 }
 
 // grid = (n_chunks, n_pairs), block = 256.
-template <typename T>
+template <typename T, bool WIDE = (sizeof(T) == 8)>
 __global__ void __launch_bounds__(PEARSON_THREADS)
 pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
                long long src_pitch, long long smp_pitch, long long L,
@@ -395,7 +398,7 @@ pearson_kernel(const T* __restrict__ sources, const T* __restrict__ samples,
 {
     __shared__ PearsonShared<PEARSON_THREADS> sh;
     pdl_prologue();
-    pearson_block<T, PEARSON_THREADS>(sources, samples, src_pitch, smp_pitch, L, peaks, explicit_n, peak_scale, partials,
+    pearson_block<T, PEARSON_THREADS, WIDE>(sources, samples, src_pitch, smp_pitch, L, peaks, explicit_n, peak_scale, partials,
                                       tickets, n_chunks, results, (int)blockIdx.y, (int)blockIdx.x,
                                       (int)threadIdx.x, sh);
 }

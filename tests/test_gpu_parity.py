@@ -694,6 +694,95 @@ def test_host_batch_api(ac, ctx, capi, npdt):
             assert close(r["peaks"][i], gold[i]["peak"])
 
 
+def _narrow_case(capi, L, n, seed):
+    s64 = np.empty((n, 2 * L), np.float64); p64 = np.empty((n, L), np.float64)
+    for i in range(n):
+        s64[i], p64[i] = capi.synth_pair(seed, i, L)            # fp32-exact values
+    return s64, p64
+
+
+def _records_equal(ac, a, b):
+    for name in ac.RESULT_DTYPE.names:
+        assert np.array_equal(a[name], b[name], equal_nan=True), name
+
+
+@pytest.mark.parametrize("L,n", [(480000, 24), (6000, 300), (1000, 40), (100000, 9)])
+def test_lossless_host_narrowing_is_bit_identical(ac, capi, L, n):
+    """Default mode of the F64 HOST batch call: pairs whose doubles are exact images of floats cross
+    PCIe as fp32 (narrowed by the copy threads) while others go up as doubles, and EVERY field of
+    every record equals the un-narrowed call's -- static plans, runtime-radix plans, the single-CTA
+    and the time-domain kernels; pinned (fed both ways at once) and pageable (all narrowed) inputs."""
+    s64, p64 = _narrow_case(capi, L, n, SEED + 80)
+    with ac.Context([0]) as c:
+        c.set_host_narrowing(ac.NARROW_OFF)
+        ref = c.xcorr_batch_records(s64.ctypes.data, p64.ctypes.data, n, L, ac.F64, ac.HOST)
+        c.set_host_narrowing(ac.NARROW_LOSSLESS)
+        got = c.xcorr_batch_records(s64.ctypes.data, p64.ctypes.data, n, L, ac.F64, ac.HOST)      # pageable
+        with ac.RealBuffer(n * 2 * L) as sb, ac.RealBuffer(n * L) as mb:                           # pinned
+            sb.array[:] = s64.reshape(-1); mb.array[:] = p64.reshape(-1)
+            got_pinned = c.xcorr_batch_records(sb.ptr, mb.ptr, n, L, ac.F64, ac.HOST)
+    _records_equal(ac, got, ref)
+    _records_equal(ac, got_pinned, ref)
+    for i in range(0, n, max(1, n // 5)):
+        assert int(ref["lag"][i]) == capi.synth_true_lag(SEED + 80, i, L)
+
+
+@pytest.mark.parametrize("where", ["first", "middle", "last_pair_sample", "nan"])
+def test_lossless_host_narrowing_gives_up_on_inexact_values(ac, capi, where):
+    """One double that is not the image of a float -- anywhere in the batch -- and the records still
+    equal the un-narrowed call's bit for bit (that chunk and all later ones go up as doubles)."""
+    L, n = 144000, 130                     # several upload chunks, pinned and pageable
+    s64, p64 = _narrow_case(capi, L, n, SEED + 81)
+    if where == "first":
+        s64[0, 5] += 2.0 ** -40
+    elif where == "middle":
+        s64[n // 2, L] = np.pi / 8
+    elif where == "last_pair_sample":
+        p64[n - 1, L - 1] += 2.0 ** -33
+    else:
+        p64[n // 3, 17] = np.nan
+    with ac.Context([0]) as c:
+        c.set_host_narrowing(ac.NARROW_OFF)
+        ref = c.xcorr_batch_records(s64.ctypes.data, p64.ctypes.data, n, L, ac.F64, ac.HOST)
+        c.set_host_narrowing(ac.NARROW_LOSSLESS)
+        got = c.xcorr_batch_records(s64.ctypes.data, p64.ctypes.data, n, L, ac.F64, ac.HOST)
+        with ac.RealBuffer(n * 2 * L) as sb, ac.RealBuffer(n * L) as mb:
+            sb.array[:] = s64.reshape(-1); mb.array[:] = p64.reshape(-1)
+            got_pinned = c.xcorr_batch_records(sb.ptr, mb.ptr, n, L, ac.F64, ac.HOST)
+            again = c.xcorr_batch_records(sb.ptr, mb.ptr, n, L, ac.F64, ac.HOST)
+    _records_equal(ac, got, ref)
+    _records_equal(ac, got_pinned, ref)
+    _records_equal(ac, again, ref)
+    if where == "nan":
+        assert int(ref["ret"][n // 3]) == -1
+
+
+def test_host_narrowing_always_equals_the_fp32_batch(ac, capi):
+    """NARROW_ALWAYS: an f64 HOST batch converted to fp32 while it is staged returns, bit for bit,
+    what the fp32 batch of the rounded values returns (pinned and pageable sources, more than one
+    ring buffer per pair), and stays within tolerance of the f64 path."""
+    L, n = 480000, 5
+    s64, p64 = _narrow_case(capi, L, n, SEED + 80)
+    s64 *= 1.0 + 2.0 ** -30                                 # no longer exact in fp32
+    p64 *= 1.0 - 2.0 ** -31
+    s32, p32 = s64.astype(np.float32), p64.astype(np.float32)
+    with ac.Context([0]) as c:
+        ref32 = c.xcorr_batch_records(s32.ctypes.data, p32.ctypes.data, n, L, ac.F32, ac.HOST)
+        ref64 = c.xcorr_batch_records(s64.ctypes.data, p64.ctypes.data, n, L, ac.F64, ac.HOST)    # lossless: gives up
+        c.set_host_narrowing(ac.NARROW_ALWAYS)
+        got = c.xcorr_batch_records(s64.ctypes.data, p64.ctypes.data, n, L, ac.F64, ac.HOST)      # pageable
+        with ac.RealBuffer(n * 2 * L) as sb, ac.RealBuffer(n * L) as mb:                           # pinned
+            sb.array[:] = s64.reshape(-1); mb.array[:] = p64.reshape(-1)
+            got_pinned = c.xcorr_batch_records(sb.ptr, mb.ptr, n, L, ac.F64, ac.HOST)
+        c.set_precise(True)                                                                        # precise mode ignores it
+        assert "fp64" in c.describe_plan(L)
+    _records_equal(ac, got, ref32)
+    _records_equal(ac, got_pinned, ref32)
+    for i in range(n):
+        assert int(got["lag"][i]) == int(ref64["lag"][i]) == capi.synth_true_lag(SEED + 80, i, L)
+        assert close(float(got["coef"][i]), float(ref64["coef"][i]), 1e-6)
+
+
 def test_host_batch_multi_chunk_and_wave_sizes(ac, capi):
     """More pairs than one upload chunk / one kernel wave; every wave size gives the same answer."""
     L, n = 6000, 300
