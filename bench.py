@@ -612,6 +612,9 @@ def main():
         ne = min(args.e2e_pairs, n)
         reps = max(2, args.steps)
         e2e = e2e_leg(torch.float64, ac.F64, True, max(1, ne // 2), reps)
+        if os.environ.get("E2E_ONLY_HEADLINE") == "1":            # tools/e2e_feed.sh: feed-policy sweeps
+            emit({"e2e": e2e, "e2e_variants": {}})
+            return
         e2e_variants["f64_pinned_narrowing_off"] = e2e_leg(torch.float64, ac.F64, True, max(1, ne // 2), reps, narrow=ac.NARROW_OFF)
         e2e_variants["f32_pinned"] = e2e_leg(torch.float32, ac.F32, True, ne, reps)
         e2e_variants["f64_pageable"] = e2e_leg(torch.float64, ac.F64, False, max(1, ne // 4), 2)

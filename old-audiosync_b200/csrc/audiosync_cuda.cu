@@ -486,7 +486,7 @@ static int upload_from_host(void* dst, const void* src, size_t bytes, cudaStream
 // half the bytes cross PCIe.  Any host memory.  *exact is cleared when a value did not survive the
 // conversion unchanged; with stop_on_inexact the upload ends at that piece (the caller redoes it).
 static int upload_narrowed(float* dst, const double* src, size_t n, cudaStream_t st, StageRing& ring,
-                           bool* exact, bool stop_on_inexact) {
+                           bool* exact, bool stop_on_inexact, const std::function<void()>& between_pieces) {
     const size_t piece = StageRing::PIECE / sizeof(float);        // elements per ring buffer
     for (size_t o = 0; o < n; o += piece) {
         const size_t m = std::min(piece, n - o);
@@ -503,8 +503,20 @@ static int upload_narrowed(float* dst, const double* src, size_t n, cudaStream_t
         ASC_CUDA_OK(cudaMemcpyAsync(dst + o, ring.buf[i].p, m * sizeof(float), cudaMemcpyHostToDevice, st));
         ASC_CUDA_OK(cudaEventRecord(ring.ev[i], st));
         ring.pending[i] = true;
+        if (between_pieces) between_pieces();
     }
     return 0;
+}
+
+// Pieces of the staging ring whose upload has not finished yet.
+static int ring_backlog(StageRing& ring) {
+    int n = 0;
+    for (int i = 0; i < StageRing::N; i++) {
+        if (!ring.pending[i]) continue;
+        if (cudaEventQuery(ring.ev[i]) == cudaSuccess) ring.pending[i] = false;
+        else { cudaGetLastError(); n++; }
+    }
+    return n;
 }
 
 // Direct (un-narrowed) uploads of whole pairs that run beside the narrowing threads: how many
@@ -524,9 +536,9 @@ static int direct_in_flight(DeviceState& d) {
 // F64 batches with host narrowing on (see include/audiosync_cuda.h): a chunk's pairs are taken from
 // both ends.  From the back, the copy threads convert a pair to fp32 into the pinned ring and its
 // half-size pieces go up on `narrow_stream`; from the front -- page-locked inputs only -- the copy
-// engine takes whole pairs of doubles straight from the caller's memory on `copy_stream`, at most
-// DIRECT_DEPTH in flight, so that link time the conversion leaves idle is used and neither side
-// waits for the other.  The two sub-batches [0, k) (doubles) and [k, n) (exact fp32 images) are
+// engine takes pairs of doubles straight from the caller's memory on `copy_stream`, in slices of
+// 8 MB issued only while the ring's uploads keep up, so that link time the conversion leaves idle
+// is used and neither side waits for the other.  The two sub-batches [0, k) (doubles) and [k, n) (exact fp32 images) are
 // enqueued separately.  solo: this call drives a single device (several devices of one context
 // share the copy threads; each then feeds its device with direct uploads only).
 static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* sources,
@@ -541,7 +553,11 @@ static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* s
     const bool pageable = host_pointer_is_pageable(sources) || host_pointer_is_pageable(samples);
     int mode = (dtype == AUDIOSYNC_CUDA_F64 && !ctx->precise) ? ctx->narrow_host : AUDIOSYNC_CUDA_NARROW_OFF;
     if (mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS && !solo && !pageable) mode = AUDIOSYNC_CUDA_NARROW_OFF;
-    const bool hybrid = mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS && !pageable;
+    static const int feed_depth = [] { const char* e = getenv("AUDIOSYNC_CUDA_FEED_DEPTH");
+                                       return e ? std::max(1, std::min(atoi(e), DeviceState::DIRECT_DEPTH)) : 2; }();
+    static const int feed_backlog = [] { const char* e = getenv("AUDIOSYNC_CUDA_FEED_BACKLOG"); return e ? std::max(0, atoi(e)) : 1; }();
+    static const bool both_ways = [] { const char* e = getenv("AUDIOSYNC_CUDA_FEED_BOTH_WAYS"); return !(e && atoi(e) == 0); }();
+    const bool hybrid = mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS && !pageable && both_ways;
     // chunk: about 192 MB of input per buffer (twice that when pairs are fed both ways), at least one pair
     size_t chunk = std::max<size_t>(1, ((size_t)(hybrid ? 384u : 192u) << 20) / (src_bytes + smp_bytes));
     chunk = std::min(chunk, p1 - p0);
@@ -572,50 +588,79 @@ static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* s
             ASC_CUDA_OK(cudaStreamWaitEvent(d.copy_stream, d.ev_done[b], 0));
             if (mode != AUDIOSYNC_CUDA_NARROW_OFF) ASC_CUDA_OK(cudaStreamWaitEvent(d.narrow_stream, d.ev_done[b], 0));
         }
-        size_t lo = 0, hi = n;          // pairs [0, lo) go up as they are, pairs [hi, n) narrowed
+        // pairs [0, lo) go up as they are (pair lo too, partly, when dir_off > 0); pairs [hi, n) narrowed
+        size_t lo = 0, hi = n, dir_off = 0;
+        const size_t pair_bytes = src_bytes + smp_bytes;
         if (mode == AUDIOSYNC_CUDA_NARROW_OFF) {
             if (upload_from_host(d.in_src[b].p, hs, src_bytes * n, d.copy_stream, d.stage, pageable) != 0 ||
                 upload_from_host(d.in_smp[b].p, hm, smp_bytes * n, d.copy_stream, d.stage, pageable) != 0)
                 return -1;
             lo = n;
         }
+        // the next slice of pair lo, as doubles, straight from the caller's (page-locked) memory
+        auto direct_slice = [&]() -> int {
+            int k = 0;
+            while (k < DeviceState::DIRECT_DEPTH - 1 && d.direct_pending[k]) k++;
+            if (d.direct_pending[k]) ASC_CUDA_OK(cudaEventSynchronize(d.direct_ev[k]));
+            const bool in_src = dir_off < src_bytes;
+            const size_t o = in_src ? dir_off : dir_off - src_bytes;
+            const size_t m = std::min(DeviceState::DIRECT_SLICE, (in_src ? src_bytes : smp_bytes) - o);
+            char* dst = static_cast<char*>(in_src ? d.in_src[b].p : d.in_smp[b].p) + lo * (in_src ? src_bytes : smp_bytes) + o;
+            const char* src = (in_src ? hs : hm) + lo * (in_src ? src_bytes : smp_bytes) + o;
+            ASC_CUDA_OK(cudaMemcpyAsync(dst, src, m, cudaMemcpyHostToDevice, d.copy_stream));
+            ASC_CUDA_OK(cudaEventRecord(d.direct_ev[k], d.copy_stream));
+            d.direct_pending[k] = true;
+            dir_off += m;
+            if (dir_off == pair_bytes) { lo++; dir_off = 0; }
+            return 0;
+        };
+        // Direct slices only into link time the narrowed stream leaves idle: at most DIRECT_DEPTH
+        // in flight, and only while the ring's uploads keep up with the conversion (the narrowed
+        // form costs half the link bytes per pair, so it has the right of way; the copy threads,
+        // not the link, bound it).  Called between the pieces of the pair being narrowed.
+        int feed_rc = 0;
+        auto feed_direct = [&]() {
+            while (feed_rc == 0 && (dir_off > 0 || lo < hi) && direct_in_flight(d) < feed_depth &&
+                   ring_backlog(d.stage) <= feed_backlog)
+                feed_rc = direct_slice();
+        };
         while (lo < hi) {
-            if (mode == AUDIOSYNC_CUDA_NARROW_OFF || (hybrid && direct_in_flight(d) < DeviceState::DIRECT_DEPTH)) {
-                // the next pair from the front, as doubles (after narrowing was given up: all that is left)
-                if (mode != AUDIOSYNC_CUDA_NARROW_OFF || !pageable) {
-                    int k = 0;
-                    while (k < DeviceState::DIRECT_DEPTH - 1 && d.direct_pending[k]) k++;
-                    if (d.direct_pending[k]) ASC_CUDA_OK(cudaEventSynchronize(d.direct_ev[k]));
-                    ASC_CUDA_OK(cudaMemcpyAsync(static_cast<char*>(d.in_src[b].p) + lo * src_bytes, hs + lo * src_bytes, src_bytes,
-                                                cudaMemcpyHostToDevice, d.copy_stream));
-                    ASC_CUDA_OK(cudaMemcpyAsync(static_cast<char*>(d.in_smp[b].p) + lo * smp_bytes, hm + lo * smp_bytes, smp_bytes,
-                                                cudaMemcpyHostToDevice, d.copy_stream));
-                    ASC_CUDA_OK(cudaEventRecord(d.direct_ev[k], d.copy_stream));
-                    d.direct_pending[k] = true;
-                    lo++;
-                } else {                // pageable inputs whose narrowing was given up: the rest through the ring
-                    if (upload_from_host(static_cast<char*>(d.in_src[b].p) + lo * src_bytes, hs + lo * src_bytes, src_bytes * (hi - lo),
-                                         d.copy_stream, d.stage, true) != 0 ||
-                        upload_from_host(static_cast<char*>(d.in_smp[b].p) + lo * smp_bytes, hm + lo * smp_bytes, smp_bytes * (hi - lo),
-                                         d.copy_stream, d.stage, true) != 0)
-                        return -1;
-                    lo = hi;
-                }
-                continue;
+            if (mode == AUDIOSYNC_CUDA_NARROW_OFF) {
+                // narrowing was given up in this chunk: everything that is left goes up as doubles
+                while (dir_off > 0)
+                    if (direct_slice() != 0) return -1;
+                if (lo < hi &&
+                    (upload_from_host(static_cast<char*>(d.in_src[b].p) + lo * src_bytes, hs + lo * src_bytes, src_bytes * (hi - lo),
+                                      d.copy_stream, d.stage, pageable) != 0 ||
+                     upload_from_host(static_cast<char*>(d.in_smp[b].p) + lo * smp_bytes, hm + lo * smp_bytes, smp_bytes * (hi - lo),
+                                      d.copy_stream, d.stage, pageable) != 0))
+                    return -1;
+                lo = hi;
+                break;
+            }
+            if (hybrid) feed_direct();
+            if (feed_rc != 0) return -1;
+            if (lo == hi) break;
+            if (hi - 1 == lo && dir_off > 0) {          // only the partly fed pair is left
+                while (dir_off > 0)
+                    if (direct_slice() != 0) return -1;
+                break;
             }
             // the next pair from the back, narrowed
-            const size_t j = hi - 1;
+            const size_t j = --hi;
             bool exact = true;
             const bool stop = mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS;
+            std::function<void()> between;
+            if (hybrid) between = feed_direct;
             if (upload_narrowed(static_cast<float*>(d.in_src32[b].p) + j * src_n, reinterpret_cast<const double*>(hs) + j * src_n, src_n,
-                                d.narrow_stream, d.stage, &exact, stop) != 0)
+                                d.narrow_stream, d.stage, &exact, stop, between) != 0)
                 return -1;
             if ((exact || !stop) &&
                 upload_narrowed(static_cast<float*>(d.in_smp32[b].p) + j * smp_n, reinterpret_cast<const double*>(hm) + j * smp_n, smp_n,
-                                d.narrow_stream, d.stage, &exact, stop) != 0)
+                                d.narrow_stream, d.stage, &exact, stop, between) != 0)
                 return -1;
-            if (!exact && stop) mode = AUDIOSYNC_CUDA_NARROW_OFF;     // this pair and all later ones go up as doubles
-            else hi = j;
+            if (feed_rc != 0) return -1;
+            if (!exact && stop) { hi = j + 1; mode = AUDIOSYNC_CUDA_NARROW_OFF; }   // this pair and all later ones go up as doubles
         }
         // pairs [0, lo): doubles (or the caller's fp32); pairs [hi, n): narrowed
         if (lo > 0) {

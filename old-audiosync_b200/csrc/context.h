@@ -70,11 +70,11 @@ struct PinnedBuf {
 constexpr int ASC_DTYPE_F32_EXACT = 100;
 
 struct StageRing {
-    static constexpr int N = 4;
+    static constexpr int N = 6;
     static constexpr size_t PIECE = (size_t)8 << 20;
     PinnedBuf buf[N];
-    cudaEvent_t ev[N] = {nullptr, nullptr, nullptr, nullptr};
-    bool pending[N] = {false, false, false, false};
+    cudaEvent_t ev[N] = {};
+    bool pending[N] = {};
     int next = 0;
     void release() {
         for (int i = 0; i < N; i++) {
@@ -124,10 +124,11 @@ struct DeviceState {
     cudaEvent_t ev_up[2] = {nullptr, nullptr};
     cudaEvent_t ev_up32[2] = {nullptr, nullptr};
     cudaEvent_t ev_done[2] = {nullptr, nullptr};
-    // direct (un-narrowed) pair uploads in flight beside the narrowing threads: at most DIRECT_DEPTH
-    static constexpr int DIRECT_DEPTH = 2;
-    cudaEvent_t direct_ev[DIRECT_DEPTH] = {nullptr, nullptr};
-    bool direct_pending[DIRECT_DEPTH] = {false, false};
+    // direct (un-narrowed) upload slices in flight beside the narrowing threads: at most DIRECT_DEPTH
+    static constexpr int DIRECT_DEPTH = 4;
+    static constexpr size_t DIRECT_SLICE = (size_t)8 << 20;
+    cudaEvent_t direct_ev[DIRECT_DEPTH] = {};
+    bool direct_pending[DIRECT_DEPTH] = {};
     std::map<size_t, std::shared_ptr<FftPlan>> plans;   // by sample_len
     std::mutex mu;        // serialises users of `work`, `results`, the input mirrors and the staging ring
     std::mutex plan_mu;   // plans are built once and shared by concurrent callers
