@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <immintrin.h>
 #include <limits>
 #include <map>
 #include <thread>
@@ -434,6 +435,40 @@ public:
         run(dst, src, n, sizeof(double), sizeof(float), true, threads());
         return !inexact_.load(std::memory_order_relaxed);
     }
+    // The same on the workers alone, so that the calling thread can keep the copy engine fed in the
+    // meantime: narrow_begin(); while (!narrow_done()) { ... }; exact = narrow_end().
+    void narrow_begin(float* dst, const double* src, size_t n) {
+        run_mu_.lock();
+        inexact_.store(false, std::memory_order_relaxed);
+        const size_t parts = workers_.size();
+        if (parts == 0 || n * sizeof(double) < ((size_t)1 << 20)) {
+            run_slice(Slice{reinterpret_cast<char*>(dst), reinterpret_cast<const char*>(src), n, true});
+            return;
+        }
+        const size_t per = ((n + parts - 1) / parts + 63) & ~(size_t)63;
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            slices_.clear(); next_ = 0; pending_ = 0;
+            for (size_t o = 0; o < n; o += per) {
+                slices_.push_back(Slice{reinterpret_cast<char*>(dst + o), reinterpret_cast<const char*>(src + o), std::min(per, n - o), true});
+                pending_++;
+            }
+        }
+        cv_.notify_all();
+    }
+    bool narrow_done() {
+        std::lock_guard<std::mutex> lk(m_);
+        return pending_ == 0;
+    }
+    bool narrow_end() {
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            done_cv_.wait(lk, [&] { return pending_ == 0; });
+        }
+        const bool exact = !inexact_.load(std::memory_order_relaxed);
+        run_mu_.unlock();
+        return exact;
+    }
 };
 // Plain copies stop scaling at ~8 threads (measured on the 16-core B200 host: 4 / 8 / 12 threads
 // stage pageable doubles at 38 / 52 / 50 GB/s); narrowing keeps gaining up to 12 (45 / 68 / 77 GB/s
@@ -485,8 +520,10 @@ static int upload_from_host(void* dst, const void* src, size_t bytes, cudaStream
 // Host doubles -> device floats: converted on the host into the pinned ring (copy threads), so that
 // half the bytes cross PCIe.  Any host memory.  *exact is cleared when a value did not survive the
 // conversion unchanged; with stop_on_inexact the upload ends at that piece (the caller redoes it).
+// meanwhile: called over and over by this thread while the workers convert a piece (it then takes no
+// part in the conversion itself).
 static int upload_narrowed(float* dst, const double* src, size_t n, cudaStream_t st, StageRing& ring,
-                           bool* exact, bool stop_on_inexact, const std::function<void()>& between_pieces) {
+                           bool* exact, bool stop_on_inexact, const std::function<void()>& meanwhile) {
     const size_t piece = StageRing::PIECE / sizeof(float);        // elements per ring buffer (4 / 16 MB pieces: -13 %)
     for (size_t o = 0; o < n; o += piece) {
         const size_t m = std::min(piece, n - o);
@@ -496,14 +533,26 @@ static int upload_narrowed(float* dst, const double* src, size_t n, cudaStream_t
         if (!ring.ev[i]) ASC_CUDA_OK(cudaEventCreateWithFlags(&ring.ev[i], cudaEventDisableTiming));
         if (ring.pending[i]) ASC_CUDA_OK(cudaEventSynchronize(ring.ev[i]));
         ring.pending[i] = false;
-        if (!copy_pool().narrow(static_cast<float*>(ring.buf[i].p), src + o, m)) {
+        bool piece_exact;
+        if (meanwhile) {
+            // the workers convert; this thread keeps the copy engine fed until they are done
+            copy_pool().narrow_begin(static_cast<float*>(ring.buf[i].p), src + o, m);
+            while (!copy_pool().narrow_done()) {
+                meanwhile();
+                for (int k = 0; k < 64; k++) _mm_pause();
+            }
+            piece_exact = copy_pool().narrow_end();
+        } else {
+            piece_exact = copy_pool().narrow(static_cast<float*>(ring.buf[i].p), src + o, m);
+        }
+        if (!piece_exact) {
             *exact = false;
             if (stop_on_inexact) return 0;
         }
         ASC_CUDA_OK(cudaMemcpyAsync(dst + o, ring.buf[i].p, m * sizeof(float), cudaMemcpyHostToDevice, st));
         ASC_CUDA_OK(cudaEventRecord(ring.ev[i], st));
         ring.pending[i] = true;
-        if (between_pieces) between_pieces();
+        if (meanwhile) meanwhile();
     }
     return 0;
 }
