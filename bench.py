@@ -472,6 +472,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        # several processes share this host's cores: each library instance gets its share of copy
+        # threads (pageable staging / host narrowing; below 8 the library feeds page-locked doubles
+        # through the copy engine alone) -- read by the library on first use
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        os.environ.setdefault("AUDIOSYNC_CUDA_COPY_THREADS",
+                              str(max(1, min(12, len(os.sched_getaffinity(0)) * 3 // 4 // max(1, local_world)))))
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
@@ -604,6 +610,7 @@ def main():
                     "pairs_per_step": ne, "host_dtype": "f32" if esz == 4 else "f64",
                     "host_memory": "pinned" if pinned else "pageable", "host_binding": numa,
                     "host_narrowing": (None if esz == 4 else ["off", "lossless", "always"][narrow]),
+                    "copy_threads": ac.copy_threads(),
                     "pairs_fed_as_doubles": fed_direct, "pairs_narrowed_on_host": fed_narrowed,
                     "host_gbs_per_gpu": ne * 3 * L * esz * reps / float(tt[0]) / 1e9,
                     "link_gbs_per_gpu": link_bytes / float(tt[0]) / 1e9,

@@ -260,6 +260,10 @@ int  audiosync_cuda_set_host_narrowing(audiosync_cuda_ctx *ctx, int mode);
 /* The host-side conversion itself (copy threads, SIMD): dst[i] = (float)src[i], round to nearest
  * even; returns 1 when every value survived unchanged, 0 otherwise.  Needs no GPU. */
 int  audiosync_cuda_host_narrow(float *dst, const double *src, size_t n);
+/* Copy threads of this process (pageable staging, host narrowing): AUDIOSYNC_CUDA_COPY_THREADS, default
+ * three quarters of the cores the process may run on, at most 12.  With fewer than 8, LOSSLESS
+ * narrowing leaves page-locked inputs to the copy engine alone (pageable ones are still narrowed). */
+int  audiosync_cuda_copy_threads(void);
 /* fp64-ARITHMETIC validation mode: every transform runs on the double-precision instantiation
  * of the runtime-radix kernels (the reference computes in double complex throughout,
  * src/cross_correlation.c:187-239) and the argmax on full double keys -- several times slower

@@ -23,7 +23,7 @@ __all__ = [
     "AudiosyncCudaError", "lib", "lib_path", "cross_correlation", "pearson_coefficient",
     "interval_loop", "Context", "RESULT_DTYPE", "MIN_CONFIDENCE", "SAMPLE_RATE",
     "INTERV_SAMPLE", "frames_to_ms", "F32", "F64", "HOST", "DEVICE",
-    "PATH_AUTO", "PATH_FFT", "PATH_DIRECT", "NARROW_OFF", "NARROW_LOSSLESS", "NARROW_ALWAYS", "EXPORTED_SYMBOLS", "shard_pairs", "gather_results", "host_narrow",
+    "PATH_AUTO", "PATH_FFT", "PATH_DIRECT", "NARROW_OFF", "NARROW_LOSSLESS", "NARROW_ALWAYS", "EXPORTED_SYMBOLS", "shard_pairs", "gather_results", "host_narrow", "copy_threads",
     "cross_correlation_ptr", "RealBuffer", "set_residency", "dropin_stats", "dropin_max_inflight", "SessionPool",
 ]
 
@@ -50,7 +50,7 @@ EXPORTED_SYMBOLS = [
     "audiosync_cuda_xcorr_batch", "audiosync_cuda_xcorr_batch_results", "audiosync_cuda_xcorr_batch_device",
     "audiosync_cuda_synth_pairs", "audiosync_cuda_synchronize",
     "audiosync_cuda_set_path", "audiosync_cuda_set_wave_pairs", "audiosync_cuda_set_debug", "audiosync_cuda_set_precise",
-    "audiosync_cuda_set_host_narrowing", "audiosync_cuda_host_narrow",
+    "audiosync_cuda_set_host_narrowing", "audiosync_cuda_host_narrow", "audiosync_cuda_copy_threads",
     "audiosync_cuda_set_residency", "audiosync_cuda_dropin_stats", "audiosync_cuda_dropin_max_inflight",
     "audiosync_cuda_pool_create", "audiosync_cuda_pool_destroy", "audiosync_cuda_pool_reset",
     "audiosync_cuda_pool_append", "audiosync_cuda_pool_append_async", "audiosync_cuda_pool_flush",
@@ -117,6 +117,8 @@ def lib() -> C.CDLL:
     L.audiosync_cuda_set_path.argtypes = [vp, i32]
     L.audiosync_cuda_set_host_narrowing.restype = i32
     L.audiosync_cuda_set_host_narrowing.argtypes = [vp, i32]
+    L.audiosync_cuda_copy_threads.restype = i32
+    L.audiosync_cuda_copy_threads.argtypes = []
     L.audiosync_cuda_host_narrow.restype = i32
     L.audiosync_cuda_host_narrow.argtypes = [vp, vp, C.c_size_t]
     L.audiosync_cuda_set_precise.restype = i32
@@ -293,6 +295,11 @@ class RealBuffer:
 
     def __exit__(self, *exc):
         self.free()
+
+
+def copy_threads() -> int:
+    """Copy threads of this process (pageable staging, host narrowing)."""
+    return int(lib().audiosync_cuda_copy_threads())
 
 
 def host_narrow(x: np.ndarray):

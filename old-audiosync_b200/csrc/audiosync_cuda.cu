@@ -14,6 +14,7 @@
 #include <cstring>
 #include <functional>
 #include <immintrin.h>
+#include <sched.h>
 #include <limits>
 #include <map>
 #include <thread>
@@ -472,20 +473,25 @@ public:
 };
 // Plain copies stop scaling at ~8 threads (measured on the 16-core B200 host: 4 / 8 / 12 threads
 // stage pageable doubles at 38 / 52 / 50 GB/s); narrowing keeps gaining up to 12 (45 / 68 / 77 GB/s
-// of doubles read).  Default: three quarters of this process's share of the cores, at most 12.
+// of doubles read).  Default: three quarters of the cores this process may run on, at most 12; a
+// launcher that runs several processes per host divides the cores among them through
+// AUDIOSYNC_CUDA_COPY_THREADS (bench.py under torchrun does).
 static CopyPool& copy_pool() {
     static CopyPool* pool = [] {
         unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        int gpus = 1;
-        if (cudaGetDeviceCount(&gpus) != cudaSuccess || gpus < 1) { cudaGetLastError(); gpus = 1; }
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) hw = (unsigned)CPU_COUNT(&set);
         const char* e = getenv("AUDIOSYNC_CUDA_COPY_THREADS");
-        const unsigned share = std::max(1u, hw * 3 / 4 / (unsigned)gpus);
-        unsigned n = e ? (unsigned)std::max(1, atoi(e)) : std::min(12u, share);
+        unsigned n = e ? (unsigned)std::max(1, atoi(e)) : std::min(12u, std::max(1u, hw * 3 / 4));
         const char* nt = getenv("AUDIOSYNC_CUDA_NT_STORES");
         return new CopyPool(n - 1, std::min(8u, n), !(nt && atoi(nt) == 0));
     }();
     return *pool;
 }
+// Below this many copy threads the conversion cannot outrun the link it is meant to relieve
+// (8 GPUs on a 32-vCPU host, 3 threads per process: 4.96 k pairs/s narrowing page-locked doubles
+// vs 5.37 k sending them as they are; pageable inputs need the threads anyway and gain at any count).
+constexpr size_t NARROW_MIN_THREADS = 8;
 
 // Host -> device copy of `bytes` on `st` from ANY host memory.  Page-locked (cudaMallocHost /
 // cudaHostRegister'ed, e.g. this library's fftw_alloc_real) and managed sources go straight to
@@ -601,7 +607,8 @@ static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* s
     const size_t src_bytes = src_n * esz, smp_bytes = smp_n * esz;
     const bool pageable = host_pointer_is_pageable(sources) || host_pointer_is_pageable(samples);
     int mode = (dtype == AUDIOSYNC_CUDA_F64 && !ctx->precise) ? ctx->narrow_host : AUDIOSYNC_CUDA_NARROW_OFF;
-    if (mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS && !solo && !pageable) mode = AUDIOSYNC_CUDA_NARROW_OFF;
+    if (mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS && !pageable && (!solo || copy_pool().threads() < NARROW_MIN_THREADS))
+        mode = AUDIOSYNC_CUDA_NARROW_OFF;
     static const int feed_depth = [] { const char* e = getenv("AUDIOSYNC_CUDA_FEED_DEPTH");
                                        return e ? std::max(1, std::min(atoi(e), DeviceState::DIRECT_DEPTH)) : 2; }();
     static const int feed_backlog = [] { const char* e = getenv("AUDIOSYNC_CUDA_FEED_BACKLOG"); return e ? std::max(0, atoi(e)) : 1; }();
@@ -896,6 +903,8 @@ int audiosync_cuda_set_host_narrowing(audiosync_cuda_ctx* ctx, int mode) {
     ctx->narrow_host = mode;
     return 0;
 }
+
+int audiosync_cuda_copy_threads(void) { return (int)copy_pool().threads(); }
 
 int audiosync_cuda_host_narrow(float* dst, const double* src, size_t n) {
     if (n == 0) return 1;

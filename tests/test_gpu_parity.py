@@ -717,10 +717,18 @@ def test_lossless_host_narrowing_is_bit_identical(ac, capi, L, n):
         c.set_host_narrowing(ac.NARROW_OFF)
         ref = c.xcorr_batch_records(s64.ctypes.data, p64.ctypes.data, n, L, ac.F64, ac.HOST)
         c.set_host_narrowing(ac.NARROW_LOSSLESS)
+        c.host_feed_stats(reset=True)
         got = c.xcorr_batch_records(s64.ctypes.data, p64.ctypes.data, n, L, ac.F64, ac.HOST)      # pageable
+        assert c.host_feed_stats(reset=True) == (0, n)                                             # every pair narrowed
         with ac.RealBuffer(n * 2 * L) as sb, ac.RealBuffer(n * L) as mb:                           # pinned
             sb.array[:] = s64.reshape(-1); mb.array[:] = p64.reshape(-1)
             got_pinned = c.xcorr_batch_records(sb.ptr, mb.ptr, n, L, ac.F64, ac.HOST)
+        as_doubles, narrowed = c.host_feed_stats(reset=True)
+        assert as_doubles + narrowed == n
+        if ac.copy_threads() >= 8:
+            assert narrowed > 0                                                                    # fed both ways
+        else:
+            assert narrowed == 0                                                                   # too few threads: copy engine only
     _records_equal(ac, got, ref)
     _records_equal(ac, got_pinned, ref)
     for i in range(0, n, max(1, n // 5)):
