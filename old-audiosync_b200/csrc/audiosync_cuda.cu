@@ -614,6 +614,8 @@ static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* s
     static const int feed_backlog = [] { const char* e = getenv("AUDIOSYNC_CUDA_FEED_BACKLOG"); return e ? std::max(0, atoi(e)) : 1; }();
     static const bool both_ways = [] { const char* e = getenv("AUDIOSYNC_CUDA_FEED_BOTH_WAYS"); return !(e && atoi(e) == 0); }();
     const bool hybrid = mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS && !pageable && both_ways;
+    // what narrowed pairs are enqueued as: exact images keep the f64 call's arithmetic, ALWAYS answers as an fp32 batch
+    const int narrowed_dtype = mode == AUDIOSYNC_CUDA_NARROW_ALWAYS ? AUDIOSYNC_CUDA_F32 : ASC_DTYPE_F32_EXACT;
     // chunk: about 192 MB of input per buffer (twice that when pairs are fed both ways), at least one pair
     size_t chunk = std::max<size_t>(1, ((size_t)(hybrid ? 384u : 192u) << 20) / (src_bytes + smp_bytes));
     chunk = std::min(chunk, p1 - p0);
@@ -727,9 +729,8 @@ static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* s
         if (hi < n) {
             ASC_CUDA_OK(cudaEventRecord(d.ev_up32[b], d.narrow_stream));
             ASC_CUDA_OK(cudaStreamWaitEvent(d.stream, d.ev_up32[b], 0));
-            const int dt = ctx->narrow_host == AUDIOSYNC_CUDA_NARROW_ALWAYS ? AUDIOSYNC_CUDA_F32 : ASC_DTYPE_F32_EXACT;
             if (enqueue_batch(ctx, d, d.work, static_cast<float*>(d.in_src32[b].p) + hi * src_n,
-                              static_cast<float*>(d.in_smp32[b].p) + hi * smp_n, n - hi, L, dt, d_res + c0 + hi, d.stream) != 0)
+                              static_cast<float*>(d.in_smp32[b].p) + hi * smp_n, n - hi, L, narrowed_dtype, d_res + c0 + hi, d.stream) != 0)
                 return -1;
         }
         ASC_CUDA_OK(cudaEventRecord(d.ev_done[b], d.stream));
