@@ -184,6 +184,71 @@ def _hard_144k():
     return [c for c in d["cases"] if c["L"] == 144000]
 
 
+def _random_lengths(seed, count, lo, hi):
+    """Seeded mix of arbitrary integers, 2/3/5-smooth numbers and their +-1 neighbours in [lo, hi]."""
+    rng = np.random.default_rng(seed)
+    smooth = sorted({2 ** a * 3 ** b * 5 ** c for a in range(22) for b in range(14) for c in range(10)
+                     if lo <= 2 ** a * 3 ** b * 5 ** c <= hi})
+    out = set()
+    while len(out) < count:
+        k = len(out) % 4
+        if k == 0:
+            out.add(int(rng.integers(lo, hi + 1)))
+        elif k == 1:
+            out.add(int(np.exp(rng.uniform(np.log(lo), np.log(hi)))))
+        elif k == 2:
+            out.add(smooth[int(rng.integers(len(smooth)))])
+        else:
+            out.add(min(hi, max(lo, smooth[int(rng.integers(len(smooth)))] + int(rng.choice([-1, 1])))))
+    return sorted(out)
+
+
+def test_generic_planner_on_two_thousand_random_lengths():
+    """Property sweep of the planner the runtime-radix kernels rely on (gen_plan.h): for ANY
+    sample_len up to 3 million frames a plan exists, M = M1 * M2 is the length itself when it is
+    2/3/5-smooth and an embedding 2M >= 3L otherwise (at most ~20 % above the minimum), every radix
+    is one the kernels implement, and both the column tile and the four rows fit one SM."""
+    import re
+    E = C.CDLL(os.path.join(HERE, "emu", "libasc_emu.so"))
+    E.emu_generic_describe.argtypes = [C.c_longlong, C.c_int, C.c_char_p, C.c_size_t]
+    buf = C.create_string_buffer(256)
+    for L in _random_lengths(0xA11, 2000, 64, 3 * 10 ** 6):
+        for precise in (0, 1):
+            assert E.emu_generic_describe(L, precise, buf, 256) == 0, (L, precise)
+            d = buf.value.decode()
+            m = re.search(r"M=(\d+) M1=(\d+) M2=(\d+) col=([0-9x]+) row=([0-9x]+) (?:padded|plain) tile=(\d+)", d)
+            assert m, d
+            M, M1, M2, ct = int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(6))
+            col = [int(x) for x in m.group(4).split("x")]; row = [int(x) for x in m.group(5).split("x")]
+            assert M1 * M2 == M and int(np.prod(col)) == M1 and int(np.prod(row)) == M2, d
+            assert all(r in (2, 3, 4, 5, 6, 8, 9, 10, 12, 15, 16) for r in col + row), d
+            n = L
+            for q in (2, 3, 5):
+                while n % q == 0:
+                    n //= q
+            if n == 1 and M == L:
+                assert "embedded" not in d
+            else:                                   # embedded (a smooth length may be too: no split of it fits)
+                assert "embedded" in d and 2 * M >= 3 * L and M <= 1.2 * 1.5 * L + 64, (L, d)
+            elem = 16 if precise else 8
+            assert M1 * ct * elem <= 220 * 1024 and 4 * (M2 + M2 // 8 + 1) * elem <= 220 * 1024, d
+            assert len(col) <= 6 and len(row) <= 6, d
+
+
+@pytest.mark.parametrize("L", _random_lengths(0xB22, 16, 300, 30000))
+def test_generic_kernels_random_lengths_vs_oracle(emu, L):
+    """The runtime-radix kernel bodies on the CPU at seeded random lengths (arbitrary, smooth,
+    smooth +- 1): raw index exact, peak within the fp32 tolerance."""
+    from oracle import xcorr_numpy
+    src, smp = capi.synth_pair(0xFACE + 1, L % 7, L)
+    o = xcorr_numpy.cross_correlation(src, smp)
+    assert o["margin"] > 1e-3
+    idx, peak, sec, desc = run_generic(emu, src, smp)
+    assert idx == o["raw_index"], desc
+    assert abs(peak - o["peak"]) <= 1e-5 * abs(o["peak"]), desc
+    assert abs(sec - o["second"]) <= 1e-4 * o["second"] + 1e-6 * abs(o["peak"]), desc
+
+
 @pytest.mark.parametrize("case", _hard_144k(), ids=lambda c: "%s-%.0e" % (c["kind"], c["margin"] or 0))
 def test_emulated_kernels_resolve_low_margins_and_edges(emu, case):
     """The fp32 four-step kernel bodies on the hard goldens at L = 144,000: peaks 3e-4 .. 1e-2 apart,

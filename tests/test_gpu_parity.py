@@ -230,6 +230,51 @@ def test_generic_plan_any_length_vs_oracle(ac, ctx, capi, L):
             assert (ret, lag) == (o["ret"], o["lag"]) and close(coef, o["coef"])
 
 
+def _random_lengths(seed, count, lo, hi):
+    """Seeded mix of arbitrary integers, 2/3/5-smooth numbers and their +-1 neighbours in [lo, hi]."""
+    rng = np.random.default_rng(seed)
+    smooth = sorted({2 ** a * 3 ** b * 5 ** c for a in range(22) for b in range(14) for c in range(10)
+                     if lo <= 2 ** a * 3 ** b * 5 ** c <= hi})
+    out = set()
+    while len(out) < count:
+        k = len(out) % 4
+        if k == 0:
+            out.add(int(rng.integers(lo, hi + 1)))
+        elif k == 1:
+            out.add(int(np.exp(rng.uniform(np.log(lo), np.log(hi)))))
+        elif k == 2:
+            out.add(smooth[int(rng.integers(len(smooth)))])
+        else:
+            out.add(min(hi, max(lo, smooth[int(rng.integers(len(smooth)))] + int(rng.choice([-1, 1])))))
+    return sorted(out)
+
+
+def test_any_length_random_sweep(ac, ctx, capi):
+    """Sixty seeded random sample_len values between 4,096 and 2.5 million frames -- arbitrary integers,
+    2/3/5-smooth numbers, smooth +- 1 -- through whatever plan the library picks: the injected lag of
+    every pair, and on the first pair of each length raw index / peak / coefficient against the NumPy
+    (pocketfft) oracle.  The reference plans FFTW per call for any length
+    (src/cross_correlation.c:34, :141-142, :237)."""
+    from oracle import xcorr_numpy
+    kinds = set()
+    for L in _random_lengths(0xC33, 60, 4096, 2500000):
+        n = 3 if L < 500000 else 2
+        res, d_src, d_smp = _batch_on_device(ac, ctx, SEED + 90, 0, n, L)
+        desc = ctx.describe_plan(L)
+        kinds.add(desc.split()[0] + (" embedded" if "embedded" in desc else ""))
+        for i in range(n):
+            assert int(res["ret"][i]) == 0 and int(res["lag"][i]) == capi.synth_true_lag(SEED + 90, i, L), (L, i, desc)
+        src, smp = capi.synth_pair(SEED + 90, 0, L)
+        o = xcorr_numpy.cross_correlation(src, smp)
+        r = res[0]
+        assert o["margin"] > 1e-4
+        assert int(r["raw_index"]) == o["raw_index"] and int(r["lag"]) == o["lag"], (L, desc)
+        assert close(float(r["coef"]), o["coef"]) and close(float(r["peak"]), o["peak"]), (L, desc)
+        assert abs(float(r["margin"]) - o["margin"]) <= 1e-4, (L, desc)
+        del d_src, d_smp
+    assert any("embedded" in k for k in kinds) and len(kinds) >= 2, kinds
+
+
 def test_generic_plans_of_different_sizes_in_one_context(ac, ctx, capi):
     """A large plan, a small one, the large one again, all on the same kernels of one context: the
     shared-memory limit of a kernel must not shrink with the last plan built."""
