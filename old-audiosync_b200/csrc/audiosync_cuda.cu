@@ -491,7 +491,10 @@ static CopyPool& copy_pool() {
 // Below this many copy threads the conversion cannot outrun the link it is meant to relieve
 // (8 GPUs on a 32-vCPU host, 3 threads per process: 4.96 k pairs/s narrowing page-locked doubles
 // vs 5.37 k sending them as they are; pageable inputs need the threads anyway and gain at any count).
-constexpr size_t NARROW_MIN_THREADS = 8;
+static size_t narrow_min_threads() {
+    static const size_t n = [] { const char* e = getenv("AUDIOSYNC_CUDA_NARROW_MIN_THREADS"); return (size_t)(e ? std::max(1, atoi(e)) : 8); }();
+    return n;
+}
 
 // Host -> device copy of `bytes` on `st` from ANY host memory.  Page-locked (cudaMallocHost /
 // cudaHostRegister'ed, e.g. this library's fftw_alloc_real) and managed sources go straight to
@@ -607,7 +610,7 @@ static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* s
     const size_t src_bytes = src_n * esz, smp_bytes = smp_n * esz;
     const bool pageable = host_pointer_is_pageable(sources) || host_pointer_is_pageable(samples);
     int mode = (dtype == AUDIOSYNC_CUDA_F64 && !ctx->precise) ? ctx->narrow_host : AUDIOSYNC_CUDA_NARROW_OFF;
-    if (mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS && !pageable && (!solo || copy_pool().threads() < NARROW_MIN_THREADS))
+    if (mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS && !pageable && (!solo || copy_pool().threads() < narrow_min_threads()))
         mode = AUDIOSYNC_CUDA_NARROW_OFF;
     static const int feed_depth = [] { const char* e = getenv("AUDIOSYNC_CUDA_FEED_DEPTH");
                                        return e ? std::max(1, std::min(atoi(e), DeviceState::DIRECT_DEPTH)) : 2; }();
