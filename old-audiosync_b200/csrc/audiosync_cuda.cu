@@ -136,17 +136,24 @@ static int build_generic_plan_t(FftPlan* plan) {
         upload(plan->g_wpos, tb.wpos) != 0 || upload(plan->g_f2p_row, tb.f2p_row) != 0)
         return -1;
     const bool small_col = sh.nt_col == GEN_THREADS_SMALL, small_row = sh.nt_row == GEN_THREADS_SMALL;
+    // rows on a static row kernel where the plan's M2 has one (fp32 only): its output carries the
+    // factor 1/2 of the merge step that the runtime-radix row kernel leaves to peak_scale
+    static const bool no_static_rows = getenv("AUDIOSYNC_CUDA_NO_STATIC_ROWS") != nullptr;      // diagnostics / A-B runs
+    const bool static_rows = sizeof(T) == 4 && sh.static_rows != 0 && !no_static_rows;
+    if (static_rows) plan->peak_scale *= 2.0;
     if ((small_col ? GenStage<T, GEN_THREADS_SMALL>::prepare_cols(sh) : GenStage<T, GEN_THREADS>::prepare_cols(sh)) != 0 ||
-        (small_row ? GenStage<T, GEN_THREADS_SMALL>::prepare_rows(sh) : GenStage<T, GEN_THREADS>::prepare_rows(sh)) != 0)
+        (static_rows ? static_rows_prepare(plan)
+                     : small_row ? GenStage<T, GEN_THREADS_SMALL>::prepare_rows(sh) : GenStage<T, GEN_THREADS>::prepare_rows(sh)) != 0)
         return -1;
-    plan->run_wave = [plan, small_col, small_row](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
+    plan->run_wave = [plan, small_col, small_row, static_rows](audiosync_cuda_ctx* ctx, DeviceState& d, const void* src, const void* smp,
                                                   int dtype, long long sp, long long mp, void* ws, PairPeak* peaks, int pairs,
                                                   cudaStream_t st) {
         using Big = GenStage<T, GEN_THREADS>;
         using Small = GenStage<T, GEN_THREADS_SMALL>;
         if ((small_col ? Small::col_fwd(plan, ctx, d, src, smp, dtype, sp, mp, ws, peaks, pairs, st)
                        : Big::col_fwd(plan, ctx, d, src, smp, dtype, sp, mp, ws, peaks, pairs, st)) != 0) return -1;
-        if ((small_row ? Small::rows(plan, ctx, d, ws, pairs, st) : Big::rows(plan, ctx, d, ws, pairs, st)) != 0) return -1;
+        if ((static_rows ? static_rows_launch(plan, ctx, d, ws, pairs, st)
+                         : small_row ? Small::rows(plan, ctx, d, ws, pairs, st) : Big::rows(plan, ctx, d, ws, pairs, st)) != 0) return -1;
         return small_col ? Small::col_inv(plan, ctx, d, ws, peaks, pairs, st) : Big::col_inv(plan, ctx, d, ws, peaks, pairs, st);
     };
     return 0;

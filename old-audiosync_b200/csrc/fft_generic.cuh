@@ -87,6 +87,7 @@ struct GenShape {
     int ct;             // columns per tile of the column kernels (fp32: 16 or 8, fp64: 8)
     int nt_col, nt_row; // threads per CTA of the column / row kernels (GEN_THREADS or GEN_THREADS_SMALL)
     int row_pad;        // rows of the row kernel padded by one point per 128 bytes (1) or plain (0)
+    int static_rows;    // fp32 plans: M2 has a static row kernel (gen_plan.h: gen_static_rows); the library runs the rows there
     GenAxis col, row;
 };
 

@@ -645,7 +645,8 @@ ASC_HD void split_mul_merge_w2(cplx a, cplx b, cplx c, cplx d, cplx w2, cplx& qk
 template <class RL, int M1_, int NT>
 struct RowFusedKernel {
     static constexpr int M2 = RL::n;
-    static constexpr int M1 = M1_;
+    static constexpr int M1 = M1_;  // 0: the number of rows is a launch parameter (Params::m1) -- the rows of a
+                                    // runtime-radix plan whose row length has a static kernel (gen_plan.h)
     static constexpr int P = RL::count;
     static constexpr int THREADS = NT;
     static constexpr int RP = M2;   // row pitch in shared memory
@@ -671,6 +672,7 @@ struct RowFusedKernel {
         const cplx* m_hi;
         long long L;
         const cplx* rtab;        // [M1][TABP]: per row k1 the final-pass tables (fft_plan.h: build_row_tab)
+        int m1 = 0;              // rows per plane when M1_ == 0
     };
     // Final-pass twiddle tables of one row k1: S0 entries 0.5 * W_M^(j*k1) (the factor 1/2 of the
     // merge step rides here, exactly), then R0 entries W_M^(k*S0*k1); padded to an even count so
@@ -689,9 +691,10 @@ struct RowFusedKernel {
         const int r = ex.bx();
         const long long pair = ex.bz();
         const long long M = p.L;
-        const bool two = (r != 0) && (2 * r != M1);
+        const int m1 = M1 > 0 ? M1 : p.m1;
+        const bool two = (r != 0) && (2 * r != m1);
         const int nrows = two ? 2 : 1;
-        const int k1a = r, k1b = M1 - r;   // k1b unused when !two
+        const int k1a = r, k1b = m1 - r;   // k1b unused when !two
         cplx* __restrict__ plane_s = p.planes + pair * 2 * M;
         cplx* __restrict__ plane_p = plane_s + M;
         // final-pass twiddle tables of the two rows, copied into the (then dead) sample rows

@@ -88,6 +88,14 @@ inline std::vector<int> gen_freq2pos(const GenAxis& ax) {
     return t;
 }
 
+// Row lengths for which a STATIC row kernel exists (RowFusedKernel<RL, 0, NT>: compile-time radices,
+// strides and twiddle steps -- about half the time of the runtime-radix row kernel, which spends
+// 45 % of its instructions on address and table arithmetic).  A runtime-radix plan whose M2 is one
+// of them runs its rows there (fp32 arithmetic only); the planner prefers such splits -- every
+// embedded length can choose one, and so can every length that is a multiple of 480.
+inline bool gen_static_rows(long long M2) { return M2 == 480 || M2 == 960 || M2 == 1200 || M2 == 2400; }
+constexpr double GEN_STATIC_ROWS_GAIN = 0.55;
+
 // Relative cost of a split (lower is better), 0 = unusable.  elem = bytes per complex point,
 // ct = columns per tile.
 inline double gen_split_cost(long long M, int M1, int elem, int ct) {
@@ -107,7 +115,9 @@ inline double gen_split_cost(long long M, int M1, int elem, int ct) {
     double col = 2.5 * pc.cost / util((double)M1 * ct / 10.0) * occupancy_penalty(tile);
     if (ct * elem < 128) col *= 1.3;            // half cache lines per tile row (measured: K_A +27 % at M1 = 250)
     if (M2 % ct != 0) col *= 1.25;              // ragged last tile, rows not line-aligned
-    const double row = 3.0 * pr.cost / util(4.0 * (double)M2 / 10.0) * occupancy_penalty(rows);
+    double row = 3.0 * pr.cost / util(4.0 * (double)M2 / 10.0) * occupancy_penalty(rows);
+    if (elem == 8 && gen_static_rows(M2))       // static row kernel: plain rows of exactly 4 * M2 points
+        row = 3.0 * pr.cost / util(4.0 * (double)M2 / 10.0) * occupancy_penalty((size_t)4 * M2 * elem) * GEN_STATIC_ROWS_GAIN;
     return col + row;
 }
 
@@ -210,6 +220,7 @@ inline bool gen_make_shape(long long L, bool is_double, GenShape* out) {
     const size_t tile_bytes = (size_t)sh.M1 * sh.ct * elem, rows_bytes = (size_t)4 * (sh.M2 + sh.M2 / 8 + 1) * elem;
     sh.nt_col = ((sh.M1 / max_radix(sh.col)) * sh.ct >= GEN_THREADS || tile_bytes > 18 * 1024) ? GEN_THREADS : GEN_THREADS_SMALL;
     sh.nt_row = ((sh.M2 / max_radix(sh.row)) * 2 >= GEN_THREADS || rows_bytes > 18 * 1024) ? GEN_THREADS : GEN_THREADS_SMALL;
+    sh.static_rows = (!is_double && gen_static_rows(sh.M2)) ? 1 : 0;
     *out = sh;
     return true;
 }
@@ -251,6 +262,7 @@ inline std::string gen_describe(const GenShape& sh, bool is_double) {
     d += " row=";
     for (int i = 0; i < sh.row.npass; i++) d += (i ? "x" : "") + std::to_string(sh.row.radix[i]);
     d += std::string(sh.row_pad ? " padded" : " plain") + " tile=" + std::to_string(sh.ct) + " threads=" + std::to_string(sh.nt_col) + "/" + std::to_string(sh.nt_row);
+    if (sh.static_rows && !is_double) d += " static-rows";
     d += sh.M == sh.L ? " generic four-step" : " generic four-step, embedded (N'=2M>=3L)";
     d += is_double ? " fp64" : " fp32";
     return d;

@@ -155,4 +155,9 @@ struct GenStage {
                        cudaStream_t st);
 };
 
+// static_rows.cu: the rows of a runtime-radix fp32 plan on a static row kernel (RowFusedKernel<RL, 0, NT>)
+// when the plan's M2 has one (GenShape::static_rows).  prepare: tables + kernel attributes.
+int static_rows_prepare(FftPlan* plan);
+int static_rows_launch(FftPlan* plan, audiosync_cuda_ctx* ctx, DeviceState& d, void* ws, int pairs, cudaStream_t st);
+
 }  // namespace asc

@@ -201,7 +201,9 @@ def test_hard_goldens_dropin_and_batch(ac, ctx, case):
 
 
 # ------------------------------------------------------------------ any length: runtime-radix plans
-GEN_LENGTHS = [4099, 8749, 10007, 24000, 98415, 100000, 250000, 1000000, 1048576, 1440002]
+GEN_LENGTHS = [4099, 8749, 10007, 24000, 48000, 98415, 100000, 192000, 250000, 1000000, 1048576, 1440002, 2400000]
+# rows on a static row kernel (M2 in 480 / 960 / 1200 / 2400: multiples of 480 and every embedded length that can choose one)
+STATIC_ROW_LENGTHS = {10007, 48000, 192000, 1440002, 2400000}
 
 
 @pytest.mark.parametrize("L", GEN_LENGTHS)
@@ -213,7 +215,8 @@ def test_generic_plan_any_length_vs_oracle(ac, ctx, capi, L):
     from oracle import xcorr_numpy
     desc = ctx.describe_plan(L)
     assert "generic four-step" in desc and "fp32" in desc, desc
-    n = 3
+    assert ("static-rows" in desc) == (L in STATIC_ROW_LENGTHS), desc
+    n = 3 if L < 2000000 else 2
     res, d_src, d_smp = _batch_on_device(ac, ctx, SEED + 50, 0, n, L)
     for i in range(n):
         src, smp = capi.synth_pair(SEED + 50, i, L)
