@@ -656,36 +656,43 @@ static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* s
             ASC_CUDA_OK(cudaStreamWaitEvent(d.copy_stream, d.ev_done[b], 0));
             if (mode != AUDIOSYNC_CUDA_NARROW_OFF) ASC_CUDA_OK(cudaStreamWaitEvent(d.narrow_stream, d.ev_done[b], 0));
         }
-        // pairs [0, lo) go up as they are (pair lo too, partly, when dir_off > 0); pairs [hi, n) narrowed
-        size_t lo = 0, hi = n, dir_off = 0;
+        // The chunk is fed in UNITS of g consecutive pairs (about 32 MB of doubles; one pair at the
+        // headline length, hundreds at short ones, so that the per-unit bookkeeping never shows):
+        // units [0, lo) go up as they are (unit lo too, partly, when dir_off > 0); units [hi, nu) narrowed.
         const size_t pair_bytes = src_bytes + smp_bytes;
+        const size_t g = std::max<size_t>(1, ((size_t)32 << 20) / pair_bytes);
+        const size_t nu = (n + g - 1) / g;
+        auto unit_pairs = [&](size_t u) { return std::min(g, n - u * g); };
+        size_t lo = 0, hi = nu, dir_off = 0;
         if (mode == AUDIOSYNC_CUDA_NARROW_OFF) {
             if (upload_from_host(d.in_src[b].p, hs, src_bytes * n, d.copy_stream, d.stage, pageable) != 0 ||
                 upload_from_host(d.in_smp[b].p, hm, smp_bytes * n, d.copy_stream, d.stage, pageable) != 0)
                 return -1;
-            lo = n;
+            lo = nu;
         }
-        // the next slice of pair lo, as doubles, straight from the caller's (page-locked) memory
+        // the next slice of unit lo, as doubles, straight from the caller's (page-locked) memory:
+        // first the unit's sources, then its samples (both contiguous)
         auto direct_slice = [&]() -> int {
             int k = 0;
             while (k < DeviceState::DIRECT_DEPTH - 1 && d.direct_pending[k]) k++;
             if (d.direct_pending[k]) ASC_CUDA_OK(cudaEventSynchronize(d.direct_ev[k]));
-            const bool in_src = dir_off < src_bytes;
-            const size_t o = in_src ? dir_off : dir_off - src_bytes;
-            const size_t m = std::min(DeviceState::DIRECT_SLICE, (in_src ? src_bytes : smp_bytes) - o);
-            char* dst = static_cast<char*>(in_src ? d.in_src[b].p : d.in_smp[b].p) + lo * (in_src ? src_bytes : smp_bytes) + o;
-            const char* src = (in_src ? hs : hm) + lo * (in_src ? src_bytes : smp_bytes) + o;
+            const size_t up = unit_pairs(lo), usrc = up * src_bytes, usmp = up * smp_bytes;
+            const bool in_src = dir_off < usrc;
+            const size_t o = in_src ? dir_off : dir_off - usrc;
+            const size_t m = std::min(DeviceState::DIRECT_SLICE, (in_src ? usrc : usmp) - o);
+            char* dst = static_cast<char*>(in_src ? d.in_src[b].p : d.in_smp[b].p) + lo * g * (in_src ? src_bytes : smp_bytes) + o;
+            const char* src = (in_src ? hs : hm) + lo * g * (in_src ? src_bytes : smp_bytes) + o;
             ASC_CUDA_OK(cudaMemcpyAsync(dst, src, m, cudaMemcpyHostToDevice, d.copy_stream));
             ASC_CUDA_OK(cudaEventRecord(d.direct_ev[k], d.copy_stream));
             d.direct_pending[k] = true;
             dir_off += m;
-            if (dir_off == pair_bytes) { lo++; dir_off = 0; }
+            if (dir_off == usrc + usmp) { lo++; dir_off = 0; }
             return 0;
         };
         // Direct slices only into link time the narrowed stream leaves idle: at most DIRECT_DEPTH
         // in flight, and only while the ring's uploads keep up with the conversion (the narrowed
         // form costs half the link bytes per pair, so it has the right of way; the copy threads,
-        // not the link, bound it).  Called between the pieces of the pair being narrowed.
+        // not the link, bound it).  Called over and over while a piece is being narrowed.
         int feed_rc = 0;
         auto feed_direct = [&]() {
             while (feed_rc == 0 && (dir_off > 0 || lo < hi) && direct_in_flight(d) < feed_depth &&
@@ -697,54 +704,57 @@ static int run_host_range(audiosync_cuda_ctx* ctx, DeviceState& d, const char* s
                 // narrowing was given up in this chunk: everything that is left goes up as doubles
                 while (dir_off > 0)
                     if (direct_slice() != 0) return -1;
-                if (lo < hi &&
-                    (upload_from_host(static_cast<char*>(d.in_src[b].p) + lo * src_bytes, hs + lo * src_bytes, src_bytes * (hi - lo),
-                                      d.copy_stream, d.stage, pageable) != 0 ||
-                     upload_from_host(static_cast<char*>(d.in_smp[b].p) + lo * smp_bytes, hm + lo * smp_bytes, smp_bytes * (hi - lo),
-                                      d.copy_stream, d.stage, pageable) != 0))
-                    return -1;
+                if (lo < hi) {
+                    const size_t p_lo = lo * g, p_hi = std::min(n, hi * g);
+                    if (upload_from_host(static_cast<char*>(d.in_src[b].p) + p_lo * src_bytes, hs + p_lo * src_bytes, src_bytes * (p_hi - p_lo),
+                                         d.copy_stream, d.stage, pageable) != 0 ||
+                        upload_from_host(static_cast<char*>(d.in_smp[b].p) + p_lo * smp_bytes, hm + p_lo * smp_bytes, smp_bytes * (p_hi - p_lo),
+                                         d.copy_stream, d.stage, pageable) != 0)
+                        return -1;
+                }
                 lo = hi;
                 break;
             }
             if (hybrid) feed_direct();
             if (feed_rc != 0) return -1;
             if (lo == hi) break;
-            if (hi - 1 == lo && dir_off > 0) {          // only the partly fed pair is left
+            if (hi - 1 == lo && dir_off > 0) {          // only the partly fed unit is left
                 while (dir_off > 0)
                     if (direct_slice() != 0) return -1;
                 break;
             }
-            // the next pair from the back, narrowed
-            const size_t j = --hi;
+            // the next unit from the back, narrowed
+            const size_t j = --hi, up = unit_pairs(j);
             bool exact = true;
             const bool stop = mode == AUDIOSYNC_CUDA_NARROW_LOSSLESS;
             std::function<void()> between;
             if (hybrid) between = feed_direct;
-            if (upload_narrowed(static_cast<float*>(d.in_src32[b].p) + j * src_n, reinterpret_cast<const double*>(hs) + j * src_n, src_n,
-                                d.narrow_stream, d.stage, &exact, stop, between) != 0)
+            if (upload_narrowed(static_cast<float*>(d.in_src32[b].p) + j * g * src_n, reinterpret_cast<const double*>(hs) + j * g * src_n,
+                                up * src_n, d.narrow_stream, d.stage, &exact, stop, between) != 0)
                 return -1;
             if ((exact || !stop) &&
-                upload_narrowed(static_cast<float*>(d.in_smp32[b].p) + j * smp_n, reinterpret_cast<const double*>(hm) + j * smp_n, smp_n,
-                                d.narrow_stream, d.stage, &exact, stop, between) != 0)
+                upload_narrowed(static_cast<float*>(d.in_smp32[b].p) + j * g * smp_n, reinterpret_cast<const double*>(hm) + j * g * smp_n,
+                                up * smp_n, d.narrow_stream, d.stage, &exact, stop, between) != 0)
                 return -1;
             if (feed_rc != 0) return -1;
-            if (!exact && stop) { hi = j + 1; mode = AUDIOSYNC_CUDA_NARROW_OFF; }   // this pair and all later ones go up as doubles
+            if (!exact && stop) { hi = j + 1; mode = AUDIOSYNC_CUDA_NARROW_OFF; }   // this unit and all later ones go up as doubles
         }
-        // pairs [0, lo): doubles (or the caller's fp32); pairs [hi, n): narrowed
-        if (lo > 0) {
+        // pairs [0, n_dbl): doubles (or the caller's fp32); pairs [p_nar, n): narrowed
+        const size_t n_dbl = std::min(n, lo * g), p_nar = std::min(n, hi * g);
+        if (n_dbl > 0) {
             ASC_CUDA_OK(cudaEventRecord(d.ev_up[b], d.copy_stream));
             ASC_CUDA_OK(cudaStreamWaitEvent(d.stream, d.ev_up[b], 0));
-            if (enqueue_batch(ctx, d, d.work, d.in_src[b].p, d.in_smp[b].p, lo, L, dtype, d_res + c0, d.stream) != 0) return -1;
+            if (enqueue_batch(ctx, d, d.work, d.in_src[b].p, d.in_smp[b].p, n_dbl, L, dtype, d_res + c0, d.stream) != 0) return -1;
         }
-        if (hi < n) {
+        if (p_nar < n) {
             ASC_CUDA_OK(cudaEventRecord(d.ev_up32[b], d.narrow_stream));
             ASC_CUDA_OK(cudaStreamWaitEvent(d.stream, d.ev_up32[b], 0));
-            if (enqueue_batch(ctx, d, d.work, static_cast<float*>(d.in_src32[b].p) + hi * src_n,
-                              static_cast<float*>(d.in_smp32[b].p) + hi * smp_n, n - hi, L, narrowed_dtype, d_res + c0 + hi, d.stream) != 0)
+            if (enqueue_batch(ctx, d, d.work, static_cast<float*>(d.in_src32[b].p) + p_nar * src_n,
+                              static_cast<float*>(d.in_smp32[b].p) + p_nar * smp_n, n - p_nar, L, narrowed_dtype, d_res + c0 + p_nar, d.stream) != 0)
                 return -1;
         }
         ASC_CUDA_OK(cudaEventRecord(d.ev_done[b], d.stream));
-        if (dtype == AUDIOSYNC_CUDA_F64) { ctx->fed_direct += lo; ctx->fed_narrowed += n - hi; }
+        if (dtype == AUDIOSYNC_CUDA_F64) { ctx->fed_direct += n_dbl; ctx->fed_narrowed += n - p_nar; }
     }
     ASC_CUDA_OK(cudaMemcpyAsync(d.h_results.p, d_res, sizeof(audiosync_cuda_result) * total,
                                 cudaMemcpyDeviceToHost, d.stream));

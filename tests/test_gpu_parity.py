@@ -773,10 +773,11 @@ def test_lossless_host_narrowing_is_bit_identical(ac, capi, L, n):
             got_pinned = c.xcorr_batch_records(sb.ptr, mb.ptr, n, L, ac.F64, ac.HOST)
         as_doubles, narrowed = c.host_feed_stats(reset=True)
         assert as_doubles + narrowed == n
-        if ac.copy_threads() >= 8:
+        units = -(-n // max(1, (32 << 20) // (3 * L * 8)))             # the chunk is fed in units of ~32 MB of doubles
+        if ac.copy_threads() >= 8 and units >= 2:
             assert narrowed > 0                                                                    # fed both ways
         else:
-            assert narrowed == 0                                                                   # too few threads: copy engine only
+            assert narrowed == 0                                                                   # one unit / too few threads: copy engine only
     _records_equal(ac, got, ref)
     _records_equal(ac, got_pinned, ref)
     for i in range(0, n, max(1, n // 5)):
